@@ -1,0 +1,133 @@
+// Internal declarations of libbcs (sm_100a).  Nothing here crosses the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "bcs.h"
+
+namespace bcs {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: C ABI functions return codes, never exit (the reference printf+exit()s,
+// utilities/cuda_handle_error.cuh:18-25)
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+struct Error {
+    int code;
+    std::string msg;
+};
+#define BCS_CUDA(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess)                                                                                  \
+            throw ::bcs::Error{BCS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                                 ":" + std::to_string(__LINE__) + ")"};                        \
+    } while (0)
+#define BCS_REQUIRE(cond, code, msg)                       \
+    do {                                                   \
+        if (!(cond)) throw ::bcs::Error{(code), (msg)};    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-side parameter blocks (passed by value to kernels / kept in __constant__-like structs)
+// ---------------------------------------------------------------------------------------------
+struct TypeDev {            // one blood-cell type in final (meta-factory) order
+    int count;
+    int P;                  // particles per cell
+    int pStart;             // particleStarts
+    int cStart;             // bloodCellTypesStarts
+    int mStart;             // bloodCellModelStarts
+    int warpSync;           // reference would use handleVeinEndsWarpSync (no ending-sphere test)
+    int adjStart;           // offset of this type's adjacency (ELL) in adjJ/adjL
+    int maxDeg;             // ELL width
+};
+
+struct TypesDev {
+    int n;
+    TypeDev t[BCS_MAX_TYPES];
+};
+
+struct GridDev {
+    float minx, miny, minz;     // grid origin (minX,minY,minZ)
+    float lenx, leny, lenz;     // width,height,depth (the clamp bound of calculateIdForCell)
+    float maxx, maxy, maxz;
+    int csx, csy, csz;          // cell size (ints, converted to float at use like the reference)
+    int nx, ny, nz;             // cell counts
+    int cells;
+    int n;                      // objects
+    int keyBits;                // bits needed for a cell id
+};
+
+struct PhysDev {
+    float dt;
+    float velocity_collision_damping;
+    float particle_k_sniff, vein_k_sniff, particle_d_fact, vein_d_fact;
+    float vein_collision_force_intensity;
+    float viscous_damping;
+    float coll_spring, coll_damping, coll_shear;
+    float max_cell_size_factor, big_brake_intensity;
+    float initvx, initvy, initvz;
+    float impact2;              // veinImpactDistance^2 (float product)
+    float impactNear;           // veinImpactDistance + margin, used only to cull
+    float minForce2;            // veinImpactMinimalForceDistance^2
+    float gx, gy, gz;
+    float min_spawn_y, cylinder_radius;
+    // vein-end thresholds, vein_end.cu:12-18
+    float upperY, lowerY, rightX, leftX, frontZ, backZ;
+    int useBloodFlow, reactionForce, bigBrake;
+    int nEndings;
+};
+
+struct Counters {               // device-resident, see bcs_stats
+    unsigned long long pairTests, pairHits, triTests, veinHits, teleported, oob;
+    unsigned long long step;    // completed steps (drives the respawn RNG counter)
+};
+
+// packed triangle in sorted-slot order, refreshed every step from the moving vein vertices
+struct TriPacked {
+    float4 a;   // v0.xyz, e1.x
+    float4 b;   // e1.yz, e2.xy
+    float4 c;   // e2.z, triangle id (int bits), unused, unused
+};
+
+struct Aabb {
+    float lox, loy, loz, hix, hiy, hiz;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host-side derived scene (meta_factory + generateBoundingSpheres equivalents), scene_host.cpp
+// ---------------------------------------------------------------------------------------------
+struct HostType {
+    int count, P, pStart, cStart, mStart, gStart, srcDef, warpSync;
+    float smallestRadius;
+};
+
+struct HostScene {
+    std::vector<HostType> types;
+    int N = 0, B = 0, nModel = 0, nGraph = 0, V = 0, T = 0;
+    std::vector<float> graph;               // dense spring lengths
+    std::vector<float> mx, my, mz;          // model vertices in final order
+    std::vector<float> collR, initR;        // collision radius, distance from model centroid
+    std::vector<int32_t> adjJ;              // ELL adjacency per type: [adjStart + d*P + i] = mate index j (or -1)
+    std::vector<float> adjL;                // spring length
+    std::vector<int> adjStart, maxDeg;
+    float gmin[3], gmax[3], gsize[3];
+    std::vector<float> vx, vy, vz;
+    std::vector<uint32_t> vidx;
+    std::vector<int32_t> nbrIds;            // [slot][vertex]
+    std::vector<float> nbrLen;
+    std::vector<float> tcx, tcy, tcz;       // triangle centres (initial)
+    std::vector<float> endC, endR;
+    int cellSize[3], triCellSize[3];
+    int gdims[3], tdims[3];
+    bcs_physics ph;
+    int useBloodFlow, reactionForce, bigBrake, bsCoeff;
+};
+
+void derive_scene(const bcs_scene& in, HostScene& out);   // throws bcs::Error
+
+}  // namespace bcs

@@ -1,0 +1,729 @@
+// C ABI of libbcs (include/bcs.h): handle lifetime, state transfer, stage sequencing, CUDA-graph replay.
+//
+// Stage order of one step (main.cu:175-208 + simulation_controller.cu:246-331):
+//   grid(particles) [grid(triangles) is static] -> vein springs -> cell springs -> particle collisions ->
+//   vein collisions -> integrate particles -> integrate vein (+clear forces) -> vein end
+// The reference separates the stages with 11 device-wide cudaDeviceSynchronize calls and launches each
+// particle stage once per blood-cell type; here everything is ordered on one stream, one launch per stage
+// covers all types, and bcs_step replays the whole step as a captured CUDA graph.
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "bcs_internal.cuh"
+#include "device_math.cuh"
+#include "kernels.cuh"
+
+namespace bcs {
+
+static thread_local std::string g_lastError;
+void set_error(const std::string& msg) { g_lastError = msg; }
+
+template <class T>
+static T* dev_alloc(size_t count, bool zero = true)
+{
+    T* p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) throw Error{BCS_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
+    if (zero) BCS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    return p;
+}
+template <class T>
+static T* dev_upload(const std::vector<T>& v)
+{
+    T* p = dev_alloc<T>(v.size(), false);
+    if (!v.empty()) BCS_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+// ---- SoA <-> float4 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                                   float4* __restrict__ out, int n, const TypesDev types, const float* __restrict__ collR,
+                                                   int setRadius)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float w = 0.f;
+    if (setRadius) {
+        // pos4.w = the particle's own collision radius (bounding sphere of its model vertex)
+        int t = 0;
+        while (t + 1 < types.n && i >= types.t[t + 1].pStart) ++t;
+        w = collR[types.t[t].mStart + (i - types.t[t].pStart) % types.t[t].P];
+    }
+    out[i] = make_float4(x[i], y[i], z[i], w);
+}
+__global__ void __launch_bounds__(256) unpack_kernel(const float4* __restrict__ in, float* __restrict__ x, float* __restrict__ y,
+                                                     float* __restrict__ z, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = in[i];
+    x[i] = v.x; y[i] = v.y; z[i] = v.z;
+}
+__global__ void fill_int_kernel(int* p, int v, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+// sparse view of a dense cell table, ascending cell order (single block per chunk keeps it simple: debug path)
+__global__ void mark_cells_kernel(const int* __restrict__ cs, const int* __restrict__ ce, int cells, int reference, int* __restrict__ flags)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int s = cs[c], e = ce[c];
+    flags[c] = reference ? (s != 0 || e != 0) : (e >= s);
+}
+
+}  // namespace bcs
+
+using namespace bcs;
+
+struct bcs_sim {
+    HostScene hs;
+    int device = 0;
+    int semantics = BCS_SEM_CLEAN;
+    bool useGraph = true, stats = false, ownStream = false;
+    unsigned long long seed = 0;
+    cudaStream_t stream = nullptr;
+    // particles
+    float4 *pos = nullptr, *vel = nullptr, *frc = nullptr, *spos = nullptr, *svel = nullptr, *centers = nullptr;
+    int *keys[2] = {nullptr, nullptr}, *ids[2] = {nullptr, nullptr}, *cellStart = nullptr, *cellEnd = nullptr;
+    // vein
+    float4 *vpos = nullptr, *vvel = nullptr, *vfrc = nullptr, *tcent = nullptr;
+    int *tkeys[2] = {nullptr, nullptr}, *tids[2] = {nullptr, nullptr}, *tcellStart = nullptr, *tcellEnd = nullptr;
+    TriPacked* tris = nullptr;
+    unsigned* vidx = nullptr;
+    int* nbrIds = nullptr;
+    float* nbrLen = nullptr;
+    // tables
+    float *collR = nullptr, *initR = nullptr, *mx = nullptr, *my = nullptr, *mz = nullptr, *endC = nullptr, *endR = nullptr;
+    int* adjJ = nullptr;
+    float* adjL = nullptr;
+    Counters* counters = nullptr;
+    float* staging = nullptr;   // 3 * maxLen floats
+    int stagingLen = 0;
+    SortScratch sortP, sortT;
+    TypesDev types{};
+    GridDev pg{}, tg{};
+    PhysDev phys{};
+    SpringPlan plan{};
+    bool gridBuilt = false;
+    cudaGraphExec_t graphExec = nullptr;
+    std::vector<void*> owned;
+
+    template <class T> T* track(T* p) { owned.push_back((void*)p); return p; }
+};
+
+namespace {
+
+int bits_for(int cells)
+{
+    int b = 1;
+    while ((1ll << b) < cells) ++b;
+    return b;
+}
+
+GridDev make_grid(const HostScene& hs, const int cs[3], const int dims[3], int n)
+{
+    GridDev g{};
+    g.minx = hs.gmin[0]; g.miny = hs.gmin[1]; g.minz = hs.gmin[2];
+    g.maxx = hs.gmax[0]; g.maxy = hs.gmax[1]; g.maxz = hs.gmax[2];
+    g.lenx = hs.gsize[0]; g.leny = hs.gsize[1]; g.lenz = hs.gsize[2];
+    g.csx = cs[0]; g.csy = cs[1]; g.csz = cs[2];
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    g.cells = dims[0] * dims[1] * dims[2];
+    g.n = n;
+    g.keyBits = bits_for(g.cells);
+    return g;
+}
+
+void fill_phys(const HostScene& hs, PhysDev& p)
+{
+    const bcs_physics& s = hs.ph;
+    p.dt = s.dt;
+    p.velocity_collision_damping = s.velocity_collision_damping;
+    p.particle_k_sniff = s.particle_k_sniff; p.vein_k_sniff = s.vein_k_sniff;
+    p.particle_d_fact = s.particle_d_fact; p.vein_d_fact = s.vein_d_fact;
+    p.vein_collision_force_intensity = s.vein_collision_force_intensity;
+    p.viscous_damping = s.viscous_damping;
+    p.coll_spring = s.collision_spring_coeff; p.coll_damping = s.collision_damping_coeff; p.coll_shear = s.collision_shear_coeff;
+    p.max_cell_size_factor = s.max_cell_size_factor_before_brake; p.big_brake_intensity = s.big_particle_braking_intensity;
+    p.initvx = s.init_velocity[0]; p.initvy = s.init_velocity[1]; p.initvz = s.init_velocity[2];
+    p.impact2 = s.vein_impact_distance * s.vein_impact_distance;
+    p.impactNear = s.vein_impact_distance * 1.001f + 0.01f;
+    p.minForce2 = s.vein_impact_minimal_force_distance * s.vein_impact_minimal_force_distance;
+    p.gx = s.gravity[0]; p.gy = s.gravity[1]; p.gz = s.gravity[2];
+    p.min_spawn_y = s.min_spawn_y; p.cylinder_radius = s.cylinder_radius;
+    // vein_end.cu:12-18
+    p.upperY = hs.gmax[1] - 3 * s.grid_y_margin / 4;
+    p.lowerY = hs.gmin[1] + s.grid_y_margin / 2;
+    p.rightX = hs.gmax[0] - s.grid_xz_margin / 2;
+    p.leftX = hs.gmin[0] + s.grid_xz_margin / 2;
+    p.frontZ = hs.gmax[2] - s.grid_xz_margin / 2;
+    p.backZ = hs.gmin[2] + s.grid_xz_margin / 2;
+    p.useBloodFlow = hs.useBloodFlow; p.reactionForce = hs.reactionForce; p.bigBrake = hs.bigBrake;
+    p.nEndings = (int)hs.endR.size();
+}
+
+// ---- stage launchers ------------------------------------------------------------------------------------
+GridBuildArgs particle_grid_args(bcs_sim* s)
+{
+    GridBuildArgs a{};
+    a.grid = s->pg; a.objPos = s->pos;
+    a.keys[0] = s->keys[0]; a.keys[1] = s->keys[1]; a.ids[0] = s->ids[0]; a.ids[1] = s->ids[1];
+    a.cellStart = s->cellStart; a.cellEnd = s->cellEnd;
+    a.scratch = &s->sortP; a.counters = s->counters;
+    a.reference = s->semantics == BCS_SEM_REFERENCE;
+    a.tablesValid = true;
+    a.reorder = true;
+    a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
+    return a;
+}
+
+void build_triangle_grid(bcs_sim* s)
+{
+    GridBuildArgs a{};
+    a.grid = s->tg; a.objPos = s->tcent;
+    a.keys[0] = s->tkeys[0]; a.keys[1] = s->tkeys[1]; a.ids[0] = s->tids[0]; a.ids[1] = s->tids[1];
+    a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
+    a.scratch = &s->sortT; a.counters = s->counters;
+    a.reference = s->semantics == BCS_SEM_REFERENCE;
+    a.tablesValid = true;
+    a.reorder = false;
+    launch_grid_build(a, s->stream);
+}
+
+VeinArgs vein_args(bcs_sim* s)
+{
+    VeinArgs a{};
+    a.V = s->hs.V; a.T = s->hs.T; a.phys = s->phys;
+    a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc;
+    a.nbrIds = s->nbrIds; a.nbrLen = s->nbrLen; a.vidx = s->vidx;
+    return a;
+}
+
+VeinCollideArgs vein_collide_args(bcs_sim* s)
+{
+    VeinCollideArgs a{};
+    a.tgrid = s->tg; a.types = s->types; a.phys = s->phys;
+    a.n = s->hs.N; a.T = s->hs.T;
+    a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
+    a.vpos = s->vpos; a.vfrc = s->vfrc; a.vidx = s->vidx;
+    a.triIds = s->tids[1]; a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
+    a.tris = s->tris; a.collR = s->collR; a.counters = s->counters;
+    a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
+    return a;
+}
+
+CollideArgs collide_args(bcs_sim* s)
+{
+    CollideArgs a{};
+    a.grid = s->pg; a.types = s->types; a.phys = s->phys; a.n = s->hs.N;
+    a.keys = s->keys[1]; a.spos = s->spos; a.svel = s->svel;
+    a.cellStart = s->cellStart; a.cellEnd = s->cellEnd; a.collR = s->collR;
+    a.frc = s->frc; a.counters = s->counters;
+    a.reference = s->semantics == BCS_SEM_REFERENCE; a.stats = s->stats;
+    a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
+    return a;
+}
+
+IntegrateArgs integrate_args(bcs_sim* s)
+{
+    IntegrateArgs a{};
+    a.types = s->types; a.phys = s->phys; a.n = s->hs.N; a.nCells = s->hs.B;
+    a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
+    a.mx = s->mx; a.my = s->my; a.mz = s->mz; a.endC = s->endC; a.endR = s->endR;
+    a.counters = s->counters; a.seed = s->seed;
+    return a;
+}
+
+void stage(bcs_sim* s, int st)
+{
+    switch (st) {
+    case BCS_STAGE_GRID_PARTICLES:
+        launch_grid_build(particle_grid_args(s), s->stream);
+        s->gridBuilt = true;
+        break;
+    case BCS_STAGE_GRID_TRIANGLES:
+        break;   // static: built at creation from the initial centres
+    case BCS_STAGE_VEIN_GATHER: launch_vein_gather(vein_args(s), s->stream); break;
+    case BCS_STAGE_SPRINGS: {
+        SpringArgs a{};
+        a.types = s->types; a.plan = s->plan; a.phys = s->phys;
+        a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
+        a.adjJ = s->adjJ; a.adjL = s->adjL; a.initR = s->initR;
+        launch_springs(a, s->stream);
+        break;
+    }
+    case BCS_STAGE_PARTICLE_COLLISIONS:
+        BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle collisions need a built grid (bcs_build_grid)");
+        launch_particle_collisions(collide_args(s), s->stream);
+        break;
+    case BCS_STAGE_VEIN_COLLISIONS: {
+        VeinCollideArgs a = vein_collide_args(s);
+        launch_tri_refit(a, s->stream);
+        launch_vein_collisions(a, s->stream);
+        break;
+    }
+    case BCS_STAGE_INTEGRATE_PARTICLES: launch_integrate_particles(integrate_args(s), s->stream); break;
+    case BCS_STAGE_INTEGRATE_VEIN: launch_vein_integrate(vein_args(s), s->stream); break;
+    case BCS_STAGE_VEIN_END: launch_vein_end(integrate_args(s), s->stream); break;
+    default: throw Error{BCS_ERR_INVALID, "unknown stage"};
+    }
+}
+
+void enqueue_step(bcs_sim* s)
+{
+    for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_END; ++st) stage(s, st);
+}
+
+struct Array {
+    float4* ptr;
+    int n;
+    bool isParticlePos;
+};
+Array array_of(bcs_sim* s, int which)
+{
+    switch (which) {
+    case BCS_PARTICLE_POS: return {s->pos, s->hs.N, true};
+    case BCS_PARTICLE_VEL: return {s->vel, s->hs.N, false};
+    case BCS_PARTICLE_FRC: return {s->frc, s->hs.N, false};
+    case BCS_VEIN_POS: return {s->vpos, s->hs.V, false};
+    case BCS_VEIN_VEL: return {s->vvel, s->hs.V, false};
+    case BCS_VEIN_FRC: return {s->vfrc, s->hs.V, false};
+    case BCS_CELL_CENTERS: return {s->centers, s->hs.B, false};
+    }
+    throw Error{BCS_ERR_INVALID, "unknown array id"};
+}
+
+void destroy(bcs_sim* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
+    for (void* p : s->owned) cudaFree(p);
+    s->sortP.release();
+    s->sortT.release();
+    if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+}  // namespace
+
+#define BCS_API_BEGIN try {
+#define BCS_API_END                                   \
+    return BCS_OK;                                    \
+    }                                                 \
+    catch (const bcs::Error& e) {                     \
+        bcs::set_error(e.msg);                        \
+        return e.code;                                \
+    }                                                 \
+    catch (const std::exception& e) {                 \
+        bcs::set_error(e.what());                     \
+        return BCS_ERR_INVALID;                       \
+    }
+
+extern "C" {
+
+const char* bcs_last_error(void) { return g_lastError.c_str(); }
+int bcs_abi_version(void) { return BCS_ABI_VERSION; }
+
+int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
+{
+    bcs_sim* s = nullptr;
+    try {
+        BCS_REQUIRE(scene && out, BCS_ERR_INVALID, "null argument");
+        BCS_REQUIRE(!opts || opts->struct_size == sizeof(bcs_opts), BCS_ERR_INVALID, "bcs_opts.struct_size mismatch");
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0)
+            throw Error{BCS_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); libbcs has no CPU fallback"};
+        s = new bcs_sim();
+        s->device = opts ? opts->device : 0;
+        BCS_REQUIRE(s->device >= 0 && s->device < ndev, BCS_ERR_INVALID, "device ordinal out of range");
+        BCS_CUDA(cudaSetDevice(s->device));
+        s->semantics = opts ? opts->semantics : BCS_SEM_CLEAN;
+        BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN || s->semantics == BCS_SEM_REFERENCE, BCS_ERR_INVALID, "unknown semantics");
+        s->useGraph = opts ? opts->use_graph != 0 : true;
+        s->stats = opts ? opts->collect_stats != 0 : false;
+        s->seed = opts ? opts->seed : 0;
+        if (opts && opts->stream) s->stream = (cudaStream_t)opts->stream;
+        else { BCS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->ownStream = true; }
+
+        derive_scene(*scene, s->hs);
+        const HostScene& hs = s->hs;
+        const int N = hs.N, B = hs.B, V = hs.V, T = hs.T;
+
+        s->types.n = (int)hs.types.size();
+        for (int i = 0; i < s->types.n; ++i) {
+            const HostType& h = hs.types[i];
+            s->types.t[i] = TypeDev{h.count, h.P, h.pStart, h.cStart, h.mStart, h.warpSync, hs.adjStart[i], hs.maxDeg[i]};
+        }
+        s->plan = make_spring_plan(s->types);
+        s->pg = make_grid(hs, hs.cellSize, hs.gdims, N);
+        s->tg = make_grid(hs, hs.triCellSize, hs.tdims, T);
+        fill_phys(hs, s->phys);
+
+        s->pos = s->track(dev_alloc<float4>(N)); s->vel = s->track(dev_alloc<float4>(N)); s->frc = s->track(dev_alloc<float4>(N));
+        s->spos = s->track(dev_alloc<float4>(N)); s->svel = s->track(dev_alloc<float4>(N));
+        s->centers = s->track(dev_alloc<float4>(B));
+        for (int k = 0; k < 2; ++k) {
+            s->keys[k] = s->track(dev_alloc<int>(N)); s->ids[k] = s->track(dev_alloc<int>(N));
+            s->tkeys[k] = s->track(dev_alloc<int>(T)); s->tids[k] = s->track(dev_alloc<int>(T));
+        }
+        s->cellStart = s->track(dev_alloc<int>(s->pg.cells)); s->cellEnd = s->track(dev_alloc<int>(s->pg.cells));
+        s->tcellStart = s->track(dev_alloc<int>(s->tg.cells)); s->tcellEnd = s->track(dev_alloc<int>(s->tg.cells));
+        if (s->semantics == BCS_SEM_CLEAN) {
+            // empty cell = (start 0, end -1); reference semantics keep the zero fill = (0,0)
+            BCS_CUDA(cudaMemset(s->cellEnd, 0xFF, (size_t)s->pg.cells * sizeof(int)));
+            BCS_CUDA(cudaMemset(s->tcellEnd, 0xFF, (size_t)s->tg.cells * sizeof(int)));
+        }
+        s->vpos = s->track(dev_alloc<float4>(V)); s->vvel = s->track(dev_alloc<float4>(V)); s->vfrc = s->track(dev_alloc<float4>(V));
+        s->tcent = s->track(dev_alloc<float4>(T));
+        s->tris = s->track(dev_alloc<TriPacked>(T));
+        s->vidx = s->track(dev_upload(hs.vidx));
+        s->nbrIds = s->track(dev_upload(hs.nbrIds)); s->nbrLen = s->track(dev_upload(hs.nbrLen));
+        s->collR = s->track(dev_upload(hs.collR)); s->initR = s->track(dev_upload(hs.initR));
+        s->mx = s->track(dev_upload(hs.mx)); s->my = s->track(dev_upload(hs.my)); s->mz = s->track(dev_upload(hs.mz));
+        s->endC = s->track(dev_upload(hs.endC)); s->endR = s->track(dev_upload(hs.endR));
+        s->adjJ = s->track(dev_upload(hs.adjJ)); s->adjL = s->track(dev_upload(hs.adjL));
+        s->counters = s->track(dev_alloc<Counters>(1));
+        s->stagingLen = std::max(std::max(N, V), std::max(B, T));
+        s->staging = s->track(dev_alloc<float>(3 * (size_t)s->stagingLen));
+        s->sortP.allocate(N);
+        s->sortT.allocate(T);
+
+        // vein vertices -> device, triangle centres (calculateCentersKernel, run once), static triangle grid
+        {
+            float* sx = s->staging; float* sy = sx + s->stagingLen; float* sz = sy + s->stagingLen;
+            BCS_CUDA(cudaMemcpy(sx, hs.vx.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+            BCS_CUDA(cudaMemcpy(sy, hs.vy.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+            BCS_CUDA(cudaMemcpy(sz, hs.vz.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+            pack_kernel<<<(V + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, s->vpos, V, s->types, s->collR, 0);
+            launch_tri_centers(vein_args(s), s->tcent, s->stream);
+            build_triangle_grid(s);
+            BCS_CUDA(cudaStreamSynchronize(s->stream));
+        }
+        *out = s;
+        return BCS_OK;
+    } catch (const bcs::Error& e) {
+        bcs::set_error(e.msg);
+        destroy(s);
+        return e.code;
+    } catch (const std::exception& e) {
+        bcs::set_error(e.what());
+        destroy(s);
+        return BCS_ERR_INVALID;
+    }
+}
+
+void bcs_destroy(bcs_sim* s) { destroy(s); }
+
+int bcs_get_layout(const bcs_sim* s, bcs_layout* o)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && o, BCS_ERR_INVALID, "null argument");
+    std::memset(o, 0, sizeof *o);
+    const HostScene& hs = s->hs;
+    o->n_types = (int)hs.types.size();
+    o->n_particles = hs.N; o->n_cells = hs.B; o->n_model = hs.nModel; o->n_graph = hs.nGraph;
+    o->n_vertices = hs.V; o->n_triangles = hs.T;
+    for (int d = 0; d < 3; ++d) {
+        o->grid_dims[d] = hs.gdims[d]; o->tri_grid_dims[d] = hs.tdims[d];
+        o->grid_min[d] = hs.gmin[d]; o->grid_max[d] = hs.gmax[d]; o->grid_size[d] = hs.gsize[d];
+    }
+    o->grid_cells = s->pg.cells; o->tri_grid_cells = s->tg.cells;
+    for (size_t i = 0; i < hs.types.size(); ++i) {
+        const HostType& t = hs.types[i];
+        o->types[i] = bcs_type_info{t.count, t.P, t.pStart, t.cStart, t.mStart, t.gStart, t.srcDef, t.warpSync, t.smallestRadius};
+    }
+    BCS_API_END
+}
+
+int bcs_get_table(bcs_sim* s, int table, void* dst, size_t bytes)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && dst, BCS_ERR_INVALID, "null argument");
+    const HostScene& hs = s->hs;
+    const void* src = nullptr;
+    size_t n = 0;
+    std::vector<float> tmp;
+    switch (table) {
+    case BCS_TABLE_SPRING_GRAPH: src = hs.graph.data(); n = hs.graph.size() * 4; break;
+    case BCS_TABLE_MODEL_X: src = hs.mx.data(); n = hs.mx.size() * 4; break;
+    case BCS_TABLE_MODEL_Y: src = hs.my.data(); n = hs.my.size() * 4; break;
+    case BCS_TABLE_MODEL_Z: src = hs.mz.data(); n = hs.mz.size() * 4; break;
+    case BCS_TABLE_COLLISION_RADII: src = hs.collR.data(); n = hs.collR.size() * 4; break;
+    case BCS_TABLE_INITIAL_RADII: src = hs.initR.data(); n = hs.initR.size() * 4; break;
+    case BCS_TABLE_VEIN_NBR_IDS: src = hs.nbrIds.data(); n = hs.nbrIds.size() * 4; break;
+    case BCS_TABLE_VEIN_NBR_LEN: src = hs.nbrLen.data(); n = hs.nbrLen.size() * 4; break;
+    case BCS_TABLE_TRI_CENTERS_X:
+    case BCS_TABLE_TRI_CENTERS_Y:
+    case BCS_TABLE_TRI_CENTERS_Z: {
+        BCS_CUDA(cudaSetDevice(s->device));
+        std::vector<float4> c(hs.T);
+        BCS_CUDA(cudaMemcpyAsync(c.data(), s->tcent, hs.T * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        tmp.resize(hs.T);
+        for (int i = 0; i < hs.T; ++i) tmp[i] = table == BCS_TABLE_TRI_CENTERS_X ? c[i].x : table == BCS_TABLE_TRI_CENTERS_Y ? c[i].y : c[i].z;
+        src = tmp.data(); n = tmp.size() * 4;
+        break;
+    }
+    default: throw Error{BCS_ERR_INVALID, "unknown table id"};
+    }
+    BCS_REQUIRE(bytes >= n, BCS_ERR_INVALID, "destination buffer too small");
+    std::memcpy(dst, src, n);
+    BCS_API_END
+}
+
+int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const float* z, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && x && y && z, BCS_ERR_INVALID, "null argument");
+    BCS_REQUIRE(which != BCS_CELL_CENTERS, BCS_ERR_INVALID, "cell centres are derived, not uploadable");
+    BCS_CUDA(cudaSetDevice(s->device));
+    Array a = array_of(s, which);
+    BCS_REQUIRE(n == a.n, BCS_ERR_INVALID, "array length mismatch");
+    float* sx = s->staging; float* sy = sx + s->stagingLen; float* sz = sy + s->stagingLen;
+    BCS_CUDA(cudaMemcpyAsync(sx, x, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(sy, y, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(sz, z, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, a.ptr, n, s->types, s->collR, a.isParticlePos ? 1 : 0);
+    BCS_CUDA(cudaGetLastError());
+    BCS_API_END
+}
+
+int bcs_download(bcs_sim* s, int which, float* x, float* y, float* z, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && x && y && z, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    Array a = array_of(s, which);
+    BCS_REQUIRE(n == a.n, BCS_ERR_INVALID, "array length mismatch");
+    float* sx = s->staging; float* sy = sx + s->stagingLen; float* sz = sy + s->stagingLen;
+    unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(a.ptr, sx, sy, sz, n);
+    BCS_CUDA(cudaGetLastError());
+    BCS_CUDA(cudaMemcpyAsync(x, sx, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(y, sy, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(z, sz, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    BCS_API_END
+}
+
+int bcs_device_ptrs(bcs_sim* s, bcs_device_view* o)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && o, BCS_ERR_INVALID, "null argument");
+    o->particle_pos4 = s->pos; o->particle_vel4 = s->vel; o->particle_frc4 = s->frc;
+    o->vein_pos4 = s->vpos; o->vein_vel4 = s->vvel; o->vein_frc4 = s->vfrc;
+    o->stream = (void*)s->stream;
+    BCS_API_END
+}
+
+int bcs_host_alloc(void** out, size_t bytes)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(out, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    BCS_API_END
+}
+int bcs_host_free(void* p)
+{
+    BCS_API_BEGIN
+    BCS_CUDA(cudaFreeHost(p));
+    BCS_API_END
+}
+
+int bcs_run_stage(bcs_sim* s, int st)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    stage(s, st);
+    BCS_API_END
+}
+
+int bcs_build_grid(bcs_sim* s)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    stage(s, BCS_STAGE_GRID_PARTICLES);
+    stage(s, BCS_STAGE_GRID_TRIANGLES);
+    BCS_API_END
+}
+
+int bcs_compute_forces(bcs_sim* s)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    for (int st = BCS_STAGE_VEIN_GATHER; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
+    BCS_API_END
+}
+
+int bcs_integrate(bcs_sim* s)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    for (int st = BCS_STAGE_INTEGRATE_PARTICLES; st <= BCS_STAGE_VEIN_END; ++st) stage(s, st);
+    BCS_API_END
+}
+
+int bcs_step(bcs_sim* s, int32_t nsteps)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && nsteps >= 0, BCS_ERR_INVALID, "bad argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    if (!s->useGraph) {
+        for (int i = 0; i < nsteps; ++i) enqueue_step(s);
+    } else {
+        if (!s->graphExec) {
+            cudaGraph_t graph = nullptr;
+            BCS_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_step(s);
+            } catch (...) {
+                cudaStreamEndCapture(s->stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            BCS_CUDA(cudaStreamEndCapture(s->stream, &graph));
+            cudaError_t e = cudaGraphInstantiate(&s->graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            BCS_CUDA(e);
+        }
+        for (int i = 0; i < nsteps; ++i) BCS_CUDA(cudaGraphLaunch(s->graphExec, s->stream));
+    }
+    BCS_API_END
+}
+
+int bcs_synchronize(bcs_sim* s)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    BCS_API_END
+}
+
+int bcs_get_step_count(const bcs_sim* s, int64_t* out)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && out, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    Counters c;
+    BCS_CUDA(cudaMemcpyAsync(&c, s->counters, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    *out = (int64_t)c.step;
+    BCS_API_END
+}
+
+int bcs_get_stats(bcs_sim* s, bcs_stats* o)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && o, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    Counters c;
+    BCS_CUDA(cudaMemcpyAsync(&c, s->counters, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    o->pair_tests = c.pairTests; o->pair_hits = c.pairHits; o->triangle_tests = c.triTests;
+    o->vein_hits = c.veinHits; o->teleported_cells = c.teleported; o->out_of_bounds = c.oob;
+    BCS_API_END
+}
+
+int bcs_download_grid(bcs_sim* s, int which, int32_t* keys, int32_t* ids, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && keys && ids, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    const int m = which ? s->hs.T : s->hs.N;
+    BCS_REQUIRE(n == m, BCS_ERR_INVALID, "array length mismatch");
+    BCS_REQUIRE(which || s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
+    BCS_CUDA(cudaMemcpyAsync(keys, which ? s->tkeys[1] : s->keys[1], n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(ids, which ? s->tids[1] : s->ids[1], n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    BCS_API_END
+}
+
+int bcs_download_cell_table(bcs_sim* s, int which, int32_t cap, int32_t* cells, int32_t* starts, int32_t* ends, int32_t* count)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && cells && starts && ends && count, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    const int nc = which ? s->tg.cells : s->pg.cells;
+    // debug path: copy the dense tables and compact on the host
+    std::vector<int> hs_(nc), he_(nc);
+    BCS_CUDA(cudaMemcpyAsync(hs_.data(), which ? s->tcellStart : s->cellStart, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(he_.data(), which ? s->tcellEnd : s->cellEnd, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    const bool ref = s->semantics == BCS_SEM_REFERENCE;
+    int k = 0;
+    for (int c = 0; c < nc; ++c) {
+        const bool keep = ref ? (hs_[c] != 0 || he_[c] != 0) : (he_[c] >= hs_[c]);
+        if (!keep) continue;
+        if (k < cap) { cells[k] = c; starts[k] = hs_[c]; ends[k] = he_[c]; }
+        ++k;
+    }
+    *count = k;
+    BCS_REQUIRE(k <= cap, BCS_ERR_INVALID, "capacity too small for the cell table");
+    BCS_API_END
+}
+
+int bcs_debug_candidates(bcs_sim* s, int32_t* counts, uint64_t* sums, int32_t* hits, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && counts && sums && hits, BCS_ERR_INVALID, "null argument");
+    BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
+    BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
+    BCS_CUDA(cudaSetDevice(s->device));
+    int* dc = dev_alloc<int>(n);
+    int* dh = dev_alloc<int>(n);
+    unsigned long long* ds = dev_alloc<unsigned long long>(n);
+    CollideArgs a = collide_args(s);
+    a.dbgCount = dc; a.dbgSum = ds; a.dbgHits = dh;
+    cudaError_t e = cudaSuccess;
+    try {
+        launch_particle_collisions(a, s->stream);
+        BCS_CUDA(cudaMemcpyAsync(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaMemcpyAsync(hits, dh, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaMemcpyAsync(sums, ds, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        e = cudaStreamSynchronize(s->stream);
+    } catch (...) {
+        cudaFree(dc); cudaFree(dh); cudaFree(ds);
+        throw;
+    }
+    cudaFree(dc); cudaFree(dh); cudaFree(ds);
+    BCS_CUDA(e);
+    BCS_API_END
+}
+
+int bcs_debug_vein_hits(bcs_sim* s, int32_t* tri, float* t, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && tri && t, BCS_ERR_INVALID, "null argument");
+    BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
+    BCS_CUDA(cudaSetDevice(s->device));
+    int* dt_ = dev_alloc<int>(n);
+    float* df = dev_alloc<float>(n);
+    VeinCollideArgs a = vein_collide_args(s);
+    a.apply = false; a.dbgTri = dt_; a.dbgT = df;
+    cudaError_t e = cudaSuccess;
+    try {
+        launch_tri_refit(a, s->stream);
+        launch_vein_collisions(a, s->stream);
+        BCS_CUDA(cudaMemcpyAsync(tri, dt_, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaMemcpyAsync(t, df, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        e = cudaStreamSynchronize(s->stream);
+    } catch (...) {
+        cudaFree(dt_); cudaFree(df);
+        throw;
+    }
+    cudaFree(dt_); cudaFree(df);
+    BCS_CUDA(e);
+    BCS_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Uniform-grid build: cell keys -> stable LSD radix sort by cell key -> cell start/end tables
+// (+ reordering of particle state into sorted-slot order for the collision pass).
+//
+// Stands in for UniformGrid::calculateGrid (grids/uniform_grid.cu:129-155): calculateCellIdKernel (:38-49),
+// thrust::stable_sort_by_key (:144-147) and calculateStartAndEndOfCellKernel (:51-80).  Results are
+// bit-identical by construction: same key formula, and a stable sort of (key, id) is unique.
+#include "bcs_internal.cuh"
+#include "device_math.cuh"
+#include "kernels.cuh"
+
+namespace bcs {
+
+// ------------------------------------------------------------------------------------------------
+// keys
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cell_keys_kernel(const float4* __restrict__ pos, GridDev g, int* __restrict__ keys,
+                                                        int* __restrict__ ids, unsigned* __restrict__ digitTotals, int passes,
+                                                        Counters* __restrict__ counters)
+{
+    __shared__ unsigned hist[4][256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += stride) {
+        const float4 p = pos[i];
+        const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
+        int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
+                  axis_cell(p.x, g.minx, g.lenx, g.csx);
+        if (oob) {
+            // The reference printf()s and then indexes out of its tables; clamp for memory safety and count.
+            atomicAdd(&counters->oob, 1ull);
+            key = max(0, min(key, g.cells - 1));
+        } else if (key >= g.cells) {
+            key = g.cells - 1;   // position exactly on the upper bound
+        }
+        keys[i] = key;
+        ids[i] = i;
+        for (int p2 = 0; p2 < passes; ++p2) atomicAdd(&hist[p2][(key >> (8 * p2)) & 255], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
+        const unsigned v = (&hist[0][0])[i];
+        if (v) atomicAdd(&digitTotals[i], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix sort, one 8-bit digit per pass: per-tile histograms -> per-bin scan -> stable scatter
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+__global__ void __launch_bounds__(SORT_THREADS) radix_tile_hist_kernel(const int* __restrict__ keys, int n, int shift,
+                                                                       unsigned* __restrict__ tileHist)
+{
+    __shared__ unsigned hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int idx = base + i * SORT_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&hist[(keys[idx] >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    tileHist[(size_t)blockIdx.x * 256 + threadIdx.x] = hist[threadIdx.x];
+}
+
+// one block per digit value: global base of the bin + exclusive prefix of the bin's counts over tiles
+__global__ void __launch_bounds__(256) radix_scan_kernel(unsigned* __restrict__ tileHist, int numTiles,
+                                                         const unsigned* __restrict__ digitTotals)
+{
+    __shared__ unsigned warpSums[8];
+    __shared__ unsigned carry;
+    const int bin = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // bin base = sum of totals of smaller digits
+    unsigned v = (threadIdx.x < bin) ? digitTotals[threadIdx.x] : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) warpSums[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned s = 0;
+        for (int w = 0; w < 8; ++w) s += warpSums[w];
+        carry = s;
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < numTiles; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        const unsigned c = (t < numTiles) ? tileHist[(size_t)t * 256 + bin] : 0u;
+        unsigned incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        unsigned wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warpSums[w];
+        const unsigned base = carry;
+        if (t < numTiles) tileHist[(size_t)t * 256 + bin] = base + wbase + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = base + wbase + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int* __restrict__ keysIn, const int* __restrict__ valsIn,
+                                                                     int* __restrict__ keysOut, int* __restrict__ valsOut, int n,
+                                                                     int shift, const unsigned* __restrict__ tileBase)
+{
+    __shared__ unsigned warpCnt[SORT_WARPS][256];   // per-warp digit counters, later exclusive offsets
+    __shared__ unsigned binStart[256];              // tile-local start of each digit
+    __shared__ unsigned scanTmp[8];
+    __shared__ int exKeys[SORT_TILE];
+    __shared__ int exVals[SORT_TILE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tileStart = blockIdx.x * SORT_TILE;
+    for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&warpCnt[0][0])[i] = 0;
+    __syncthreads();
+
+    int key[SORT_ITEMS], val[SORT_ITEMS];
+    unsigned rank[SORT_ITEMS];
+    const unsigned ltMask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        // warp-striped: warp w owns [w*256, (w+1)*256) of the tile; element order inside the tile is
+        // (warp, item, lane), which is also ascending input order -> stability
+        const int idx = tileStart + warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? keysIn[idx] : 0;
+        val[i] = valid ? valsIn[idx] : 0;
+        const unsigned digit = valid ? ((unsigned)(key[i] >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (valid && lane == leader) {
+            base = warpCnt[warp][digit];
+            warpCnt[warp][digit] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[i] = base + __popc(peers & ltMask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit (thread == digit): exclusive prefix over warps, then exclusive scan over digits
+    unsigned total = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+        const unsigned c = warpCnt[w][tid];
+        warpCnt[w][tid] = total;
+        total += c;
+    }
+    unsigned incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) scanTmp[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += scanTmp[w];
+    binStart[tid] = wbase + incl - total;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int idx = tileStart + warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        if (idx < n) {
+            const unsigned digit = (unsigned)(key[i] >> shift) & 255u;
+            const unsigned pos = binStart[digit] + warpCnt[warp][digit] + rank[i];
+            exKeys[pos] = key[i];
+            exVals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+
+    const int tileCount = min(SORT_TILE, n - tileStart);
+    const unsigned* base = tileBase + (size_t)blockIdx.x * 256;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int j = i * SORT_THREADS + tid;
+        if (j < tileCount) {
+            const int k = exKeys[j];
+            const unsigned digit = (unsigned)(k >> shift) & 255u;
+            const unsigned dst = base[digit] + (unsigned)j - binStart[digit];
+            keysOut[dst] = k;
+            valsOut[dst] = exVals[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cell tables + reorder
+// ------------------------------------------------------------------------------------------------
+// clean semantics: forget last step's occupied cells (instead of a memset of the whole table)
+__global__ void __launch_bounds__(256) clear_cells_kernel(const int* __restrict__ sortedKeys, int n, int* __restrict__ cellStart,
+                                                          int* __restrict__ cellEnd)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const int key = sortedKeys[slot];
+    if (slot == 0 || key != sortedKeys[slot - 1]) {
+        cellStart[key] = 0;
+        cellEnd[key] = -1;
+    }
+}
+
+template <bool REFERENCE, bool REORDER>
+__global__ void __launch_bounds__(256) finalize_grid_kernel(const int* __restrict__ keys, const int* __restrict__ ids, int n,
+                                                            int* __restrict__ cellStart, int* __restrict__ cellEnd,
+                                                            const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                                            float4* __restrict__ spos, float4* __restrict__ svel)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const int key = keys[slot];
+    const int prev = slot > 0 ? keys[slot - 1] : -1;
+    const int next = slot < n - 1 ? keys[slot + 1] : -1;
+    if (REFERENCE) {
+        // uniform_grid.cu:51-80 as written, including thread N-1's `cellStarts[...] = N-1` (:76-79).  That
+        // stray write races with the true start of the last occupied cell; it is issued later in program
+        // order, so it is made the winner here deterministically.
+        const int lastKey = keys[n - 1];
+        if (slot > 0 && key != prev && key != lastKey) cellStart[key] = slot;
+        if (slot < n - 1 && key != next) cellEnd[key] = slot;
+        if (slot == 0 && key != lastKey) cellStart[key] = 0;
+        if (slot == n - 1) cellStart[key] = n - 1;
+    } else {
+        if (key != prev) cellStart[key] = slot;
+        if (key != next) cellEnd[key] = slot;
+    }
+    if (REORDER) {
+        const int id = ids[slot];
+        float4 p = pos[id];
+        float4 v = vel[id];
+        // canonical pos4.w already carries the particle's own collision radius (set at upload, preserved by
+        // the integrator); the reference-compatible radius lookup needs the particle id instead
+        if (REFERENCE) p.w = __int_as_float(id);
+        v.w = __int_as_float(id);
+        spos[slot] = p;
+        svel[slot] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side driver
+// ------------------------------------------------------------------------------------------------
+void SortScratch::allocate(int n)
+{
+    numTiles = (n + SORT_TILE - 1) / SORT_TILE;
+    BCS_CUDA(cudaMalloc(&tileHist, (size_t)numTiles * 256 * sizeof(unsigned)));
+    BCS_CUDA(cudaMalloc(&digitTotals, 4 * 256 * sizeof(unsigned)));
+}
+void SortScratch::release()
+{
+    cudaFree(tileHist);
+    cudaFree(digitTotals);
+    tileHist = digitTotals = nullptr;
+}
+
+void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
+{
+    const GridDev& g = a.grid;
+    const int n = g.n;
+    const int passes = (g.keyBits + 7) / 8;
+    const int blocks = (n + 255) / 256;
+    // buffer schedule: the last pass must land in buffer 1
+    int cur = (passes & 1) ? 0 : 1;
+    if (!a.reference && a.tablesValid) clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd);
+    BCS_CUDA(cudaMemsetAsync(a.scratch->digitTotals, 0, 4 * 256 * sizeof(unsigned), st));
+    const int keyBlocks = min(blocks, 148 * 8);
+    cell_keys_kernel<<<keyBlocks, 256, 0, st>>>(a.objPos, g, a.keys[cur], a.ids[cur], a.scratch->digitTotals, passes, a.counters);
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        radix_tile_hist_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], n, shift, a.scratch->tileHist);
+        radix_scan_kernel<<<256, 256, 0, st>>>(a.scratch->tileHist, a.scratch->numTiles, a.scratch->digitTotals + 256 * p);
+        radix_scatter_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], a.ids[cur], a.keys[cur ^ 1], a.ids[cur ^ 1],
+                                                                           n, shift, a.scratch->tileHist);
+        cur ^= 1;
+    }
+    // cur == 1 here
+    if (a.reference) {
+        if (a.reorder)
+            finalize_grid_kernel<true, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
+                                                                     a.spos, a.svel);
+        else
+            finalize_grid_kernel<true, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
+                                                                      nullptr, nullptr, nullptr);
+    } else {
+        if (a.reorder)
+            finalize_grid_kernel<false, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
+                                                                      a.spos, a.svel);
+        else
+            finalize_grid_kernel<false, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
+                                                                       nullptr, nullptr, nullptr);
+    }
+    BCS_CUDA(cudaGetLastError());
+}
+
+}  // namespace bcs

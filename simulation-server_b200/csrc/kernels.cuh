@@ -1,0 +1,141 @@
+// Launchers of the hot-path kernels (one .cu per stage family).  All launches are asynchronous on
+// the stream given; errors are thrown as bcs::Error.
+#pragma once
+#include "bcs_internal.cuh"
+
+namespace bcs {
+
+// ---- grid.cu -------------------------------------------------------------------------------------------
+struct SortScratch {
+    unsigned* tileHist = nullptr;      // [numTiles][256] per-tile digit counts -> global offsets
+    unsigned* digitTotals = nullptr;   // [4][256] whole-array digit counts per pass
+    int numTiles = 0;
+    void allocate(int n);
+    void release();
+};
+
+struct GridBuildArgs {
+    GridDev grid;
+    const float4* objPos;     // positions the keys are computed from (particles or triangle centres)
+    int* keys[2];             // ping-pong; the sorted result always lands in [1]
+    int* ids[2];
+    int* cellStart;
+    int* cellEnd;
+    SortScratch* scratch;
+    Counters* counters;
+    bool reference;           // BCS_SEM_REFERENCE table semantics
+    bool tablesValid;         // clean semantics: tables hold last step's ranges (to be un-written)
+    bool reorder;             // also write sorted-order copies of pos/vel
+    const float4* pos;
+    const float4* vel;
+    float4* spos;
+    float4* svel;
+};
+void launch_grid_build(const GridBuildArgs& a, cudaStream_t st);
+
+// ---- springs.cu ----------------------------------------------------------------------------------------
+struct SpringPlan {
+    int blockStart[BCS_MAX_TYPES + 1];   // first block of each type
+    int cellsPerBlock[BCS_MAX_TYPES];
+    int totalBlocks;
+};
+SpringPlan make_spring_plan(const TypesDev& types);
+struct SpringArgs {
+    TypesDev types;
+    SpringPlan plan;
+    PhysDev phys;
+    const float4* pos;
+    const float4* vel;
+    float4* frc;
+    float4* centers;            // [B]
+    const int* adjJ;
+    const float* adjL;
+    const float* initR;         // [nModel]
+};
+void launch_springs(const SpringArgs& a, cudaStream_t st);
+
+// ---- collide.cu ----------------------------------------------------------------------------------------
+struct CollideArgs {
+    GridDev grid;
+    TypesDev types;
+    PhysDev phys;
+    int n;
+    const int* keys;            // sorted cell ids
+    const float4* spos;         // sorted positions  (w: radius | particle id bits in reference mode)
+    const float4* svel;         // sorted velocities (w: particle id bits)
+    const int* cellStart;
+    const int* cellEnd;
+    const float* collR;         // [nModel] (reference-mode lookup)
+    float4* frc;
+    Counters* counters;
+    bool reference;
+    bool stats;
+    // debug outputs (indexed by particle id), all null in production
+    int* dbgCount;
+    unsigned long long* dbgSum;
+    int* dbgHits;
+};
+void launch_particle_collisions(const CollideArgs& a, cudaStream_t st);
+
+// ---- vein.cu -------------------------------------------------------------------------------------------
+struct VeinArgs {
+    int V, T;
+    PhysDev phys;
+    float4* vpos;
+    float4* vvel;
+    float4* vfrc;
+    const int* nbrIds;          // [9][V]
+    const float* nbrLen;
+    const unsigned* vidx;       // [3T]
+};
+void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st);
+void launch_vein_gather(const VeinArgs& a, cudaStream_t st);
+void launch_vein_integrate(const VeinArgs& a, cudaStream_t st);
+
+struct VeinCollideArgs {
+    GridDev tgrid;
+    TypesDev types;
+    PhysDev phys;
+    int n;                      // particles
+    int T;
+    float4* pos;
+    float4* vel;
+    float4* frc;
+    const float4* vpos;
+    float4* vfrc;
+    const unsigned* vidx;
+    const int* triIds;          // sorted triangle ids
+    const int* cellStart;
+    const int* cellEnd;
+    TriPacked* tris;            // [T] packed triangles in sorted-slot order (refit each step)
+    const float* collR;
+    Counters* counters;
+    bool stats;
+    bool apply;                 // false: only fill the debug outputs
+    int* dbgTri;
+    float* dbgT;
+};
+void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st);
+void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st);
+
+// ---- integrate.cu --------------------------------------------------------------------------------------
+struct IntegrateArgs {
+    TypesDev types;
+    PhysDev phys;
+    int n;
+    int nCells;
+    float4* pos;
+    float4* vel;
+    const float4* frc;
+    const float* mx;
+    const float* my;
+    const float* mz;
+    const float* endC;
+    const float* endR;
+    Counters* counters;
+    unsigned long long seed;
+};
+void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
+void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter
+
+}  // namespace bcs

@@ -1,0 +1,122 @@
+"""GPU (B200): parity of libbcs.so - called through its C ABI - with (a) dumps of the reference CUDA build
+(reference-compatible semantics) and (b) the CPU oracle (clean and reference-compatible semantics)."""
+import numpy as np
+import pytest
+
+import refcheck
+from conftest import (capi, golden_dump, golden_scene, make_bcs, make_oracle, pkg, seeded_state, small_cylinder_scene)
+from test_oracle_vs_reference import CASES, TRAJECTORY_CASES, check_trajectory
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "mini3", "cfg2"])
+def test_derived_tables(bcs_lib, oracle_lib, cfg):
+    sc = golden_scene(cfg)
+    with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
+        a, b = sim.layout, orc.layout
+        assert bytes(a) == bytes(b)
+        for t in range(11):
+            assert np.array_equal(sim.table(t), orc.table(t)), f"table {t}"
+
+
+@pytest.mark.parametrize("cfg,variant,steps,vein_steps", CASES)
+def test_stage_by_stage_vs_reference(bcs_lib, cfg, variant, steps, vein_steps):
+    sc = golden_scene(cfg)
+    with make_bcs(sc, capi.SEM_REFERENCE) as sim:
+        summary = refcheck.replay_steps(sim, cfg, variant, steps, golden_dump, sc, sc.physics, vein_steps)
+    if variant == "wide":
+        assert summary[1]["vein_hits"] > 20
+
+
+def test_candidate_sets_vs_reference_grid(bcs_lib):
+    sc = golden_scene("mini3")
+    with make_bcs(sc, capi.SEM_REFERENCE) as sim:
+        for step in (1, 2, 3):
+            d = golden_dump("mini3", "wide", step)
+            refcheck.up(sim, capi.PARTICLE_POS, refcheck.vec(d, "begin.pos"))
+            refcheck.up(sim, capi.PARTICLE_VEL, refcheck.vec(d, "begin.vel"))
+            sim.run_stage(capi.STAGE_GRID_PARTICLES)
+            cnt, chk, _ = sim.debug_candidates()
+            ecnt, echk = refcheck.expected_candidates(d, sim.layout)
+            assert np.array_equal(cnt, ecnt)
+            assert np.array_equal(chk, echk)
+
+
+@pytest.mark.parametrize("cfg,variant", TRAJECTORY_CASES)
+def test_100_step_trajectory_vs_reference(bcs_lib, cfg, variant):
+    sc = golden_scene(cfg)
+    st, _ = seeded_state(cfg, variant)
+    with make_bcs(sc, capi.SEM_REFERENCE) as sim:
+        sim.upload_state(st)
+        sim.step(100)
+        pos = refcheck.down(sim, capi.PARTICLE_POS)
+        assert sim.step_count() == 100
+    check_trajectory(pos, cfg, variant, st)
+
+
+def _compare_step(sim, orc, nsteps, tag):
+    """one step at a time: stage outputs of libbcs vs oracle from identical inputs"""
+    for step in range(nsteps):
+        # identical inputs: copy the oracle's state into the device handle
+        for which in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC):
+            refcheck.up(sim, which, refcheck.down(orc, which))
+        sim.run_stage(capi.STAGE_GRID_PARTICLES); orc.run_stage(capi.STAGE_GRID_PARTICLES)
+        for which in (0, 1):
+            ka, ia = sim.grid(which); kb, ib = orc.grid(which)
+            assert np.array_equal(ka, kb) and np.array_equal(ia, ib), f"{tag} step {step}: grid {which}"
+            ta, tb = sim.cell_table(which), orc.cell_table(which)
+            assert all(np.array_equal(x, y) for x, y in zip(ta, tb)), f"{tag} step {step}: cell table {which}"
+        ca, cb = sim.debug_candidates(), orc.debug_candidates()
+        assert all(np.array_equal(x, y) for x, y in zip(ca, cb)), f"{tag} step {step}: candidate sets"
+        ha, hb = sim.debug_vein_hits(), orc.debug_vein_hits()
+        for st in (capi.STAGE_VEIN_GATHER, capi.STAGE_SPRINGS, capi.STAGE_PARTICLE_COLLISIONS):
+            sim.run_stage(st); orc.run_stage(st)
+            refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_FRC), refcheck.down(orc, capi.PARTICLE_FRC), f"{tag} step {step} stage {st} forces")
+        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), refcheck.down(orc, capi.VEIN_FRC), f"{tag} step {step} vein spring forces",
+                              scale=max(0.5, float(np.abs(refcheck.down(orc, capi.VEIN_FRC)).max())))
+        ha, hb = sim.debug_vein_hits(), orc.debug_vein_hits()
+        same = ha[0] == hb[0]
+        assert same.mean() > 0.999, f"{tag} step {step}: first-hit triangles differ for {(~same).sum()} particles"
+        sim.run_stage(capi.STAGE_VEIN_COLLISIONS); orc.run_stage(capi.STAGE_VEIN_COLLISIONS)
+        ok = same
+        refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_FRC)[ok], refcheck.down(orc, capi.PARTICLE_FRC)[ok], f"{tag} step {step} forces after vein collisions")
+        refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_VEL)[ok], refcheck.down(orc, capi.PARTICLE_VEL)[ok], f"{tag} step {step} velocities after vein collisions")
+        vf = refcheck.down(orc, capi.VEIN_FRC)
+        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), vf, f"{tag} step {step} vein forces", scale=float(np.abs(vf).max()),
+                              allowed=0 if same.all() else 9)
+        for st in (capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END):
+            sim.run_stage(st); orc.run_stage(st)
+        if same.all():
+            refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_POS), refcheck.down(orc, capi.PARTICLE_POS), f"{tag} step {step} positions", scale=0.0)
+            refcheck.assert_close(refcheck.down(sim, capi.VEIN_POS), refcheck.down(orc, capi.VEIN_POS), f"{tag} step {step} vein positions", scale=0.0)
+
+
+@pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
+@pytest.mark.parametrize("cfg,variant", [("mini3", "wide"), ("cfg1", "wide"), ("cfg1", "spawn")])
+def test_vs_oracle_default_vein(bcs_lib, oracle_lib, cfg, variant, semantics):
+    sc = golden_scene(cfg)
+    st, _ = seeded_state(cfg, variant)
+    with make_bcs(sc, semantics) as sim, make_oracle(oracle_lib, sc, semantics) as orc:
+        orc.upload_state(st)
+        _compare_step(sim, orc, 6, f"{cfg}/{variant}/sem{semantics}")
+
+
+def test_vs_oracle_cylinder_scene(bcs_lib, oracle_lib):
+    sc = small_cylinder_scene()
+    st = pkg.make_initial_state(sc, seed=7, xz_half_width=49.0, y_range=(-25.0, -110.0))
+    with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
+        orc.upload_state(st)
+        _compare_step(sim, orc, 8, "cylinder")
+
+
+def test_graph_and_plain_launch_agree(bcs_lib):
+    sc = golden_scene("mini3")
+    st, _ = seeded_state("mini3", "wide")
+    out = []
+    for use_graph in (True, False):
+        with make_bcs(sc, use_graph=use_graph) as sim:
+            sim.upload_state(st)
+            sim.step(20)
+            out.append(refcheck.down(sim, capi.PARTICLE_POS))
+    refcheck.assert_close(out[0], out[1], "graph replay vs plain launches", rtol=1e-4, scale=0.0)
