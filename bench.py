@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the per-step physics hot path (BASELINE.json: particle-steps/s and ms/step at 1 M particles).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" = grid build + forces + integration of ALL particles of the
+workload (bcs_step).  `value` is measured with the state resident in HBM (CUDA events on the library's
+stream around K graph-replayed steps); `e2e` is the same metric through the C ABI with HOST buffers:
+every step uploads positions/velocities/forces from pinned host memory and downloads the positions.
+`--impl reference` times the host-core port of the reference step (oracle/, OpenMP, all host threads) -
+upstream has no CPU path of its own - on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_s"
+UNIT = "particle-steps/s"
+
+
+def _pkg():
+    return importlib.import_module("simulation-server_b200"), importlib.import_module("simulation-server_b200.capi"), \
+        importlib.import_module("simulation-server_b200.workloads")
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- roofline
+def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, hits: int = 0):
+    """Compulsory bytes of one launch (fp32 vec3 = 12 B, ids = 4 B); DESIGN.md section 'Kernels and rooflines'.
+    The spring and collision figures are SURVEY.md 8(d)'s contract numbers."""
+    table = {
+        "cell_keys": 20 * N,                       # R pos 12N, W key+id 8N
+        "radix_tile_hist": 4 * N,                  # R keys
+        "radix_scan": 0,
+        "radix_scatter": 16 * N,                   # R key+id 8N, W key+id 8N
+        "clear_cells": 4 * N + 8 * c_occ,
+        "finalize_grid": 8 * N + 16 * c_occ + 48 * N,   # R key+id, W start/end per occupied cell, reorder pos+vel R+W
+        "vein_gather": 120 * V,
+        "springs": 48 * N + 12 * B,                # R pos,vel,frc 36N, W frc 12N, W centres 12B
+        "particle_collisions": 56 * N + 8 * c_occ,
+        "tri_refit": 96 * T,
+        "vein_collisions": 24 * N + 120 * hits,
+        "integrate_particles": 60 * N,
+        "vein_integrate": 72 * V,
+        "vein_end": 12 * N,
+        "advance_step": 0,
+    }
+    return table.get(kernel, 0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------- oracle (CPU) leg
+def oracle_library():
+    path = os.path.join(ROOT, "oracle", "libbcs_oracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    return ctypes.CDLL(path)
+
+
+def time_oracle(particles: int, steps: int, warmup: int):
+    """Host-core port of the reference step on a bounded sample: a section of the same vein at the same density."""
+    pkg, capi, workloads = _pkg()
+    lib = oracle_library()
+    lib.orc_threads.restype = ctypes.c_int
+    cores = int(lib.orc_threads())
+    sc, st, info = workloads.long_vein(particles)
+    sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, lib=lib, prefix="orc_")
+    sim.upload_state(st)
+    sim.step(warmup)
+    t0 = time.perf_counter()
+    sim.step(steps)
+    dt = time.perf_counter() - t0
+    n = sim.n_particles
+    sim.close()
+    return n * steps / dt, dt / steps * 1e3, cores, n, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(args.particles, args.reference_sample)
+    value, ms, cores, n, info = time_oracle(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"long_vein_{args.particles}", "particles": args.particles, "timed_sample_particles": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n}-particle section of the {args.particles}-particle long-vein workload (same density, same step), "
+                                   f"{args.steps} steps after {args.warmup} warm-up; upstream has no CPU path, this is the host-core port under oracle/"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    pkg, capi, workloads = _pkg()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU slab decomposition is not available in this build of bench.py")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+
+    sc, st, info = workloads.long_vein(args.particles)
+    sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, device=local_rank, use_graph=True)
+    N, B, V, T = sim.n_particles, sim.n_cells, sim.n_vertices, sim.n_triangles
+    sim.upload_state(st)
+    view = sim.device_view()
+    stream = torch.cuda.ExternalStream(view.stream, device=local_rank)
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K steps between two events
+    sim.step(args.warmup)
+    sim.synchronize()
+    launches0 = sim.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        start.record(stream)
+        sim.step(args.steps)
+        end.record(stream)
+        sim.synchronize()
+        torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.steps
+    launches = sim.launch_count() - launches0
+    value = N / (ms * 1e-3)
+
+    # ---- per-kernel times (CUDA events around every launch, plain launches) and the roofline of the dominant kernel
+    keys, _ = sim.grid(0)
+    c_occ = int(np.unique(keys).size)
+    hits0 = sim.stats()["vein_hits"]
+    prof_steps = 5
+    prof = sim.profile_steps(prof_steps)
+    hits = (sim.stats()["vein_hits"] - hits0) // prof_steps
+    total_ms = sum(v[0] for v in prof.values())
+    kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps, "share": v[0] / total_ms}
+               for k, v in prof.items()}
+    dominant = max(prof, key=lambda k: prof[k][0])
+    peak, peak_src = measured_peaks()
+
+    def roof(name):
+        per_launch_ms = prof[name][0] / prof[name][1]
+        b = algorithmic_bytes(name, N, B, V, T, c_occ, hits)
+        gbs = b / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms, "peak_source": peak_src}
+
+    roofline = roof(dominant)
+    roofline["contract_kernels"] = {k: roof(k) for k in ("springs", "particle_collisions") if k in prof}
+    step_bytes = sum(algorithmic_bytes(k, N, B, V, T, c_occ, hits) * v[1] / prof_steps for k, v in prof.items())
+    roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    host = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in st.items()}
+    out = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(3)]
+    hp = {k: ctypes.cast(v.data_ptr(), ctypes.POINTER(ctypes.c_float)) for k, v in host.items()}
+    op = [ctypes.cast(v.data_ptr(), ctypes.POINTER(ctypes.c_float)) for v in out]
+    n32 = ctypes.c_int32(N)
+
+    def e2e_step():
+        sim._call("upload", sim._h, capi.PARTICLE_POS, hp["pos_x"], hp["pos_y"], hp["pos_z"], n32)
+        sim._call("upload", sim._h, capi.PARTICLE_VEL, hp["vel_x"], hp["vel_y"], hp["vel_z"], n32)
+        sim._call("upload", sim._h, capi.PARTICLE_FRC, hp["frc_x"], hp["frc_y"], hp["frc_z"], n32)
+        sim._call("step", sim._h, ctypes.c_int32(1))
+        sim._call("download", sim._h, capi.PARTICLE_POS, op[0], op[1], op[2], n32)
+
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(3):
+        e2e_step()
+    sim.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sim.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 36 * N, "d2h_bytes_per_step": 12 * N,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
+
+    # ---- CPU baseline (rank 0, N=1): the host-core port on a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        cv, cms, cores, cn, _ = time_oracle(min(args.particles, args.reference_sample), 3, 1)
+        cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cms,
+               "sample": f"{cn}-particle section of the workload (same density), 3 steps after 1 warm-up, OpenMP on {cores} threads"}
+
+    ws_mb = (16 * 3 * N + 16 * 2 * N + 16 * N + 64 * c_occ + 48 * V + 48 * T) / 1e6
+    config = dict(info)
+    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step",
+                   "l2": f"no flush: per-step working set ~{ws_mb:.0f} MB exceeds the 126 MB L2 (inputs larger than L2)",
+                   "occupied_grid_cells": c_occ, "grid_cells": int(sim.layout.grid_cells)})
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+    }
+    sim.close()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--impl", default="bcs", choices=["bcs", "reference"])
+    ap.add_argument("--reference-sample", type=int, default=100_000, help="particles in the CPU-timed sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -299,6 +299,21 @@ typedef struct bcs_stats {
 /* Totals since creation (pair/triangle counters only advance when bcs_opts.collect_stats = 1). */
 int bcs_get_stats(bcs_sim* sim, bcs_stats* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement support (no reference counterpart: the reference only prints a wall-clock average at exit,
+ * main.cu:248-253).
+ * ------------------------------------------------------------------------------------------- */
+/* Number of libbcs kernels enqueued on the handle's stream since creation (CUDA-graph replays count
+ * their kernel nodes). */
+int bcs_get_launch_count(bcs_sim* sim, uint64_t* kernels);
+
+#define BCS_KERNEL_NAME_LEN 48
+/* Runs nsteps full steps with plain launches, bracketing EVERY kernel with CUDA events on the handle's
+ * stream, and returns per kernel name the summed device time (ms) and launch count, in first-launch
+ * order.  Synchronous.  The simulation state advances by nsteps. */
+int bcs_profile_steps(bcs_sim* sim, int32_t nsteps, int32_t capacity, char (*names)[BCS_KERNEL_NAME_LEN], float* ms_total,
+                      int32_t* launches, int32_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -325,6 +325,20 @@ class Sim:
         self._call("get_stats", self._h, C.byref(s))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
 
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._call("get_launch_count", self._h, C.byref(v))
+        return v.value
+
+    def profile_steps(self, nsteps: int = 1, capacity: int = 64):
+        """Per-kernel device time of ``nsteps`` plain-launch steps: {name: (ms_total, launches)}."""
+        names = ((C.c_char * 48) * capacity)()
+        ms = (C.c_float * capacity)()
+        launches = (C.c_int32 * capacity)()
+        cnt = C.c_int32()
+        self._call("profile_steps", self._h, C.c_int32(nsteps), C.c_int32(capacity), names, ms, launches, C.byref(cnt))
+        return {names[i].value.decode(): (float(ms[i]), int(launches[i])) for i in range(cnt.value)}
+
     def device_view(self) -> DeviceView:
         v = DeviceView()
         self._call("device_ptrs", self._h, C.byref(v))

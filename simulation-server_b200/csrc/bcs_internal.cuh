@@ -33,6 +33,31 @@ struct Error {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// launch bookkeeping: every kernel launch goes through BCS_LAUNCH so that the library can (a) report how
+// many of its kernels ran (bcs_get_launch_count) and (b) time each kernel with CUDA events on the launching
+// stream when profiling is on (bcs_profile_steps).
+// ---------------------------------------------------------------------------------------------
+struct LaunchRecord {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+struct LaunchCtx {
+    unsigned long long launches = 0;
+    bool timing = false;
+    std::vector<LaunchRecord> records;
+};
+LaunchCtx* current_launch_ctx();
+void set_launch_ctx(LaunchCtx* c);
+void launch_begin(const char* name, cudaStream_t st);
+void launch_end(cudaStream_t st);
+#define BCS_LAUNCH(name, st, ...)            \
+    do {                                     \
+        ::bcs::launch_begin(name, st);       \
+        __VA_ARGS__;                         \
+        ::bcs::launch_end(st);               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
 // device-side parameter blocks (passed by value to kernels / kept in __constant__-like structs)
 // ---------------------------------------------------------------------------------------------
 struct TypeDev {            // one blood-cell type in final (meta-factory) order

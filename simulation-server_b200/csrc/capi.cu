@@ -19,6 +19,32 @@ namespace bcs {
 static thread_local std::string g_lastError;
 void set_error(const std::string& msg) { g_lastError = msg; }
 
+static thread_local LaunchCtx* g_launchCtx = nullptr;
+LaunchCtx* current_launch_ctx() { return g_launchCtx; }
+void set_launch_ctx(LaunchCtx* c) { g_launchCtx = c; }
+void launch_begin(const char* name, cudaStream_t st)
+{
+    LaunchCtx* c = g_launchCtx;
+    if (!c) return;
+    ++c->launches;
+    if (c->timing) {
+        LaunchRecord r{name, nullptr, nullptr};
+        cudaEventCreate(&r.start);
+        cudaEventCreate(&r.stop);
+        cudaEventRecord(r.start, st);
+        c->records.push_back(r);
+    }
+}
+void launch_end(cudaStream_t st)
+{
+    LaunchCtx* c = g_launchCtx;
+    if (c && c->timing && !c->records.empty()) cudaEventRecord(c->records.back().stop, st);
+}
+struct CtxScope {
+    explicit CtxScope(LaunchCtx* c) { set_launch_ctx(c); }
+    ~CtxScope() { set_launch_ctx(nullptr); }
+};
+
 template <class T>
 static T* dev_alloc(size_t count, bool zero = true)
 {
@@ -109,6 +135,8 @@ struct bcs_sim {
     SpringPlan plan{};
     bool gridBuilt = false;
     cudaGraphExec_t graphExec = nullptr;
+    LaunchCtx ctx;
+    unsigned long long kernelsPerGraph = 0;
     std::vector<void*> owned;
 
     template <class T> T* track(T* p) { owned.push_back((void*)p); return p; }
@@ -482,6 +510,7 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     BCS_API_BEGIN
     BCS_REQUIRE(s && x && y && z, BCS_ERR_INVALID, "null argument");
     BCS_REQUIRE(which != BCS_CELL_CENTERS, BCS_ERR_INVALID, "cell centres are derived, not uploadable");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     Array a = array_of(s, which);
     BCS_REQUIRE(n == a.n, BCS_ERR_INVALID, "array length mismatch");
@@ -498,6 +527,7 @@ int bcs_download(bcs_sim* s, int which, float* x, float* y, float* z, int32_t n)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s && x && y && z, BCS_ERR_INVALID, "null argument");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     Array a = array_of(s, which);
     BCS_REQUIRE(n == a.n, BCS_ERR_INVALID, "array length mismatch");
@@ -539,6 +569,7 @@ int bcs_run_stage(bcs_sim* s, int st)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     stage(s, st);
     BCS_API_END
@@ -548,6 +579,7 @@ int bcs_build_grid(bcs_sim* s)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     stage(s, BCS_STAGE_GRID_PARTICLES);
     stage(s, BCS_STAGE_GRID_TRIANGLES);
@@ -558,6 +590,7 @@ int bcs_compute_forces(bcs_sim* s)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     for (int st = BCS_STAGE_VEIN_GATHER; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
     BCS_API_END
@@ -567,6 +600,7 @@ int bcs_integrate(bcs_sim* s)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     for (int st = BCS_STAGE_INTEGRATE_PARTICLES; st <= BCS_STAGE_VEIN_END; ++st) stage(s, st);
     BCS_API_END
@@ -576,6 +610,7 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s && nsteps >= 0, BCS_ERR_INVALID, "bad argument");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     if (!s->useGraph) {
         for (int i = 0; i < nsteps; ++i) enqueue_step(s);
@@ -583,8 +618,11 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
         if (!s->graphExec) {
             cudaGraph_t graph = nullptr;
             BCS_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            const unsigned long long before = s->ctx.launches;
             try {
                 enqueue_step(s);
+                s->kernelsPerGraph = s->ctx.launches - before;
+                s->ctx.launches = before;   // captured, not executed
             } catch (...) {
                 cudaStreamEndCapture(s->stream, &graph);
                 if (graph) cudaGraphDestroy(graph);
@@ -595,8 +633,62 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
             cudaGraphDestroy(graph);
             BCS_CUDA(e);
         }
-        for (int i = 0; i < nsteps; ++i) BCS_CUDA(cudaGraphLaunch(s->graphExec, s->stream));
+        for (int i = 0; i < nsteps; ++i) {
+            BCS_CUDA(cudaGraphLaunch(s->graphExec, s->stream));
+            s->ctx.launches += s->kernelsPerGraph;
+        }
     }
+    BCS_API_END
+}
+
+int bcs_get_launch_count(bcs_sim* s, uint64_t* kernels)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && kernels, BCS_ERR_INVALID, "null argument");
+    *kernels = s->ctx.launches;
+    BCS_API_END
+}
+
+int bcs_profile_steps(bcs_sim* s, int32_t nsteps, int32_t cap, char (*names)[BCS_KERNEL_NAME_LEN], float* ms_total, int32_t* launches,
+                      int32_t* count)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && names && ms_total && launches && count && nsteps > 0 && cap > 0, BCS_ERR_INVALID, "bad argument");
+    CtxScope scope(&s->ctx);
+    BCS_CUDA(cudaSetDevice(s->device));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    s->ctx.records.clear();
+    s->ctx.timing = true;
+    try {
+        for (int i = 0; i < nsteps; ++i) enqueue_step(s);
+    } catch (...) {
+        s->ctx.timing = false;
+        throw;
+    }
+    s->ctx.timing = false;
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    int k = 0;
+    for (const LaunchRecord& r : s->ctx.records) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        int j = 0;
+        for (; j < k; ++j)
+            if (std::strncmp(names[j], r.name, BCS_KERNEL_NAME_LEN - 1) == 0) break;
+        if (j == k) {
+            if (k == cap) continue;
+            std::strncpy(names[k], r.name, BCS_KERNEL_NAME_LEN - 1);
+            names[k][BCS_KERNEL_NAME_LEN - 1] = 0;
+            ms_total[k] = 0.f;
+            launches[k] = 0;
+            ++k;
+        }
+        ms_total[j] += ms;
+        launches[j] += 1;
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    s->ctx.records.clear();
+    *count = k;
     BCS_API_END
 }
 
@@ -678,6 +770,7 @@ int bcs_debug_candidates(bcs_sim* s, int32_t* counts, uint64_t* sums, int32_t* h
     BCS_REQUIRE(s && counts && sums && hits, BCS_ERR_INVALID, "null argument");
     BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
     BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     int* dc = dev_alloc<int>(n);
     int* dh = dev_alloc<int>(n);
@@ -705,6 +798,7 @@ int bcs_debug_vein_hits(bcs_sim* s, int32_t* tri, float* t, int32_t n)
     BCS_API_BEGIN
     BCS_REQUIRE(s && tri && t, BCS_ERR_INVALID, "null argument");
     BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
+    CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     int* dt_ = dev_alloc<int>(n);
     float* df = dev_alloc<float>(n);

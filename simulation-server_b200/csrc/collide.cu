@@ -157,13 +157,13 @@ void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
     const bool dbg = a.dbgCount != nullptr;
     if (a.reference) {
-        if (dbg) particle_collisions_kernel<true, true, false><<<blocks, threads, 0, st>>>(a);
-        else if (a.stats) particle_collisions_kernel<true, false, true><<<blocks, threads, 0, st>>>(a);
-        else particle_collisions_kernel<true, false, false><<<blocks, threads, 0, st>>>(a);
+        if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, true, false><<<blocks, threads, 0, st>>>(a));
+        else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, true><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, false><<<blocks, threads, 0, st>>>(a));
     } else {
-        if (dbg) particle_collisions_kernel<false, true, false><<<blocks, threads, 0, st>>>(a);
-        else if (a.stats) particle_collisions_kernel<false, false, true><<<blocks, threads, 0, st>>>(a);
-        else particle_collisions_kernel<false, false, false><<<blocks, threads, 0, st>>>(a);
+        if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, true, false><<<blocks, threads, 0, st>>>(a));
+        else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, true><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false><<<blocks, threads, 0, st>>>(a));
     }
     BCS_CUDA(cudaGetLastError());
 }

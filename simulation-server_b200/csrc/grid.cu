@@ -273,33 +273,38 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
     const int blocks = (n + 255) / 256;
     // buffer schedule: the last pass must land in buffer 1
     int cur = (passes & 1) ? 0 : 1;
-    if (!a.reference && a.tablesValid) clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd);
+    if (!a.reference && a.tablesValid)
+        BCS_LAUNCH("clear_cells", st, clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd));
     BCS_CUDA(cudaMemsetAsync(a.scratch->digitTotals, 0, 4 * 256 * sizeof(unsigned), st));
     const int keyBlocks = min(blocks, 148 * 8);
-    cell_keys_kernel<<<keyBlocks, 256, 0, st>>>(a.objPos, g, a.keys[cur], a.ids[cur], a.scratch->digitTotals, passes, a.counters);
+    BCS_LAUNCH("cell_keys", st,
+               cell_keys_kernel<<<keyBlocks, 256, 0, st>>>(a.objPos, g, a.keys[cur], a.ids[cur], a.scratch->digitTotals, passes, a.counters));
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
-        radix_tile_hist_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], n, shift, a.scratch->tileHist);
-        radix_scan_kernel<<<256, 256, 0, st>>>(a.scratch->tileHist, a.scratch->numTiles, a.scratch->digitTotals + 256 * p);
-        radix_scatter_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], a.ids[cur], a.keys[cur ^ 1], a.ids[cur ^ 1],
-                                                                           n, shift, a.scratch->tileHist);
+        BCS_LAUNCH("radix_tile_hist", st,
+                   radix_tile_hist_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], n, shift, a.scratch->tileHist));
+        BCS_LAUNCH("radix_scan", st,
+                   radix_scan_kernel<<<256, 256, 0, st>>>(a.scratch->tileHist, a.scratch->numTiles, a.scratch->digitTotals + 256 * p));
+        BCS_LAUNCH("radix_scatter", st,
+                   radix_scatter_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], a.ids[cur], a.keys[cur ^ 1],
+                                                                                      a.ids[cur ^ 1], n, shift, a.scratch->tileHist));
         cur ^= 1;
     }
     // cur == 1 here
     if (a.reference) {
         if (a.reorder)
-            finalize_grid_kernel<true, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
-                                                                     a.spos, a.svel);
+            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<true, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
+                                                                     a.spos, a.svel));
         else
-            finalize_grid_kernel<true, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
-                                                                      nullptr, nullptr, nullptr);
+            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<true, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
+                                                                      nullptr, nullptr, nullptr));
     } else {
         if (a.reorder)
-            finalize_grid_kernel<false, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
-                                                                      a.spos, a.svel);
+            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<false, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
+                                                                      a.spos, a.svel));
         else
-            finalize_grid_kernel<false, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
-                                                                       nullptr, nullptr, nullptr);
+            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<false, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
+                                                                       nullptr, nullptr, nullptr));
     }
     BCS_CUDA(cudaGetLastError());
 }

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) integrate_particles_kernel(float4* __rest
 
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st)
 {
-    integrate_particles_kernel<<<(a.n + 255) / 256, 256, 0, st>>>(a.pos, a.vel, a.frc, a.n, a.phys.dt);
+    BCS_LAUNCH("integrate_particles", st, integrate_particles_kernel<<<(a.n + 255) / 256, 256, 0, st>>>(a.pos, a.vel, a.frc, a.n, a.phys.dt));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -77,8 +77,8 @@ __global__ void advance_step_kernel(Counters* c) { c->step += 1; }
 
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st)
 {
-    if (a.phys.useBloodFlow) vein_end_kernel<<<(a.nCells + 127) / 128, 128, 0, st>>>(a);
-    advance_step_kernel<<<1, 1, 0, st>>>(a.counters);
+    if (a.phys.useBloodFlow) BCS_LAUNCH("vein_end", st, vein_end_kernel<<<(a.nCells + 127) / 128, 128, 0, st>>>(a));
+    BCS_LAUNCH("advance_step", st, advance_step_kernel<<<1, 1, 0, st>>>(a.counters));
     BCS_CUDA(cudaGetLastError());
 }
 

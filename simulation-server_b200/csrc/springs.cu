@@ -101,8 +101,9 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
 
 void launch_springs(const SpringArgs& a, cudaStream_t st)
 {
-    springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, 0, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers, a.adjJ,
-                                                                  a.adjL, a.initR);
+    BCS_LAUNCH("springs", st,
+               springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, 0, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
+                                                                             a.adjJ, a.adjL, a.initR));
     BCS_CUDA(cudaGetLastError());
 }
 

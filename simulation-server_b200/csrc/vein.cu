@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) tri_centers_kernel(const float4* __restri
 
 void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st)
 {
-    tri_centers_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.T, centers);
+    BCS_LAUNCH("tri_centers", st, tri_centers_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.T, centers));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
 
 void launch_vein_gather(const VeinArgs& a, cudaStream_t st)
 {
-    vein_gather_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a);
+    BCS_LAUNCH("vein_gather", st, vein_gather_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
 
 void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)
 {
-    vein_integrate_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a);
+    BCS_LAUNCH("vein_integrate", st, vein_integrate_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict
 
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
 {
-    tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris);
+    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
-    if (a.stats) vein_collisions_kernel<true><<<blocks, threads, 0, st>>>(a);
-    else vein_collisions_kernel<false><<<blocks, threads, 0, st>>>(a);
+    if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true><<<blocks, threads, 0, st>>>(a));
+    else BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<false><<<blocks, threads, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 

@@ -83,8 +83,10 @@ def _compare_step(sim, orc, nsteps, tag):
         refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_FRC)[ok], refcheck.down(orc, capi.PARTICLE_FRC)[ok], f"{tag} step {step} forces after vein collisions")
         refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_VEL)[ok], refcheck.down(orc, capi.PARTICLE_VEL)[ok], f"{tag} step {step} velocities after vein collisions")
         vf = refcheck.down(orc, capi.VEIN_FRC)
-        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), vf, f"{tag} step {step} vein forces", scale=float(np.abs(vf).max()),
-                              allowed=0 if same.all() else 9)
+        # barycentric weights divide by d00*d11 - d01^2 (cancellation): FMA contraction moves them by up to ~1e-5
+        # relative, so the splats are compared at 1e-4
+        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), vf, f"{tag} step {step} vein forces", rtol=1e-4,
+                              scale=float(np.abs(vf).max()), allowed=0 if same.all() else 9)
         for st in (capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END):
             sim.run_stage(st); orc.run_stage(st)
         if same.all():
