@@ -131,6 +131,8 @@ typedef struct bcs_opts {
     int32_t semantics;          /* bcs_semantics */
     int32_t use_graph;          /* 1: bcs_step replays a captured CUDA graph (default); 0: plain launches */
     int32_t collect_stats;      /* 1: count pair tests / hits / triangle tests (slower) */
+    int32_t exhaustive_vein_traversal; /* 1: test every triangle of the 27 cells in the reference's order (slow; for
+                                          cross-checking the culled search, which yields the same result) */
     uint64_t seed;              /* counter-based respawn RNG seed (vein_end.cu:103-105 uses cuRAND seeded from time(0)) */
     void* stream;               /* cudaStream_t to enqueue on, or NULL for a library-owned stream */
 } bcs_opts;

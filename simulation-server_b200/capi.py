@@ -64,7 +64,8 @@ class SceneC(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("semantics", C.c_int32),
-                ("use_graph", C.c_int32), ("collect_stats", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_void_p)]
+                ("use_graph", C.c_int32), ("collect_stats", C.c_int32), ("exhaustive_vein_traversal", C.c_int32),
+                ("seed", C.c_uint64), ("stream", C.c_void_p)]
 
 
 class TypeInfo(C.Structure):
@@ -173,12 +174,14 @@ class Sim:
     ``integrate`` = ``propagateAll`` (main.cu:175-176,199,208)."""
 
     def __init__(self, scene: Scene, semantics: int = SEM_CLEAN, device: int = 0, use_graph: bool = True,
-                 collect_stats: bool = False, seed: int = 1234, lib: Optional[C.CDLL] = None, prefix: str = "bcs_"):
+                 collect_stats: bool = False, seed: int = 1234, lib: Optional[C.CDLL] = None, prefix: str = "bcs_",
+                 exhaustive_vein_traversal: bool = False):
         self.lib = lib if lib is not None else load_library()
         self.prefix = prefix
         self.scene = scene
         self._sh = SceneHandle(scene)
-        opts = Opts(C.sizeof(Opts), device, semantics, 1 if use_graph else 0, 1 if collect_stats else 0, seed, None)
+        opts = Opts(C.sizeof(Opts), device, semantics, 1 if use_graph else 0, 1 if collect_stats else 0,
+                    1 if exhaustive_vein_traversal else 0, seed, None)
         self._h = C.c_void_p()
         self._call("create", C.byref(self._sh.c), C.byref(opts), C.byref(self._h))
         lay = LayoutC()

@@ -118,6 +118,8 @@ struct bcs_sim {
     float4 *vpos = nullptr, *vvel = nullptr, *vfrc = nullptr, *tcent = nullptr;
     int *tkeys[2] = {nullptr, nullptr}, *tids[2] = {nullptr, nullptr}, *tcellStart = nullptr, *tcellEnd = nullptr;
     TriPacked* tris = nullptr;
+    Aabb *groupBox = nullptr, *cellBox = nullptr;
+    bool exhaustiveVein = false;
     unsigned* vidx = nullptr;
     int* nbrIds = nullptr;
     float* nbrLen = nullptr;
@@ -238,7 +240,8 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
     a.vpos = s->vpos; a.vfrc = s->vfrc; a.vidx = s->vidx;
     a.triIds = s->tids[1]; a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
-    a.tris = s->tris; a.collR = s->collR; a.counters = s->counters;
+    a.tris = s->tris; a.groupBox = s->groupBox; a.cellBox = s->cellBox; a.fast = !s->exhaustiveVein;
+    a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
     return a;
 }
@@ -376,6 +379,7 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->useGraph = opts ? opts->use_graph != 0 : true;
         s->stats = opts ? opts->collect_stats != 0 : false;
         s->seed = opts ? opts->seed : 0;
+        s->exhaustiveVein = opts ? opts->exhaustive_vein_traversal != 0 : false;
         if (opts && opts->stream) s->stream = (cudaStream_t)opts->stream;
         else { BCS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->ownStream = true; }
 
@@ -410,6 +414,8 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->vpos = s->track(dev_alloc<float4>(V)); s->vvel = s->track(dev_alloc<float4>(V)); s->vfrc = s->track(dev_alloc<float4>(V));
         s->tcent = s->track(dev_alloc<float4>(T));
         s->tris = s->track(dev_alloc<TriPacked>(T));
+        s->groupBox = s->track(dev_alloc<Aabb>((T + 7) / 8));
+        s->cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
         s->vidx = s->track(dev_upload(hs.vidx));
         s->nbrIds = s->track(dev_upload(hs.nbrIds)); s->nbrLen = s->track(dev_upload(hs.nbrLen));
         s->collR = s->track(dev_upload(hs.collR)); s->initR = s->track(dev_upload(hs.initR));
@@ -804,6 +810,7 @@ int bcs_debug_vein_hits(bcs_sim* s, int32_t* tri, float* t, int32_t n)
     float* df = dev_alloc<float>(n);
     VeinCollideArgs a = vein_collide_args(s);
     a.apply = false; a.dbgTri = dt_; a.dbgT = df;
+    a.fast = false;   // the debug view is the reference's own exhaustive traversal
     cudaError_t e = cudaSuccess;
     try {
         launch_tri_refit(a, s->stream);

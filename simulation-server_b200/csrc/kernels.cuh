@@ -108,6 +108,9 @@ struct VeinCollideArgs {
     const int* cellStart;
     const int* cellEnd;
     TriPacked* tris;            // [T] packed triangles in sorted-slot order (refit each step)
+    Aabb* groupBox;             // [(T+7)/8] padded AABB of each group of 8 sorted slots (refit each step)
+    Aabb* cellBox;              // [cells]   padded AABB of everything a cell's table range reaches
+    bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
     const float* collR;
     Counters* counters;
     bool stats;

@@ -82,24 +82,61 @@ void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)
 // Triangles are re-packed every step in sorted-slot order (the wall moves): v0, e1 = v1-v0, e2 = v2-v0.
 // The Moeller-Trumbore test only ever uses these three vectors, so the per-test gathers of the reference
 // (3 index loads + 9 coordinate loads through two indirections) become three aligned float4 loads.
+// The same pass refits the culling hierarchy: one AABB per group of 8 consecutive sorted slots.
+constexpr float BOX_PAD = 0.05f;   // covers float error of a Moeller-Trumbore "hit" that lies marginally outside its triangle
+
 __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict__ vpos, const unsigned* __restrict__ vidx,
-                                                        const int* __restrict__ triIds, int T, TriPacked* __restrict__ out)
+                                                        const int* __restrict__ triIds, int T, TriPacked* __restrict__ out,
+                                                        Aabb* __restrict__ groupBox)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= T) return;
-    const int tri = triIds[s];
-    const float3 v0 = xyz(vpos[vidx[3 * tri]]), v1 = xyz(vpos[vidx[3 * tri + 1]]), v2 = xyz(vpos[vidx[3 * tri + 2]]);
-    const float3 e1 = v1 - v0, e2 = v2 - v0;
-    TriPacked p;
-    p.a = make_float4(v0.x, v0.y, v0.z, e1.x);
-    p.b = make_float4(e1.y, e1.z, e2.x, e2.y);
-    p.c = make_float4(e2.z, __int_as_float(tri), 0.f, 0.f);
-    out[s] = p;
+    float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
+    if (s < T) {
+        const int tri = triIds[s];
+        const float3 v0 = xyz(vpos[vidx[3 * tri]]), v1 = xyz(vpos[vidx[3 * tri + 1]]), v2 = xyz(vpos[vidx[3 * tri + 2]]);
+        const float3 e1 = v1 - v0, e2 = v2 - v0;
+        TriPacked p;
+        p.a = make_float4(v0.x, v0.y, v0.z, e1.x);
+        p.b = make_float4(e1.y, e1.z, e2.x, e2.y);
+        p.c = make_float4(e2.z, __int_as_float(tri), 0.f, 0.f);
+        out[s] = p;
+        lox = fminf(v0.x, fminf(v1.x, v2.x)); hix = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+        loy = fminf(v0.y, fminf(v1.y, v2.y)); hiy = fmaxf(v0.y, fmaxf(v1.y, v2.y));
+        loz = fminf(v0.z, fminf(v1.z, v2.z)); hiz = fmaxf(v0.z, fmaxf(v1.z, v2.z));
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    if ((threadIdx.x & 7) == 0 && s < T) groupBox[s >> 3] = Aabb{lox - BOX_PAD, loy - BOX_PAD, loz - BOX_PAD, hix + BOX_PAD, hiy + BOX_PAD, hiz + BOX_PAD};
+}
+
+// AABB of everything a cell's table range [start,end] can reach (union of the slot groups it overlaps:
+// a superset, which is all the culling needs).  Works for both table semantics, including the stale /
+// zero-initialised ranges of the reference-compatible mode.
+__global__ void __launch_bounds__(128) cell_box_kernel(const int* __restrict__ cellStart, const int* __restrict__ cellEnd, int cells,
+                                                       const Aabb* __restrict__ groupBox, Aabb* __restrict__ cellBox)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int s = cellStart[c], e = cellEnd[c];
+    Aabb b{3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+    if (e >= s) {
+        for (int g = s >> 3; g <= (e >> 3); ++g) {
+            const Aabb q = groupBox[g];
+            b.lox = fminf(b.lox, q.lox); b.loy = fminf(b.loy, q.loy); b.loz = fminf(b.loz, q.loz);
+            b.hix = fmaxf(b.hix, q.hix); b.hiy = fmaxf(b.hiy, q.hiy); b.hiz = fmaxf(b.hiz, q.hiz);
+        }
+    }
+    cellBox[c] = b;
 }
 
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
 {
-    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris));
+    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox));
+    BCS_LAUNCH("cell_box", st, cell_box_kernel<<<(a.tgrid.cells + 127) / 128, 128, 0, st>>>(a.cellStart, a.cellEnd, a.tgrid.cells, a.groupBox, a.cellBox));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -159,9 +196,133 @@ __device__ __forceinline__ void tri_stencil_range(unsigned id, int count, int& l
     else { lo = -1; hi = 1; }
 }
 
-// Straight traversal in the reference's order: x outer, y, z inner, sorted triangles inside a cell;
-// the FIRST accepted triangle wins (vein_collisions.cuh:66-91).
+__device__ __forceinline__ TriPacked load_tri(const TriPacked* __restrict__ tris, int i)
+{
+    TriPacked tp;
+    tp.a = tris[i].a; tp.b = tris[i].b; tp.c = tris[i].c;
+    return tp;
+}
+
+// does the box [lo,hi] overlap the box q?
+__device__ __forceinline__ bool box_overlap(const Aabb& q, float lox, float loy, float loz, float hix, float hiy, float hiz)
+{
+    return q.lox <= hix && q.hix >= lox && q.loy <= hiy && q.hiy >= loy && q.loz <= hiz && q.hiz >= loz;
+}
+
+// does the half-line o + t*d, t >= 0, touch the (already padded) box?  Conservative slab test.
+__device__ __forceinline__ bool ray_box(const Aabb& q, const float3 o, const float3 d)
+{
+    float tn = 0.f, tf = 3e38f;
+    const float lo[3] = {q.lox, q.loy, q.loz}, hi[3] = {q.hix, q.hiy, q.hiz};
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (fabsf(dd[k]) < 1e-12f) {
+            if (oo[k] < lo[k] || oo[k] > hi[k]) return false;
+        } else {
+            const float inv = 1.0f / dd[k];
+            const float t1 = (lo[k] - oo[k]) * inv, t2 = (hi[k] - oo[k]) * inv;
+            tn = fmaxf(tn, fminf(t1, t2));
+            tf = fminf(tf, fmaxf(t1, t2));
+        }
+    }
+    return tn <= tf * 1.00001f + 1e-4f;
+}
+
+// ---- first hit in the reference's traversal order -------------------------------------------------------
+// Straight traversal: x outer, y, z inner, sorted triangles inside a cell; the FIRST accepted triangle
+// wins, however far away it is (vein_collisions.cuh:66-91).
 template <bool STATS>
+__device__ bool first_hit_naive(const VeinCollideArgs& a, const float3 pos, const float3 dir, int cell, int x0, int x1, int y0, int y1,
+                                int z0, int z1, RayHit& h, unsigned long long& tests)
+{
+    const GridDev& g = a.tgrid;
+    const int plane = g.nx * g.ny;
+    for (int x = x0; x <= x1; ++x)
+        for (int y = y0; y <= y1; ++y)
+            for (int z = z0; z <= z1; ++z) {
+                const int c = cell + z * plane + y * g.nx + x;
+                if (c < 0 || c >= g.cells) continue;
+                const int s = a.cellStart[c], e = a.cellEnd[c];
+                for (int i = s; i <= e; ++i) {
+                    if (STATS) ++tests;
+                    if (ray_triangle(pos, dir, load_tri(a.tris, i), h)) return true;
+                }
+            }
+    return false;
+}
+
+// Same RESULT for everything the stage can observe, without testing ~800 triangles per particle.
+// The stage only acts when the first hit in traversal order lies within veinImpactDistance (d^2 <= 36,
+// vein_collisions.cu:237); a far first hit does nothing, exactly like no hit.  So:
+//   phase A  find the first triangle in traversal order that the ray hits with t <= 6 (+margin): only
+//            cells / slot groups whose box overlaps the box of that short segment are touched; for a
+//            particle in the bulk of the vein that is 27 box tests and nothing else;
+//   phase B  (rare: only particles about to touch the wall) make sure no EARLIER triangle in traversal
+//            order is hit further away - such a far hit would have been returned first by the reference
+//            and would mask the near one.  Uses half-line vs box culling.
+// Returns true iff the reference's traversal ends on a triangle within reach; h = that hit.
+template <bool STATS>
+__device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const float3 dir, int cell, int x0, int x1, int y0, int y1,
+                               int z0, int z1, RayHit& h, unsigned long long& tests)
+{
+    const GridDev& g = a.tgrid;
+    const int plane = g.nx * g.ny;
+    const float reach = a.phys.impactNear;
+    const float3 tip = pos + reach * dir;
+    const float slx = fminf(pos.x, tip.x), shx = fmaxf(pos.x, tip.x);
+    const float sly = fminf(pos.y, tip.y), shy = fmaxf(pos.y, tip.y);
+    const float slz = fminf(pos.z, tip.z), shz = fmaxf(pos.z, tip.z);
+    // ---- phase A
+    int hitOrder = -1, hitSlot = -1;   // position of the near hit in traversal order: (cell ordinal, slot)
+    int ord = 0;
+    for (int x = x0; x <= x1 && hitOrder < 0; ++x)
+        for (int y = y0; y <= y1 && hitOrder < 0; ++y)
+            for (int z = z0; z <= z1 && hitOrder < 0; ++z, ++ord) {
+                const int c = cell + z * plane + y * g.nx + x;
+                if (c < 0 || c >= g.cells) continue;
+                if (!box_overlap(a.cellBox[c], slx, sly, slz, shx, shy, shz)) continue;
+                const int s = a.cellStart[c], e = a.cellEnd[c];
+                for (int gi = s >> 3; gi <= (e >> 3) && hitOrder < 0; ++gi) {
+                    if (!box_overlap(a.groupBox[gi], slx, sly, slz, shx, shy, shz)) continue;
+                    const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
+                    for (int i = i0; i <= i1; ++i) {
+                        if (STATS) ++tests;
+                        RayHit cand;
+                        if (ray_triangle(pos, dir, load_tri(a.tris, i), cand) && cand.t <= reach) {
+                            h = cand; hitOrder = ord; hitSlot = i;
+                            break;
+                        }
+                    }
+                }
+            }
+    if (hitOrder < 0) return false;
+    // ---- phase B: any hit (necessarily beyond reach) earlier in traversal order?
+    ord = 0;
+    for (int x = x0; x <= x1; ++x)
+        for (int y = y0; y <= y1; ++y)
+            for (int z = z0; z <= z1; ++z, ++ord) {
+                if (ord > hitOrder) return true;
+                const int c = cell + z * plane + y * g.nx + x;
+                if (c < 0 || c >= g.cells) continue;
+                if (!ray_box(a.cellBox[c], pos, dir)) continue;
+                const int s = a.cellStart[c];
+                const int e = (ord == hitOrder) ? hitSlot - 1 : a.cellEnd[c];
+                for (int gi = s >> 3; gi <= (e >> 3); ++gi) {
+                    if (e < s) break;
+                    if (!ray_box(a.groupBox[gi], pos, dir)) continue;
+                    const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
+                    for (int i = i0; i <= i1; ++i) {
+                        if (STATS) ++tests;
+                        RayHit far;
+                        if (ray_triangle(pos, dir, load_tri(a.tris, i), far)) return false;   // masked by an earlier (far) triangle
+                    }
+                }
+            }
+    return true;
+}
+
+template <bool FAST, bool STATS>
 __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideArgs a)
 {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,24 +341,11 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
         tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
         RayHit h;
         h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
-        bool hit = false;
-        const int plane = g.nx * g.ny;
-        for (int x = x0; x <= x1 && !hit; ++x)
-            for (int y = y0; y <= y1 && !hit; ++y)
-                for (int z = z0; z <= z1 && !hit; ++z) {
-                    const int c = cell + z * plane + y * g.nx + x;
-                    if (c < 0 || c >= g.cells) continue;
-                    const int s = a.cellStart[c], e = a.cellEnd[c];
-                    for (int i = s; i <= e; ++i) {
-                        TriPacked tp;
-                        tp.a = a.tris[i].a; tp.b = a.tris[i].b; tp.c = a.tris[i].c;
-                        if (STATS) ++myTests;
-                        if (ray_triangle(pos, dir, tp, h)) { hit = true; break; }
-                    }
-                }
+        const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
+                              : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
         if (a.dbgTri) {
             a.dbgTri[pid] = hit ? h.tri : -1;
-            a.dbgT[pid] = h.t;
+            a.dbgT[pid] = hit ? h.t : 1e10f;
         }
         // relativePosition = pos - (pos + t*dir), evaluated literally (vein_collisions.cu:234)
         const float3 rel = pos - (pos + h.t * dir);
@@ -243,8 +391,13 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
-    if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true><<<blocks, threads, 0, st>>>(a));
-    else BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<false><<<blocks, threads, 0, st>>>(a));
+    if (a.fast) {
+        if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true, true><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true, false><<<blocks, threads, 0, st>>>(a));
+    } else {
+        if (a.stats) BCS_LAUNCH("vein_collisions_exhaustive", st, vein_collisions_kernel<false, true><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("vein_collisions_exhaustive", st, vein_collisions_kernel<false, false><<<blocks, threads, 0, st>>>(a));
+    }
     BCS_CUDA(cudaGetLastError());
 }
 

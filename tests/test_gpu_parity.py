@@ -86,7 +86,7 @@ def _compare_step(sim, orc, nsteps, tag):
         # barycentric weights divide by d00*d11 - d01^2 (cancellation): FMA contraction moves them by up to ~1e-5
         # relative, so the splats are compared at 1e-4
         refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), vf, f"{tag} step {step} vein forces", rtol=1e-4,
-                              scale=float(np.abs(vf).max()), allowed=0 if same.all() else 9)
+                              scale=max(0.5, float(np.abs(vf).max())), allowed=0 if same.all() else 9)
         for st in (capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END):
             sim.run_stage(st); orc.run_stage(st)
         if same.all():
@@ -110,6 +110,37 @@ def test_vs_oracle_cylinder_scene(bcs_lib, oracle_lib):
     with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
         orc.upload_state(st)
         _compare_step(sim, orc, 8, "cylinder")
+
+
+@pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
+@pytest.mark.parametrize("which", ["cfg1_wide", "cylinder"])
+def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantics):
+    """The production vein-collision kernel (segment / half-line culling over a refitted box hierarchy) must
+    act on exactly the particles, with exactly the triangle, the reference's exhaustive in-order traversal
+    ends on - including far triangles that mask a near hit.  Bitwise equal particle outputs."""
+    if which == "cfg1_wide":
+        sc = golden_scene("cfg1")
+        st, _ = seeded_state("cfg1", "wide")
+    else:
+        sc = small_cylinder_scene(300, 300, 400.0)
+        st = pkg.make_initial_state(sc, seed=11, xz_half_width=50.0, y_range=(-25.0, -360.0))
+    total_hits = 0
+    with make_bcs(sc, semantics) as fast, make_bcs(sc, semantics, exhaustive_vein_traversal=True) as slow:
+        fast.upload_state(st)
+        for step in range(25):
+            for which_arr in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC):
+                refcheck.up(slow, which_arr, refcheck.down(fast, which_arr))
+            fast.run_stage(capi.STAGE_VEIN_COLLISIONS)
+            slow.run_stage(capi.STAGE_VEIN_COLLISIONS)
+            for which_arr in (capi.PARTICLE_FRC, capi.PARTICLE_VEL):
+                a, b = refcheck.down(fast, which_arr), refcheck.down(slow, which_arr)
+                assert np.array_equal(a, b), f"step {step}: culled and exhaustive vein collision differ for {(a != b).any(axis=1).sum()} particles"
+            refcheck.assert_close(refcheck.down(fast, capi.VEIN_FRC), refcheck.down(slow, capi.VEIN_FRC), "vein force splats", rtol=1e-5,
+                                  scale=1.0)
+            tri, t = fast.debug_vein_hits()
+            total_hits += int(((tri >= 0) & (t <= 6.0)).sum())
+            fast.step(1)
+    assert total_hits > 100
 
 
 def test_graph_and_plain_launch_agree(bcs_lib):
