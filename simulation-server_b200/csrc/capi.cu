@@ -114,6 +114,10 @@ struct bcs_sim {
     // particles
     float4 *pos = nullptr, *vel = nullptr, *frc = nullptr, *spos = nullptr, *svel = nullptr, *centers = nullptr;
     int *keys[2] = {nullptr, nullptr}, *ids[2] = {nullptr, nullptr}, *cellStart = nullptr, *cellEnd = nullptr;
+    // compact cell index of the particle grid (clean semantics; replaces cellStart/cellEnd)
+    unsigned* cellMask = nullptr;
+    int *cellRank = nullptr, *occStart = nullptr, *occKey = nullptr, *numOcc = nullptr;
+    int maskWords = 0;
     // vein
     float4 *vpos = nullptr, *vvel = nullptr, *vfrc = nullptr, *tcent = nullptr;
     int *tkeys[2] = {nullptr, nullptr}, *tids[2] = {nullptr, nullptr}, *tcellStart = nullptr, *tcellEnd = nullptr;
@@ -205,6 +209,9 @@ GridBuildArgs particle_grid_args(bcs_sim* s)
     a.scratch = &s->sortP; a.counters = s->counters;
     a.reference = s->semantics == BCS_SEM_REFERENCE;
     a.tablesValid = true;
+    a.compact = !a.reference;
+    a.cellMask = s->cellMask; a.maskWords = s->maskWords; a.cellRank = s->cellRank;
+    a.occStart = s->occStart; a.occKey = s->occKey; a.numOcc = s->numOcc;
     a.reorder = true;
     a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
     return a;
@@ -219,6 +226,7 @@ void build_triangle_grid(bcs_sim* s)
     a.scratch = &s->sortT; a.counters = s->counters;
     a.reference = s->semantics == BCS_SEM_REFERENCE;
     a.tablesValid = true;
+    a.compact = false;
     a.reorder = false;
     launch_grid_build(a, s->stream);
 }
@@ -252,6 +260,7 @@ CollideArgs collide_args(bcs_sim* s)
     a.grid = s->pg; a.types = s->types; a.phys = s->phys; a.n = s->hs.N;
     a.keys = s->keys[1]; a.spos = s->spos; a.svel = s->svel;
     a.cellStart = s->cellStart; a.cellEnd = s->cellEnd; a.collR = s->collR;
+    a.cellMask = s->cellMask; a.cellRank = s->cellRank; a.occStart = s->occStart;
     a.frc = s->frc; a.counters = s->counters;
     a.reference = s->semantics == BCS_SEM_REFERENCE; a.stats = s->stats;
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
@@ -404,12 +413,20 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
             s->keys[k] = s->track(dev_alloc<int>(N)); s->ids[k] = s->track(dev_alloc<int>(N));
             s->tkeys[k] = s->track(dev_alloc<int>(T)); s->tids[k] = s->track(dev_alloc<int>(T));
         }
-        s->cellStart = s->track(dev_alloc<int>(s->pg.cells)); s->cellEnd = s->track(dev_alloc<int>(s->pg.cells));
         s->tcellStart = s->track(dev_alloc<int>(s->tg.cells)); s->tcellEnd = s->track(dev_alloc<int>(s->tg.cells));
         if (s->semantics == BCS_SEM_CLEAN) {
-            // empty cell = (start 0, end -1); reference semantics keep the zero fill = (0,0)
-            BCS_CUDA(cudaMemset(s->cellEnd, 0xFF, (size_t)s->pg.cells * sizeof(int)));
+            // particle grid: compact cell index (1 bit + 1 rank word per 32 cells, starts per occupied cell)
+            s->maskWords = s->pg.cells / 32 + 2;
+            s->cellMask = s->track(dev_alloc<unsigned>(s->maskWords));
+            s->cellRank = s->track(dev_alloc<int>(s->maskWords));
+            s->occStart = s->track(dev_alloc<int>((size_t)N + 1));
+            s->occKey = s->track(dev_alloc<int>(N));
+            s->numOcc = s->track(dev_alloc<int>(1));
+            // triangle grid: dense tables, empty cell = (start 0, end -1)
             BCS_CUDA(cudaMemset(s->tcellEnd, 0xFF, (size_t)s->tg.cells * sizeof(int)));
+        } else {
+            // reference semantics: dense persistent tables, zero fill = (0,0)
+            s->cellStart = s->track(dev_alloc<int>(s->pg.cells)); s->cellEnd = s->track(dev_alloc<int>(s->pg.cells));
         }
         s->vpos = s->track(dev_alloc<float4>(V)); s->vvel = s->track(dev_alloc<float4>(V)); s->vfrc = s->track(dev_alloc<float4>(V));
         s->tcent = s->track(dev_alloc<float4>(T));
@@ -751,6 +768,21 @@ int bcs_download_cell_table(bcs_sim* s, int which, int32_t cap, int32_t* cells, 
     BCS_API_BEGIN
     BCS_REQUIRE(s && cells && starts && ends && count, BCS_ERR_INVALID, "null argument");
     BCS_CUDA(cudaSetDevice(s->device));
+    if (!which && s->semantics == BCS_SEM_CLEAN) {
+        // compact index: the occupied cells are stored explicitly
+        BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
+        int k = 0;
+        BCS_CUDA(cudaMemcpyAsync(&k, s->numOcc, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        *count = k;
+        BCS_REQUIRE(k <= cap, BCS_ERR_INVALID, "capacity too small for the cell table");
+        std::vector<int> st_(k + 1);
+        BCS_CUDA(cudaMemcpyAsync(cells, s->occKey, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaMemcpyAsync(st_.data(), s->occStart, (size_t)(k + 1) * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < k; ++i) { starts[i] = st_[i]; ends[i] = st_[i + 1] - 1; }
+        return BCS_OK;
+    }
     const int nc = which ? s->tg.cells : s->pg.cells;
     // debug path: copy the dense tables and compact on the host
     std::vector<int> hs_(nc), he_(nc);

@@ -108,13 +108,21 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                         }
                     }
                 } else {
-                    int lo = 0x7fffffff, hi = -1;
-                    for (int x = x0; x <= x1; ++x) {
-                        const int c = row + x;
-                        if (c < 0 || c >= g.cells) continue;
-                        const int s = a.cellStart[c], e = a.cellEnd[c];
-                        if (e >= s) { lo = min(lo, s); hi = max(hi, e); }
-                    }
+                    // occupancy bits of the row's cells [row+x0, row+x1] (adjacent cell ids, <= 3 of them)
+                    const int c0 = row + x0, nb = x1 - x0 + 1;
+                    if (c0 < 0 || c0 + nb > g.cells) continue;
+                    const int w0 = c0 >> 5, b0 = c0 & 31;
+                    const unsigned m0 = __ldg(a.cellMask + w0);
+                    unsigned bits = m0 >> b0;
+                    if (b0 + nb > 32) bits |= __ldg(a.cellMask + w0 + 1) << (32 - b0);
+                    bits &= (1u << nb) - 1u;
+                    if (!bits) continue;
+                    // occupied cells of a row have consecutive ranks and one contiguous slot range
+                    const int first = c0 + __ffs(bits) - 1;
+                    const int fw = first >> 5;
+                    const unsigned fm = (fw == w0) ? m0 : __ldg(a.cellMask + fw);
+                    const int rank = __ldg(a.cellRank + fw) + __popc(fm & ((1u << (first & 31)) - 1u));
+                    const int lo = __ldg(a.occStart + rank), hi = __ldg(a.occStart + rank + __popc(bits)) - 1;
                     for (int j = lo; j <= hi; ++j) {
                         if (j == slot) continue;
                         const float4 q4 = a.spos[j];

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int* 
 // ------------------------------------------------------------------------------------------------
 // cell tables + reorder
 // ------------------------------------------------------------------------------------------------
-// clean semantics: forget last step's occupied cells (instead of a memset of the whole table)
+// DENSE tables (reference-compatible semantics and the small static triangle grid): cellStart[c] /
+// cellEnd[c] for every cell of the grid, as in the reference (uniform_grid.cu:51-80).
 __global__ void __launch_bounds__(256) clear_cells_kernel(const int* __restrict__ sortedKeys, int n, int* __restrict__ cellStart,
                                                           int* __restrict__ cellEnd)
 {
@@ -210,6 +211,19 @@ __global__ void __launch_bounds__(256) clear_cells_kernel(const int* __restrict_
         cellStart[key] = 0;
         cellEnd[key] = -1;
     }
+}
+
+__device__ __forceinline__ void reorder_slot(int slot, int id, bool reference, const float4* __restrict__ pos,
+                                             const float4* __restrict__ vel, float4* __restrict__ spos, float4* __restrict__ svel)
+{
+    float4 p = pos[id];
+    float4 v = vel[id];
+    // canonical pos4.w already carries the particle's own collision radius (set at upload, preserved by
+    // the integrator); the reference-compatible radius lookup needs the particle id instead
+    if (reference) p.w = __int_as_float(id);
+    v.w = __int_as_float(id);
+    spos[slot] = p;
+    svel[slot] = v;
 }
 
 template <bool REFERENCE, bool REORDER>
@@ -236,16 +250,122 @@ __global__ void __launch_bounds__(256) finalize_grid_kernel(const int* __restric
         if (key != prev) cellStart[key] = slot;
         if (key != next) cellEnd[key] = slot;
     }
-    if (REORDER) {
-        const int id = ids[slot];
-        float4 p = pos[id];
-        float4 v = vel[id];
-        // canonical pos4.w already carries the particle's own collision radius (set at upload, preserved by
-        // the integrator); the reference-compatible radius lookup needs the particle id instead
-        if (REFERENCE) p.w = __int_as_float(id);
-        v.w = __int_as_float(id);
-        spos[slot] = p;
-        svel[slot] = v;
+    if (REORDER) reorder_slot(slot, ids[slot], REFERENCE, pos, vel, spos, svel);
+}
+
+// COMPACT cell index (clean semantics, particle grid).  A blood-cell scene occupies ~1-15 % of its grid
+// cells, and the reference's dense tables (2 ints per cell: 55 MB for the default vein, 490 MB for the
+// 1 M-particle long vein) would make every neighbour lookup a DRAM sector fetch.  Instead:
+//   cellMask[c/32]   bit c%32 set  <=> cell c holds particles            (1 bit per cell, L2 resident)
+//   cellRank[c/32]   number of occupied cells before word c/32           (valid where the word is non-zero)
+//   occStart[r]      first sorted slot of the r-th occupied cell; occStart[numOcc] = N
+//   occKey[r]        cell id of the r-th occupied cell
+// Cell ids are x-fastest, so the <= 3 cells of one stencil row are adjacent bits, their occupied cells
+// have consecutive ranks and their particles form one contiguous slot range:
+//   [ occStart[rank(first)], occStart[rank(first) + popc(bits)] ).
+// Same cell ids, same sorted order, same candidate sets as the dense tables.
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_ITEMS = 4;
+constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
+
+__global__ void __launch_bounds__(FIN_THREADS) count_cell_starts_kernel(const int* __restrict__ keys, int n, int* __restrict__ tileCount)
+{
+    __shared__ int warpSum[FIN_THREADS / 32];
+    const int base = blockIdx.x * FIN_TILE + threadIdx.x * FIN_ITEMS;
+    int c = 0;
+    int prev = (base > 0 && base - 1 < n) ? keys[base - 1] : -1;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k) {
+        const int slot = base + k;
+        if (slot < n) {
+            const int key = keys[slot];
+            c += (slot == 0 || key != prev);
+            prev = key;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) s += warpSum[w];
+        tileCount[blockIdx.x] = s;
+    }
+}
+
+template <bool REORDER>
+__global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int* __restrict__ keys, const int* __restrict__ ids, int n,
+                                                                       const int* __restrict__ tileCount, unsigned* __restrict__ cellMask,
+                                                                       int* __restrict__ cellRank, int* __restrict__ occStart,
+                                                                       int* __restrict__ occKey, int* __restrict__ numOcc,
+                                                                       const float4* __restrict__ pos, const float4* __restrict__ vel,
+                                                                       float4* __restrict__ spos, float4* __restrict__ svel)
+{
+    __shared__ int warpSum[FIN_THREADS / 32];
+    __shared__ int tileBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // occupied cells before this tile
+    int acc = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += FIN_THREADS) acc += tileCount[b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) warpSum[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) s += warpSum[w];
+        tileBase = s;
+    }
+    __syncthreads();
+
+    const int base = blockIdx.x * FIN_TILE + tid * FIN_ITEMS;
+    int key[FIN_ITEMS];
+    bool start[FIN_ITEMS];
+    int mine = 0;
+    int prev = (base > 0 && base - 1 < n) ? keys[base - 1] : -1;
+    const int prevOfFirst = prev;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k) {
+        const int slot = base + k;
+        key[k] = slot < n ? keys[slot] : -1;
+        start[k] = slot < n && (slot == 0 || key[k] != prev);
+        mine += start[k];
+        if (slot < n) prev = key[k];
+    }
+    // exclusive scan of `mine` over the block (thread order == slot order)
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warpSum[w];
+    int rank = tileBase + wbase + incl - mine;   // rank of the first cell STARTING in this thread's slots
+
+    prev = prevOfFirst;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k) {
+        const int slot = base + k;
+        if (slot >= n) break;
+        if (start[k]) {
+            const int c = key[k];
+            atomicOr(&cellMask[c >> 5], 1u << (c & 31));
+            occStart[rank] = slot;
+            occKey[rank] = c;
+            if (slot == 0 || (prev >> 5) != (c >> 5)) cellRank[c >> 5] = rank;   // first occupied cell of its word
+            ++rank;
+        }
+        if (slot == n - 1) {
+            occStart[rank] = n;     // rank == number of occupied cells here
+            *numOcc = rank;
+        }
+        prev = key[k];
+        if (REORDER) reorder_slot(slot, ids[slot], false, pos, vel, spos, svel);
     }
 }
 
@@ -257,12 +377,15 @@ void SortScratch::allocate(int n)
     numTiles = (n + SORT_TILE - 1) / SORT_TILE;
     BCS_CUDA(cudaMalloc(&tileHist, (size_t)numTiles * 256 * sizeof(unsigned)));
     BCS_CUDA(cudaMalloc(&digitTotals, 4 * 256 * sizeof(unsigned)));
+    BCS_CUDA(cudaMalloc(&finTileCount, (size_t)((n + FIN_TILE - 1) / FIN_TILE + 1) * sizeof(int)));
 }
 void SortScratch::release()
 {
     cudaFree(tileHist);
     cudaFree(digitTotals);
+    cudaFree(finTileCount);
     tileHist = digitTotals = nullptr;
+    finTileCount = nullptr;
 }
 
 void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
@@ -273,8 +396,8 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
     const int blocks = (n + 255) / 256;
     // buffer schedule: the last pass must land in buffer 1
     int cur = (passes & 1) ? 0 : 1;
-    if (!a.reference && a.tablesValid)
-        BCS_LAUNCH("clear_cells", st, clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd));
+    if (a.compact) BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
+    else if (!a.reference) BCS_LAUNCH("clear_cells", st, clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd));
     BCS_CUDA(cudaMemsetAsync(a.scratch->digitTotals, 0, 4 * 256 * sizeof(unsigned), st));
     const int keyBlocks = min(blocks, 148 * 8);
     BCS_LAUNCH("cell_keys", st,
@@ -291,20 +414,33 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
         cur ^= 1;
     }
     // cur == 1 here
-    if (a.reference) {
+    if (a.compact) {
+        const int tiles = (n + FIN_TILE - 1) / FIN_TILE;
+        BCS_LAUNCH("count_cell_starts", st, count_cell_starts_kernel<<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], n, a.scratch->finTileCount));
         if (a.reorder)
-            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<true, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
-                                                                     a.spos, a.svel));
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_compact_kernel<true><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.scratch->finTileCount, a.cellMask,
+                                                                                     a.cellRank, a.occStart, a.occKey, a.numOcc, a.pos, a.vel,
+                                                                                     a.spos, a.svel));
         else
-            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<true, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
-                                                                      nullptr, nullptr, nullptr));
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_compact_kernel<false><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.scratch->finTileCount, a.cellMask,
+                                                                                      a.cellRank, a.occStart, a.occKey, a.numOcc, nullptr,
+                                                                                      nullptr, nullptr, nullptr));
+    } else if (a.reference) {
+        if (a.reorder)
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_grid_kernel<true, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel, a.spos, a.svel));
+        else
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_grid_kernel<true, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr, nullptr, nullptr, nullptr));
     } else {
         if (a.reorder)
-            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<false, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel,
-                                                                      a.spos, a.svel));
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_grid_kernel<false, true><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, a.pos, a.vel, a.spos, a.svel));
         else
-            BCS_LAUNCH("finalize_grid", st, finalize_grid_kernel<false, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr,
-                                                                       nullptr, nullptr, nullptr));
+            BCS_LAUNCH("finalize_grid", st,
+                       finalize_grid_kernel<false, false><<<blocks, 256, 0, st>>>(a.keys[1], a.ids[1], n, a.cellStart, a.cellEnd, nullptr, nullptr, nullptr, nullptr));
     }
     BCS_CUDA(cudaGetLastError());
 }

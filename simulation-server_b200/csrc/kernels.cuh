@@ -10,6 +10,7 @@ struct SortScratch {
     unsigned* tileHist = nullptr;      // [numTiles][256] per-tile digit counts -> global offsets
     unsigned* digitTotals = nullptr;   // [4][256] whole-array digit counts per pass
     int numTiles = 0;
+    int* finTileCount = nullptr;       // occupied-cell starts per finalize tile (compact index build)
     void allocate(int n);
     void release();
 };
@@ -25,6 +26,13 @@ struct GridBuildArgs {
     Counters* counters;
     bool reference;           // BCS_SEM_REFERENCE table semantics
     bool tablesValid;         // clean semantics: tables hold last step's ranges (to be un-written)
+    bool compact;             // clean semantics, particle grid: build the compact cell index instead of dense tables
+    unsigned* cellMask;       // [maskWords] occupancy bits
+    int maskWords;
+    int* cellRank;            // [maskWords]
+    int* occStart;            // [n + 1]
+    int* occKey;              // [n]
+    int* numOcc;              // device scalar
     bool reorder;             // also write sorted-order copies of pos/vel
     const float4* pos;
     const float4* vel;
@@ -63,8 +71,11 @@ struct CollideArgs {
     const int* keys;            // sorted cell ids
     const float4* spos;         // sorted positions  (w: radius | particle id bits in reference mode)
     const float4* svel;         // sorted velocities (w: particle id bits)
-    const int* cellStart;
+    const int* cellStart;       // dense tables (reference-compatible semantics)
     const int* cellEnd;
+    const unsigned* cellMask;   // compact cell index (clean semantics), see grid.cu
+    const int* cellRank;
+    const int* occStart;
     const float* collR;         // [nModel] (reference-mode lookup)
     float4* frc;
     Counters* counters;

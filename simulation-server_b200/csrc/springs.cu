@@ -83,10 +83,14 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
         const int m = cellBase + j;
         const float3 dP = position - xyz(sp[m]);
         const float3 dv = velocity - xyz(sv[m]);
-        const float3 shift = normalize(-1.0f * dP);
+        // length(dP), normalize(dP) and normalize(-1*dP) of the reference share one sqrt and one set of
+        // IEEE divisions: |dP| = sqrtf(dot(dP,dP)), n = dP/|dP| (NaN -> 0), normalize(-dP) = -n exactly
+        const float len = sqrtf(dot(dP, dP));
+        float3 n = dP / len;
+        if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
         const float3 dv2 = dv + ph.dt * (initialForce - xyz(sf[m]));
-        const float s = (length(dP) - L) * ph.particle_k_sniff + dot(normalize(dP), dv2) * ph.particle_d_fact;
-        newForce = newForce + s * shift;
+        const float s = (len - L) * ph.particle_k_sniff + dot(n, dv2) * ph.particle_d_fact;
+        newForce = newForce + s * f3(-n.x, -n.y, -n.z);
     }
     // gravity + viscous damping (+ brake for over-stretched cells)
     const float ratio = length(position - sc[cell]) / __ldg(initR + ty.mStart + inCell);

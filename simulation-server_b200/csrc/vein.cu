@@ -42,8 +42,13 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
         if (nb != -1) {
             const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
             const float3 q = xyz(a.vpos[nb]);
-            const float sf = (length(p - q) - L) * a.phys.vein_k_sniff + dot(normalize(p - q), (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
-            F = F + sf * normalize(q - p);
+            // one sqrt + one set of IEEE divisions: q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q)
+            const float3 d = p - q;
+            const float len = sqrtf(dot(d, d));
+            float3 n = d / len;
+            if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
+            const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
+            F = F + sf * f3(-n.x, -n.y, -n.z);
         }
     }
     float4 f = a.vfrc[id];

@@ -130,6 +130,8 @@ def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantic
         for step in range(25):
             for which_arr in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC):
                 refcheck.up(slow, which_arr, refcheck.down(fast, which_arr))
+            tri, t = slow.debug_vein_hits()
+            total_hits += int(((tri >= 0) & (t <= 6.0)).sum())
             fast.run_stage(capi.STAGE_VEIN_COLLISIONS)
             slow.run_stage(capi.STAGE_VEIN_COLLISIONS)
             for which_arr in (capi.PARTICLE_FRC, capi.PARTICLE_VEL):
@@ -137,8 +139,6 @@ def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantic
                 assert np.array_equal(a, b), f"step {step}: culled and exhaustive vein collision differ for {(a != b).any(axis=1).sum()} particles"
             refcheck.assert_close(refcheck.down(fast, capi.VEIN_FRC), refcheck.down(slow, capi.VEIN_FRC), "vein force splats", rtol=1e-5,
                                   scale=1.0)
-            tri, t = fast.debug_vein_hits()
-            total_hits += int(((tri >= 0) & (t <= 6.0)).sum())
             fast.step(1)
     assert total_hits > 100
 
