@@ -123,6 +123,9 @@ struct bcs_sim {
     int *tkeys[2] = {nullptr, nullptr}, *tids[2] = {nullptr, nullptr}, *tcellStart = nullptr, *tcellEnd = nullptr;
     TriPacked* tris = nullptr;
     Aabb *groupBox = nullptr, *cellBox = nullptr;
+    int *cullList = nullptr, *cullCount = nullptr;
+    unsigned* doneBlocks = nullptr;
+    int maxP = 1;
     bool exhaustiveVein = false;
     unsigned* vidx = nullptr;
     int* nbrIds = nullptr;
@@ -249,6 +252,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.vpos = s->vpos; a.vfrc = s->vfrc; a.vidx = s->vidx;
     a.triIds = s->tids[1]; a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
     a.tris = s->tris; a.groupBox = s->groupBox; a.cellBox = s->cellBox; a.fast = !s->exhaustiveVein;
+    a.nCells = s->hs.B; a.maxP = s->maxP; a.cullList = s->cullList; a.cullCount = s->cullCount;
     a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
     return a;
@@ -314,7 +318,11 @@ void stage(bcs_sim* s, int st)
 
 void enqueue_step(bcs_sim* s)
 {
-    for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_END; ++st) stage(s, st);
+    // same stage order as the staged entry points; the tail (integrate particles, vein end, step counter) is one
+    // fused kernel, and the vein integrator - independent of it - follows
+    for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
+    launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, s->stream);
+    stage(s, BCS_STAGE_INTEGRATE_VEIN);
 }
 
 struct Array {
@@ -433,6 +441,10 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->tris = s->track(dev_alloc<TriPacked>(T));
         s->groupBox = s->track(dev_alloc<Aabb>((T + 7) / 8));
         s->cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
+        s->cullList = s->track(dev_alloc<int>(B));
+        s->cullCount = s->track(dev_alloc<int>(1));
+        s->doneBlocks = s->track(dev_alloc<unsigned>(1));
+        for (const HostType& h : hs.types) s->maxP = std::max(s->maxP, h.P);
         s->vidx = s->track(dev_upload(hs.vidx));
         s->nbrIds = s->track(dev_upload(hs.nbrIds)); s->nbrLen = s->track(dev_upload(hs.nbrLen));
         s->collR = s->track(dev_upload(hs.collR)); s->initR = s->track(dev_upload(hs.initR));

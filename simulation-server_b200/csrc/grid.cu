@@ -8,6 +8,9 @@
 #include "device_math.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
+#include <string>
+
 namespace bcs {
 
 // ------------------------------------------------------------------------------------------------
@@ -196,6 +199,122 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int* 
     }
 }
 
+// Single-kernel pass ("onesweep"): the same stable in-tile ranking, but the global offset of a tile's share of
+// every digit comes from a decoupled look-back over per-tile status words instead of two extra kernels and
+// an extra read of the keys.  status[tile][digit] = (flag << 30) | count, flag 1 = tile-local count,
+// flag 2 = inclusive prefix over all earlier tiles; one 32-bit word carries flag and value, so no fences
+// are needed.  Tiles are handed out by an atomic ticket, which guarantees that every tile a block waits
+// for has already started.
+constexpr unsigned STATUS_LOCAL = 1u << 30, STATUS_INCL = 2u << 30, STATUS_VALUE = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const int* __restrict__ keysIn, const int* __restrict__ valsIn,
+                                                                      int* __restrict__ keysOut, int* __restrict__ valsOut, int n,
+                                                                      int shift, const unsigned* __restrict__ digitTotals,
+                                                                      volatile unsigned* status, unsigned* ticket)
+{
+    __shared__ unsigned warpCnt[SORT_WARPS][256];
+    __shared__ unsigned binStart[256];
+    __shared__ unsigned globalBase[256];
+    __shared__ unsigned scanTmp[8];
+    __shared__ unsigned sTile;
+    __shared__ int exKeys[SORT_TILE];
+    __shared__ int exVals[SORT_TILE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&warpCnt[0][0])[i] = 0;
+    __syncthreads();
+    const int tile = (int)sTile;
+    const int tileStart = tile * SORT_TILE;
+
+    int key[SORT_ITEMS], val[SORT_ITEMS];
+    unsigned rank[SORT_ITEMS];
+    const unsigned ltMask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int idx = tileStart + warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        const bool valid = idx < n;
+        key[i] = valid ? keysIn[idx] : 0;
+        val[i] = valid ? valsIn[idx] : 0;
+        const unsigned digit = valid ? ((unsigned)(key[i] >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (valid && lane == leader) {
+            base = warpCnt[warp][digit];
+            warpCnt[warp][digit] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[i] = base + __popc(peers & ltMask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread == digit: count of the digit in this tile, exclusive prefix over warps
+    unsigned total = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+        const unsigned c = warpCnt[w][tid];
+        warpCnt[w][tid] = total;
+        total += c;
+    }
+    // publish the tile-local count as early as possible
+    status[(size_t)tile * 256 + tid] = STATUS_LOCAL | total;
+
+    // two block-wide exclusive scans over the 256 digits: tile-local starts and global bin bases
+    unsigned inclA = total, inclB = digitTotals[tid];
+    const unsigned myTotalB = inclB;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned ya = __shfl_up_sync(0xffffffffu, inclA, o), yb = __shfl_up_sync(0xffffffffu, inclB, o);
+        if (lane >= o) { inclA += ya; inclB += yb; }
+    }
+    __shared__ unsigned scanTmpB[8];
+    if (lane == 31) { scanTmp[warp] = inclA; scanTmpB[warp] = inclB; }
+    __syncthreads();
+    unsigned wa = 0, wb = 0;
+    for (int w = 0; w < warp; ++w) { wa += scanTmp[w]; wb += scanTmpB[w]; }
+    binStart[tid] = wa + inclA - total;
+    const unsigned binBase = wb + inclB - myTotalB;
+
+    // decoupled look-back over earlier tiles for this thread's digit
+    unsigned excl = 0;
+    for (int t = tile - 1; t >= 0; --t) {
+        unsigned v;
+        do { v = status[(size_t)t * 256 + tid]; } while ((v >> 30) == 0u);
+        excl += v & STATUS_VALUE;
+        if ((v >> 30) == 2u) break;
+    }
+    status[(size_t)tile * 256 + tid] = STATUS_INCL | (excl + total);
+    globalBase[tid] = binBase + excl;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int idx = tileStart + warp * (32 * SORT_ITEMS) + i * 32 + lane;
+        if (idx < n) {
+            const unsigned digit = (unsigned)(key[i] >> shift) & 255u;
+            const unsigned pos = binStart[digit] + warpCnt[warp][digit] + rank[i];
+            exKeys[pos] = key[i];
+            exVals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+
+    const int tileCount = min(SORT_TILE, n - tileStart);
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int j = i * SORT_THREADS + tid;
+        if (j < tileCount) {
+            const int k = exKeys[j];
+            const unsigned digit = (unsigned)(k >> shift) & 255u;
+            const unsigned dst = globalBase[digit] + (unsigned)j - binStart[digit];
+            keysOut[dst] = k;
+            valsOut[dst] = exVals[j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // cell tables + reorder
 // ------------------------------------------------------------------------------------------------
@@ -376,7 +495,10 @@ void SortScratch::allocate(int n)
 {
     numTiles = (n + SORT_TILE - 1) / SORT_TILE;
     BCS_CUDA(cudaMalloc(&tileHist, (size_t)numTiles * 256 * sizeof(unsigned)));
-    BCS_CUDA(cudaMalloc(&digitTotals, 4 * 256 * sizeof(unsigned)));
+    BCS_CUDA(cudaMalloc(&digitTotals, (4 * 256 + 4) * sizeof(unsigned)));   // + one tile ticket per pass
+    BCS_CUDA(cudaMalloc(&status, (size_t)4 * numTiles * 256 * sizeof(unsigned)));
+    const char* mode = getenv("BCS_SORT");
+    classic = mode && std::string(mode) == "classic";
     BCS_CUDA(cudaMalloc(&finTileCount, (size_t)((n + FIN_TILE - 1) / FIN_TILE + 1) * sizeof(int)));
 }
 void SortScratch::release()
@@ -384,6 +506,8 @@ void SortScratch::release()
     cudaFree(tileHist);
     cudaFree(digitTotals);
     cudaFree(finTileCount);
+    cudaFree(status);
+    status = nullptr;
     tileHist = digitTotals = nullptr;
     finTileCount = nullptr;
 }
@@ -398,12 +522,22 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
     int cur = (passes & 1) ? 0 : 1;
     if (a.compact) BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
     else if (!a.reference) BCS_LAUNCH("clear_cells", st, clear_cells_kernel<<<blocks, 256, 0, st>>>(a.keys[1], n, a.cellStart, a.cellEnd));
-    BCS_CUDA(cudaMemsetAsync(a.scratch->digitTotals, 0, 4 * 256 * sizeof(unsigned), st));
+    BCS_CUDA(cudaMemsetAsync(a.scratch->digitTotals, 0, (4 * 256 + 4) * sizeof(unsigned), st));
+    if (!a.scratch->classic)
+        BCS_CUDA(cudaMemsetAsync(a.scratch->status, 0, (size_t)passes * a.scratch->numTiles * 256 * sizeof(unsigned), st));
     const int keyBlocks = min(blocks, 148 * 8);
     BCS_LAUNCH("cell_keys", st,
                cell_keys_kernel<<<keyBlocks, 256, 0, st>>>(a.objPos, g, a.keys[cur], a.ids[cur], a.scratch->digitTotals, passes, a.counters));
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
+        if (!a.scratch->classic) {
+            BCS_LAUNCH("radix_onesweep", st,
+                       radix_onesweep_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(
+                           a.keys[cur], a.ids[cur], a.keys[cur ^ 1], a.ids[cur ^ 1], n, shift, a.scratch->digitTotals + 256 * p,
+                           a.scratch->status + (size_t)p * a.scratch->numTiles * 256, a.scratch->digitTotals + 4 * 256 + p));
+            cur ^= 1;
+            continue;
+        }
         BCS_LAUNCH("radix_tile_hist", st,
                    radix_tile_hist_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(a.keys[cur], n, shift, a.scratch->tileHist));
         BCS_LAUNCH("radix_scan", st,

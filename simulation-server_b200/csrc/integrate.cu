@@ -73,6 +73,87 @@ __global__ void __launch_bounds__(128) vein_end_kernel(const IntegrateArgs a)
     }
 }
 
+// Fused tail of the step used by bcs_step: integrate + vein-end test + respawn + step counter in ONE pass
+// over the particle state (the staged entry points above are kept for stage-by-stage parity tests).
+// A CTA owns whole blood cells (same mapping as the spring kernel), so the "any particle of the cell"
+// reduction of handleVeinEndsBlockSync/WarpSync is a shared-memory OR.
+constexpr int FINISH_THREADS = 256;
+
+__global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const IntegrateArgs a, const SpringPlan plan, unsigned* __restrict__ doneBlocks)
+{
+    __shared__ int sOut[FINISH_THREADS];
+    __shared__ int sCell[FINISH_THREADS];
+    const PhysDev& ph = a.phys;
+    int t = 0;
+    while (t + 1 < a.types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
+    const TypeDev ty = a.types.t[t];
+    const int G = plan.cellsPerBlock[t];
+    const int firstCell = ((int)blockIdx.x - plan.blockStart[t]) * G;
+    const int nCells = min(G, ty.count - firstCell);
+    const int nPart = nCells * ty.P;
+    const int basePart = ty.pStart + firstCell * ty.P;
+    const int tid = threadIdx.x;
+    const unsigned long long step = a.counters->step;   // read before any block can advance it (see below)
+
+    float4 x = make_float4(0, 0, 0, 0), v = x;
+    bool out = false;
+    if (tid < nPart) {
+        const float4 F = a.frc[basePart + tid];
+        v = a.vel[basePart + tid];
+        x = a.pos[basePart + tid];
+        const float3 v0 = f3(v.x, v.y, v.z);
+        const float3 v1 = v0 + ph.dt * xyz(F);
+        const float3 dx = (0.5f * ph.dt) * (v1 + v0);
+        v = make_float4(v1.x, v1.y, v1.z, v.w);
+        x = make_float4(x.x + dx.x, x.y + dx.y, x.z + dx.z, x.w);
+        if (ph.useBloodFlow) {
+            if (!ty.warpSync)
+                for (int e = 0; e < ph.nEndings; ++e) {
+                    const float r = a.endR[e];
+                    out = out || length_squared(f3(x.x - a.endC[3 * e], x.y - a.endC[3 * e + 1], x.z - a.endC[3 * e + 2])) <= r * r;
+                }
+            out = out || x.y <= ph.lowerY || x.y >= ph.upperY || x.x <= ph.leftX || x.x >= ph.rightX || x.z <= ph.backZ || x.z >= ph.frontZ;
+        }
+    }
+    sOut[tid] = out ? 1 : 0;
+    __syncthreads();
+    if (tid < nCells) {
+        int any = 0;
+        for (int k = 0; k < ty.P; ++k) any |= sOut[tid * ty.P + k];
+        sCell[tid] = any;
+        if (any) atomicAdd(&a.counters->teleported, 1ull);
+    }
+    __syncthreads();
+    if (tid < nPart) {
+        const int cell = tid / ty.P, k = tid - cell * ty.P;
+        if (sCell[cell]) {
+            unsigned ctr[4] = {(unsigned)(ty.cStart + firstCell + cell), (unsigned)step, (unsigned)(step >> 32), 0u};
+            philox4x32_10(ctr, (unsigned)a.seed, (unsigned)(a.seed >> 32));
+            const float u1 = u01(ctr[0]), u2 = u01(ctr[1]);
+            const float bx = (u1 - 0.5f) * 1.2f * ph.cylinder_radius, bz = (u2 - 0.5f) * 1.2f * ph.cylinder_radius;
+            x = make_float4(bx + a.mx[ty.mStart + k] - a.mx[ty.mStart], ph.min_spawn_y + a.my[ty.mStart + k] - a.my[ty.mStart],
+                            bz + a.mz[ty.mStart + k] - a.mz[ty.mStart], x.w);
+            v = make_float4(ph.initvx, ph.initvy, ph.initvz, v.w);
+        }
+        a.pos[basePart + tid] = x;
+        a.vel[basePart + tid] = v;
+    }
+    // the last CTA to finish advances the step counter: by then every CTA has read `step`
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(doneBlocks, 1u) == gridDim.x - 1) {
+            *doneBlocks = 0;
+            a.counters->step = step + 1;
+        }
+    }
+}
+
+void launch_finish_step(const IntegrateArgs& a, const SpringPlan& plan, unsigned* doneBlocks, cudaStream_t st)
+{
+    BCS_LAUNCH("finish_step", st, finish_step_kernel<<<plan.totalBlocks, FINISH_THREADS, 0, st>>>(a, plan, doneBlocks));
+    BCS_CUDA(cudaGetLastError());
+}
+
 __global__ void advance_step_kernel(Counters* c) { c->step += 1; }
 
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st)

@@ -11,6 +11,8 @@ struct SortScratch {
     unsigned* digitTotals = nullptr;   // [4][256] whole-array digit counts per pass
     int numTiles = 0;
     int* finTileCount = nullptr;       // occupied-cell starts per finalize tile (compact index build)
+    unsigned* status = nullptr;        // [4][numTiles][256] look-back status words of the onesweep passes
+    bool classic = false;              // BCS_SORT=classic: 3-kernel passes (histogram, scan, scatter) instead of onesweep
     void allocate(int n);
     void release();
 };
@@ -122,6 +124,10 @@ struct VeinCollideArgs {
     Aabb* groupBox;             // [(T+7)/8] padded AABB of each group of 8 sorted slots (refit each step)
     Aabb* cellBox;              // [cells]   padded AABB of everything a cell's table range reaches
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
+    int nCells;                 // blood cells
+    int maxP;                   // largest particles-per-cell over the types
+    int* cullList;              // [nCells] blood cells that may touch the wall this step
+    int* cullCount;             // device scalar
     const float* collR;
     Counters* counters;
     bool stats;
@@ -151,5 +157,7 @@ struct IntegrateArgs {
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter
+// integrate_particles + vein_end + step counter fused (bcs_step)
+void launch_finish_step(const IntegrateArgs& a, const SpringPlan& plan, unsigned* doneBlocks, cudaStream_t st);
 
 }  // namespace bcs

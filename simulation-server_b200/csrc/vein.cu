@@ -327,65 +327,134 @@ __device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const
     return true;
 }
 
+// one particle of the vein-collision stage (vein_collisions.cu:63-277)
+template <bool FAST, bool STATS>
+__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests)
+{
+    const GridDev& g = a.tgrid;
+    const PhysDev& ph = a.phys;
+    const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+    const float3 pos = xyz(p4), velocity = xyz(v4);
+    const float3 dir = normalize(velocity);
+    const int cell = axis_cell(pos.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(pos.y, g.miny, g.leny, g.csy) * g.nx +
+                     axis_cell(pos.x, g.minx, g.lenx, g.csx);
+    int x0, x1, y0, y1, z0, z1;
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
+    RayHit h;
+    h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
+    const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
+                          : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
+    if (a.dbgTri) {
+        a.dbgTri[pid] = hit ? h.tri : -1;
+        a.dbgT[pid] = hit ? h.t : 1e10f;
+    }
+    // relativePosition = pos - (pos + t*dir), evaluated literally (vein_collisions.cu:234)
+    const float3 rel = pos - (pos + h.t * dir);
+    const float d2 = length_squared(rel);
+    if (a.apply && hit && d2 <= ph.impact2) {
+        if (d2 > ph.minForce2) {
+            const float4 F4 = a.frc[pid];
+            const float3 F = xyz(F4);
+            float3 add;
+            if (ph.reactionForce) {
+                add = ((-1.0f * dot(F, h.normal)) * h.normal) / dot(h.normal, h.normal);
+            } else {
+                int t = 0;
+                while (t + 1 < a.types.n && pid >= a.types.t[t + 1].pStart) ++t;
+                const float radius = __ldg(a.collR + a.types.t[t].mStart + (pid - a.types.t[t].pStart) % a.types.t[t].P);
+                // physics::addResilientForceOnCollision(relativePosition, velocity, d2, radius, id, 0.5f, forces)
+                const float3 rdir = normalize(rel);
+                const float3 tang = velocity - dot(velocity, rdir) * rdir;
+                const float3 spring = (-ph.coll_spring * (radius * 2 - sqrtf(d2))) * rdir;
+                add = 0.5f * (spring + ph.coll_damping * velocity + ph.coll_shear * tang);
+            }
+            a.frc[pid] = make_float4(F.x + add.x, F.y + add.y, F.z + add.z, F4.w);
+        }
+        const float speed = length(velocity);
+        const float3 dv = 1.0f * ((ph.velocity_collision_damping * speed) * h.refl - velocity);   // gpuCount = 1
+        a.vel[pid] = make_float4(velocity.x + dv.x, velocity.y + dv.y, velocity.z + dv.z, v4.w);
+        const float3 ds = ph.vein_collision_force_intensity * velocity;
+        const unsigned i0 = a.vidx[3 * h.tri], i1 = a.vidx[3 * h.tri + 1], i2 = a.vidx[3 * h.tri + 2];
+        const float3 b = barycentric(pos + h.t * dir, xyz(a.vpos[i0]), xyz(a.vpos[i1]), xyz(a.vpos[i2]));
+        // the reference uses plain += here and loses updates when two particles share a vertex
+        atomicAdd(&a.vfrc[i0].x, b.x * ds.x); atomicAdd(&a.vfrc[i0].y, b.x * ds.y); atomicAdd(&a.vfrc[i0].z, b.x * ds.z);
+        atomicAdd(&a.vfrc[i1].x, b.y * ds.x); atomicAdd(&a.vfrc[i1].y, b.y * ds.y); atomicAdd(&a.vfrc[i1].z, b.y * ds.z);
+        atomicAdd(&a.vfrc[i2].x, b.z * ds.x); atomicAdd(&a.vfrc[i2].y, b.z * ds.y); atomicAdd(&a.vfrc[i2].z, b.z * ds.z);
+        atomicAdd(&a.counters->veinHits, 1ull);
+    }
+}
+
+// every particle (exhaustive cross-check mode and the debug view)
 template <bool FAST, bool STATS>
 __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideArgs a)
 {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myTests = 0;
-    if (pid < a.n) {
+    if (pid < a.n) vein_collide_particle<FAST, STATS>(a, pid, myTests);
+    if (STATS) {
+        for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
+        if ((threadIdx.x & 31) == 0 && a.apply) atomicAdd(&a.counters->triTests, myTests);
+    }
+}
+
+// Production path, step 1: one thread per BLOOD CELL.  The stage can only act on a particle that has a wall
+// triangle within veinImpactDistance along its ray, so a blood cell whose bounding box, widened by that
+// reach, overlaps none of the triangle-cell boxes its particles could visit is skipped as a whole.
+// Survivors are appended to a work list (order irrelevant: particles are independent).
+__global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideArgs a, int nCells, int* __restrict__ list,
+                                                             int* __restrict__ listCount)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (c < nCells) {
+        int t = 0;
+        while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+        const TypeDev ty = a.types.t[t];
+        const int first = ty.pStart + (c - ty.cStart) * ty.P;
+        float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
+        for (int k = 0; k < ty.P; ++k) {
+            const float4 p = a.pos[first + k];
+            lox = fminf(lox, p.x); hix = fmaxf(hix, p.x);
+            loy = fminf(loy, p.y); hiy = fmaxf(hiy, p.y);
+            loz = fminf(loz, p.z); hiz = fmaxf(hiz, p.z);
+        }
         const GridDev& g = a.tgrid;
-        const PhysDev& ph = a.phys;
-        const float4 p4 = a.pos[pid], v4 = a.vel[pid];
-        const float3 pos = xyz(p4), velocity = xyz(v4);
-        const float3 dir = normalize(velocity);
-        const int cell = axis_cell(pos.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(pos.y, g.miny, g.leny, g.csy) * g.nx +
-                         axis_cell(pos.x, g.minx, g.lenx, g.csx);
-        int x0, x1, y0, y1, z0, z1;
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
-        RayHit h;
-        h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
-        const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
-                              : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
-        if (a.dbgTri) {
-            a.dbgTri[pid] = hit ? h.tri : -1;
-            a.dbgT[pid] = hit ? h.t : 1e10f;
-        }
-        // relativePosition = pos - (pos + t*dir), evaluated literally (vein_collisions.cu:234)
-        const float3 rel = pos - (pos + h.t * dir);
-        const float d2 = length_squared(rel);
-        if (a.apply && hit && d2 <= ph.impact2) {
-            if (d2 > ph.minForce2) {
-                const float4 F4 = a.frc[pid];
-                const float3 F = xyz(F4);
-                float3 add;
-                if (ph.reactionForce) {
-                    add = ((-1.0f * dot(F, h.normal)) * h.normal) / dot(h.normal, h.normal);
-                } else {
-                    int t = 0;
-                    while (t + 1 < a.types.n && pid >= a.types.t[t + 1].pStart) ++t;
-                    const float radius = __ldg(a.collR + a.types.t[t].mStart + (pid - a.types.t[t].pStart) % a.types.t[t].P);
-                    // physics::addResilientForceOnCollision(relativePosition, velocity, d2, radius, id, 0.5f, forces)
-                    const float3 rdir = normalize(rel);
-                    const float3 tang = velocity - dot(velocity, rdir) * rdir;
-                    const float3 spring = (-ph.coll_spring * (radius * 2 - sqrtf(d2))) * rdir;
-                    add = 0.5f * (spring + ph.coll_damping * velocity + ph.coll_shear * tang);
-                }
-                a.frc[pid] = make_float4(F.x + add.x, F.y + add.y, F.z + add.z, F4.w);
-            }
-            const float speed = length(velocity);
-            const float3 dv = 1.0f * ((ph.velocity_collision_damping * speed) * h.refl - velocity);   // gpuCount = 1
-            a.vel[pid] = make_float4(velocity.x + dv.x, velocity.y + dv.y, velocity.z + dv.z, v4.w);
-            const float3 ds = ph.vein_collision_force_intensity * velocity;
-            const unsigned i0 = a.vidx[3 * h.tri], i1 = a.vidx[3 * h.tri + 1], i2 = a.vidx[3 * h.tri + 2];
-            const float3 b = barycentric(pos + h.t * dir, xyz(a.vpos[i0]), xyz(a.vpos[i1]), xyz(a.vpos[i2]));
-            // the reference uses plain += here and loses updates when two particles share a vertex
-            atomicAdd(&a.vfrc[i0].x, b.x * ds.x); atomicAdd(&a.vfrc[i0].y, b.x * ds.y); atomicAdd(&a.vfrc[i0].z, b.x * ds.z);
-            atomicAdd(&a.vfrc[i1].x, b.y * ds.x); atomicAdd(&a.vfrc[i1].y, b.y * ds.y); atomicAdd(&a.vfrc[i1].z, b.y * ds.z);
-            atomicAdd(&a.vfrc[i2].x, b.z * ds.x); atomicAdd(&a.vfrc[i2].y, b.z * ds.y); atomicAdd(&a.vfrc[i2].z, b.z * ds.z);
-            atomicAdd(&a.counters->veinHits, 1ull);
-        }
+        // triangle-grid cells any particle of the blood cell can visit: its own cell +-1 per axis (superset of
+        // the trimmed stencils of vein_collisions.cu:86-230)
+        const int cx0 = max(0, axis_cell(lox, g.minx, g.lenx, g.csx) - 1), cx1 = min(g.nx - 1, axis_cell(hix, g.minx, g.lenx, g.csx) + 1);
+        const int cy0 = max(0, axis_cell(loy, g.miny, g.leny, g.csy) - 1), cy1 = min(g.ny - 1, axis_cell(hiy, g.miny, g.leny, g.csy) + 1);
+        const int cz0 = max(0, axis_cell(loz, g.minz, g.lenz, g.csz) - 1), cz1 = min(g.nz - 1, axis_cell(hiz, g.minz, g.lenz, g.csz) + 1);
+        const float r = a.phys.impactNear;
+        lox -= r; loy -= r; loz -= r; hix += r; hiy += r; hiz += r;
+        for (int z = cz0; z <= cz1 && !keep; ++z)
+            for (int y = cy0; y <= cy1 && !keep; ++y)
+                for (int x = cx0; x <= cx1; ++x)
+                    if (box_overlap(a.cellBox[(z * g.ny + y) * g.nx + x], lox, loy, loz, hix, hiy, hiz)) { keep = true; break; }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(listCount, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = c;
+    }
+}
+
+// step 2: the particles of the listed blood cells (grid-stride over list entries x particles per cell)
+template <bool STATS>
+__global__ void __launch_bounds__(128) vein_collisions_listed_kernel(const VeinCollideArgs a, const int* __restrict__ list,
+                                                                    const int* __restrict__ listCount, int maxP)
+{
+    unsigned long long myTests = 0;
+    const long long items = (long long)(*listCount) * maxP;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+        const int c = list[w / maxP], k = (int)(w % maxP);
+        int t = 0;
+        while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+        if (k < a.types.t[t].P) vein_collide_particle<true, STATS>(a, a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k, myTests);
     }
     if (STATS) {
         for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
@@ -396,9 +465,15 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
-    if (a.fast) {
-        if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true, true><<<blocks, threads, 0, st>>>(a));
-        else BCS_LAUNCH("vein_collisions", st, vein_collisions_kernel<true, false><<<blocks, threads, 0, st>>>(a));
+    if (a.fast && a.cullList && !a.dbgTri) {
+        BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
+        BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
+        const int grid = min(blocks, 148 * 16);
+        if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<true><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+        else BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<false><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+    } else if (a.fast) {
+        if (a.stats) BCS_LAUNCH("vein_collisions_all", st, vein_collisions_kernel<true, true><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("vein_collisions_all", st, vein_collisions_kernel<true, false><<<blocks, threads, 0, st>>>(a));
     } else {
         if (a.stats) BCS_LAUNCH("vein_collisions_exhaustive", st, vein_collisions_kernel<false, true><<<blocks, threads, 0, st>>>(a));
         else BCS_LAUNCH("vein_collisions_exhaustive", st, vein_collisions_kernel<false, false><<<blocks, threads, 0, st>>>(a));

@@ -143,6 +143,26 @@ def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantic
     assert total_hits > 100
 
 
+@pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
+def test_fused_step_equals_staged_step(bcs_lib, semantics):
+    """bcs_step (fused tail kernel, culled vein search, graph replay) vs the nine staged entry points in the
+    reference's order, incl. vein-end teleports (a short vein so that blood cells reach the ending)."""
+    sc = small_cylinder_scene(120, 100, 120.0)
+    st = pkg.make_initial_state(sc, seed=5, xz_half_width=40.0, y_range=(-25.0, -95.0))
+    with make_bcs(sc, semantics) as a, make_bcs(sc, semantics) as b:
+        a.upload_state(st)
+        b.upload_state(st)
+        for step in range(60):
+            a.step(1)
+            for stage in range(9):
+                b.run_stage(stage)
+            if step % 10 == 9:
+                for which, name in ((capi.PARTICLE_POS, "pos"), (capi.PARTICLE_VEL, "vel"), (capi.PARTICLE_FRC, "frc"), (capi.VEIN_POS, "vein pos")):
+                    refcheck.assert_close(refcheck.down(a, which), refcheck.down(b, which), f"step {step} {name}", rtol=1e-4)
+        assert a.step_count() == b.step_count() == 60
+        assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
+
+
 def test_graph_and_plain_launch_agree(bcs_lib):
     sc = golden_scene("mini3")
     st, _ = seeded_state("mini3", "wide")
