@@ -123,6 +123,19 @@ struct Aabb {
     float lox, loy, loz, hix, hiy, hiz;
 };
 
+// slab { x : dmin <= n.x <= dmax } along a unit normal n
+struct CellSlab {
+    float nx, ny, nz, dmin, dmax;
+};
+
+// work item of the vein-collision stage: a blood cell that may be within reach of the wall, with the
+// triangle-grid cells (a <= 4x4x4 block starting at cx0,cy0,cz0; bit = (dz*4 + dy)*4 + dx) that may matter
+struct CullEntry {
+    int cell;
+    int cx0, cy0, cz0;
+    unsigned long long mask;
+};
+
 // ---------------------------------------------------------------------------------------------
 // host-side derived scene (meta_factory + generateBoundingSpheres equivalents), scene_host.cpp
 // ---------------------------------------------------------------------------------------------

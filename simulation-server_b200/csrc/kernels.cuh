@@ -123,10 +123,11 @@ struct VeinCollideArgs {
     TriPacked* tris;            // [T] packed triangles in sorted-slot order (refit each step)
     Aabb* groupBox;             // [(T+7)/8] padded AABB of each group of 8 sorted slots (refit each step)
     Aabb* cellBox;              // [cells]   padded AABB of everything a cell's table range reaches
+    CellSlab* cellSlab;         // [cells]   padded slab along the mean triangle normal of the same range
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
     int nCells;                 // blood cells
     int maxP;                   // largest particles-per-cell over the types
-    int* cullList;              // [nCells] blood cells that may touch the wall this step
+    CullEntry* cullList;        // [nCells] blood cells that may touch the wall this step
     int* cullCount;             // device scalar
     const float* collR;
     Counters* counters;

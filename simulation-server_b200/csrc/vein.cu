@@ -118,30 +118,69 @@ __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict
     if ((threadIdx.x & 7) == 0 && s < T) groupBox[s >> 3] = Aabb{lox - BOX_PAD, loy - BOX_PAD, loz - BOX_PAD, hix + BOX_PAD, hiy + BOX_PAD, hiz + BOX_PAD};
 }
 
-// AABB of everything a cell's table range [start,end] can reach (union of the slot groups it overlaps:
-// a superset, which is all the culling needs).  Works for both table semantics, including the stale /
-// zero-initialised ranges of the reference-compatible mode.
+// Bounds of everything a cell's table range [start,end] can reach: an AABB (union of the slot groups the range
+// overlaps - a superset, which is all the culling needs) and a SLAB along the mean normal of the cell's
+// triangles.  The wall patch of a 25-unit cell is nearly planar, so the slab is a few units thick where the
+// AABB of a diagonal patch reaches far into the lumen; together they reject almost every particle that is
+// not genuinely within reach of the wall.  Works for both table semantics, including the stale /
+// zero-initialised ranges of the reference-compatible mode.  One warp per cell.
 __global__ void __launch_bounds__(128) cell_box_kernel(const int* __restrict__ cellStart, const int* __restrict__ cellEnd, int cells,
-                                                       const Aabb* __restrict__ groupBox, Aabb* __restrict__ cellBox)
+                                                       const Aabb* __restrict__ groupBox, const TriPacked* __restrict__ tris,
+                                                       Aabb* __restrict__ cellBox, CellSlab* __restrict__ cellSlab)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cells) return;
     const int s = cellStart[c], e = cellEnd[c];
     Aabb b{3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
+    float3 nsum = f3(0.f, 0.f, 0.f);
     if (e >= s) {
-        for (int g = s >> 3; g <= (e >> 3); ++g) {
+        for (int g = (s >> 3) + lane; g <= (e >> 3); g += 32) {
             const Aabb q = groupBox[g];
             b.lox = fminf(b.lox, q.lox); b.loy = fminf(b.loy, q.loy); b.loz = fminf(b.loz, q.loz);
             b.hix = fmaxf(b.hix, q.hix); b.hiy = fmaxf(b.hiy, q.hiy); b.hiz = fmaxf(b.hiz, q.hiz);
         }
+        for (int i = s + lane; i <= e; i += 32) {
+            const TriPacked tp = tris[i];
+            nsum = nsum + cross(f3(tp.a.w, tp.b.x, tp.b.y), f3(tp.b.z, tp.b.w, tp.c.x));   // area-weighted normal
+        }
     }
-    cellBox[c] = b;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        b.lox = fminf(b.lox, __shfl_xor_sync(0xffffffffu, b.lox, o)); b.hix = fmaxf(b.hix, __shfl_xor_sync(0xffffffffu, b.hix, o));
+        b.loy = fminf(b.loy, __shfl_xor_sync(0xffffffffu, b.loy, o)); b.hiy = fmaxf(b.hiy, __shfl_xor_sync(0xffffffffu, b.hiy, o));
+        b.loz = fminf(b.loz, __shfl_xor_sync(0xffffffffu, b.loz, o)); b.hiz = fmaxf(b.hiz, __shfl_xor_sync(0xffffffffu, b.hiz, o));
+        nsum.x += __shfl_xor_sync(0xffffffffu, nsum.x, o); nsum.y += __shfl_xor_sync(0xffffffffu, nsum.y, o);
+        nsum.z += __shfl_xor_sync(0xffffffffu, nsum.z, o);
+    }
+    float3 n = normalize(nsum);
+    if (n.x == 0.f && n.y == 0.f && n.z == 0.f) n = f3(1.f, 0.f, 0.f);   // degenerate: any unit axis keeps the slab valid
+    float dmin = 3e38f, dmax = -3e38f;
+    if (e >= s) {
+        for (int i = s + lane; i <= e; i += 32) {
+            const TriPacked tp = tris[i];
+            const float3 v0 = f3(tp.a.x, tp.a.y, tp.a.z);
+            const float d0 = dot(n, v0), d1 = dot(n, v0 + f3(tp.a.w, tp.b.x, tp.b.y)), d2 = dot(n, v0 + f3(tp.b.z, tp.b.w, tp.c.x));
+            dmin = fminf(dmin, fminf(d0, fminf(d1, d2)));
+            dmax = fmaxf(dmax, fmaxf(d0, fmaxf(d1, d2)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) {
+        cellBox[c] = b;
+        cellSlab[c] = CellSlab{n.x, n.y, n.z, dmin - BOX_PAD, dmax + BOX_PAD};
+    }
 }
 
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
 {
     BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox));
-    BCS_LAUNCH("cell_box", st, cell_box_kernel<<<(a.tgrid.cells + 127) / 128, 128, 0, st>>>(a.cellStart, a.cellEnd, a.tgrid.cells, a.groupBox, a.cellBox));
+    BCS_LAUNCH("cell_box", st,
+               cell_box_kernel<<<(a.tgrid.cells * 32 + 127) / 128, 128, 0, st>>>(a.cellStart, a.cellEnd, a.tgrid.cells, a.groupBox, a.tris,
+                                                                                   a.cellBox, a.cellSlab));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -327,29 +366,13 @@ __device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const
     return true;
 }
 
-// one particle of the vein-collision stage (vein_collisions.cu:63-277)
-template <bool FAST, bool STATS>
-__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests)
+// what the stage does once the traversal has ended on triangle h (vein_collisions.cu:234-276)
+__device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid, const float4 p4, const float4 v4, const float3 dir,
+                                               const RayHit& h)
 {
-    const GridDev& g = a.tgrid;
     const PhysDev& ph = a.phys;
-    const float4 p4 = a.pos[pid], v4 = a.vel[pid];
     const float3 pos = xyz(p4), velocity = xyz(v4);
-    const float3 dir = normalize(velocity);
-    const int cell = axis_cell(pos.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(pos.y, g.miny, g.leny, g.csy) * g.nx +
-                     axis_cell(pos.x, g.minx, g.lenx, g.csx);
-    int x0, x1, y0, y1, z0, z1;
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
-    RayHit h;
-    h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
-    const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
-                          : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
-    if (a.dbgTri) {
-        a.dbgTri[pid] = hit ? h.tri : -1;
-        a.dbgT[pid] = hit ? h.t : 1e10f;
-    }
+    const bool hit = true;
     // relativePosition = pos - (pos + t*dir), evaluated literally (vein_collisions.cu:234)
     const float3 rel = pos - (pos + h.t * dir);
     const float d2 = length_squared(rel);
@@ -386,6 +409,32 @@ __device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, 
     }
 }
 
+// one particle of the vein-collision stage (vein_collisions.cu:63-277)
+template <bool FAST, bool STATS>
+__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests)
+{
+    const GridDev& g = a.tgrid;
+    const PhysDev& ph = a.phys;
+    const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+    const float3 pos = xyz(p4), velocity = xyz(v4);
+    const float3 dir = normalize(velocity);
+    const int cell = axis_cell(pos.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(pos.y, g.miny, g.leny, g.csy) * g.nx +
+                     axis_cell(pos.x, g.minx, g.lenx, g.csx);
+    int x0, x1, y0, y1, z0, z1;
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
+    RayHit h;
+    h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
+    const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
+                          : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
+    if (a.dbgTri) {
+        a.dbgTri[pid] = hit ? h.tri : -1;
+        a.dbgT[pid] = hit ? h.t : 1e10f;
+    }
+    if (hit) vein_apply_hit(a, pid, p4, v4, dir, h);
+}
+
 // every particle (exhaustive cross-check mode and the debug view)
 template <bool FAST, bool STATS>
 __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideArgs a)
@@ -399,15 +448,23 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
     }
 }
 
+// point (or ball) vs slab widened by `reach`
+__device__ __forceinline__ bool slab_near(const CellSlab& sl, float3 p, float reach)
+{
+    const float d = sl.nx * p.x + sl.ny * p.y + sl.nz * p.z;
+    return d + reach >= sl.dmin && d - reach <= sl.dmax;
+}
+
 // Production path, step 1: one thread per BLOOD CELL.  The stage can only act on a particle that has a wall
-// triangle within veinImpactDistance along its ray, so a blood cell whose bounding box, widened by that
-// reach, overlaps none of the triangle-cell boxes its particles could visit is skipped as a whole.
-// Survivors are appended to a work list (order irrelevant: particles are independent).
-__global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideArgs a, int nCells, int* __restrict__ list,
+// triangle within veinImpactDistance along its ray, so a blood cell is skipped as a whole unless its bounding
+// box, widened by that reach, meets the box AND the slab of one of the triangle-grid cells its particles can
+// visit.  Survivors are appended to a work list (order irrelevant: particles are independent) together with
+// the bit set of those triangle cells.
+__global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideArgs a, int nCells, CullEntry* __restrict__ list,
                                                              int* __restrict__ listCount)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    bool keep = false;
+    CullEntry ent{c, 0, 0, 0, 0ull};
     if (c < nCells) {
         int t = 0;
         while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
@@ -422,39 +479,136 @@ __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideA
         }
         const GridDev& g = a.tgrid;
         // triangle-grid cells any particle of the blood cell can visit: its own cell +-1 per axis (superset of
-        // the trimmed stencils of vein_collisions.cu:86-230)
+        // the trimmed stencils of vein_collisions.cu:86-230).  A blood cell wider than two triangle cells
+        // (> 4 cells per axis) keeps every cell bit set via the saturating fallback below.
         const int cx0 = max(0, axis_cell(lox, g.minx, g.lenx, g.csx) - 1), cx1 = min(g.nx - 1, axis_cell(hix, g.minx, g.lenx, g.csx) + 1);
         const int cy0 = max(0, axis_cell(loy, g.miny, g.leny, g.csy) - 1), cy1 = min(g.ny - 1, axis_cell(hiy, g.miny, g.leny, g.csy) + 1);
         const int cz0 = max(0, axis_cell(loz, g.minz, g.lenz, g.csz) - 1), cz1 = min(g.nz - 1, axis_cell(hiz, g.minz, g.lenz, g.csz) + 1);
+        ent.cx0 = cx0; ent.cy0 = cy0; ent.cz0 = cz0;
         const float r = a.phys.impactNear;
+        const float3 ctr = f3(0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
+        const float rad = 0.5f * sqrtf((hix - lox) * (hix - lox) + (hiy - loy) * (hiy - loy) + (hiz - loz) * (hiz - loz)) + r;
         lox -= r; loy -= r; loz -= r; hix += r; hiy += r; hiz += r;
-        for (int z = cz0; z <= cz1 && !keep; ++z)
-            for (int y = cy0; y <= cy1 && !keep; ++y)
-                for (int x = cx0; x <= cx1; ++x)
-                    if (box_overlap(a.cellBox[(z * g.ny + y) * g.nx + x], lox, loy, loz, hix, hiy, hiz)) { keep = true; break; }
+        if (cx1 - cx0 > 3 || cy1 - cy0 > 3 || cz1 - cz0 > 3) {
+            ent.mask = ~0ull;   // stretched blood cell: no cell-level culling, particles test their full neighbourhood
+            ent.cx0 = -1;
+        } else {
+            for (int z = cz0; z <= cz1; ++z)
+                for (int y = cy0; y <= cy1; ++y)
+                    for (int x = cx0; x <= cx1; ++x) {
+                        const int tc = (z * g.ny + y) * g.nx + x;
+                        if (box_overlap(a.cellBox[tc], lox, loy, loz, hix, hiy, hiz) && slab_near(a.cellSlab[tc], ctr, rad))
+                            ent.mask |= 1ull << (((z - cz0) * 4 + (y - cy0)) * 4 + (x - cx0));
+                    }
+        }
     }
+    const bool keep = ent.mask != 0ull;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (m) {
         const int lane = threadIdx.x & 31;
         int base = 0;
         if (lane == 0) base = atomicAdd(listCount, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = c;
+        if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = ent;
     }
+}
+
+// Phase A restricted to the triangle cells the blood-cell cull marked (any visiting order; the winner is the
+// near hit with the smallest (traversal ordinal, slot)), then the unchanged phase B of first_hit_fast.
+template <bool STATS>
+__device__ bool first_hit_marked(const VeinCollideArgs& a, const CullEntry& ent, const float3 pos, const float3 dir, int pcx, int pcy,
+                                 int pcz, int x0, int x1, int y0, int y1, int z0, int z1, RayHit& h, unsigned long long& tests)
+{
+    const GridDev& g = a.tgrid;
+    const float reach = a.phys.impactNear;
+    const float3 tip = pos + reach * dir;
+    const float slx = fminf(pos.x, tip.x), shx = fmaxf(pos.x, tip.x);
+    const float sly = fminf(pos.y, tip.y), shy = fmaxf(pos.y, tip.y);
+    const float slz = fminf(pos.z, tip.z), shz = fmaxf(pos.z, tip.z);
+    int bestKey = 1 << 30, bestSlot = -1;
+    unsigned long long m = ent.mask;
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int dx = ent.cx0 + (bit & 3) - pcx, dy = ent.cy0 + ((bit >> 2) & 3) - pcy, dz = ent.cz0 + (bit >> 4) - pcz;
+        if (dx < x0 || dx > x1 || dy < y0 || dy > y1 || dz < z0 || dz > z1) continue;   // outside this particle's stencil
+        const int key = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);                      // x outer, y, z inner
+        if (key > bestKey) continue;
+        const int c = ((pcz + dz) * g.ny + (pcy + dy)) * g.nx + (pcx + dx);
+        if (!box_overlap(a.cellBox[c], slx, sly, slz, shx, shy, shz) || !slab_near(a.cellSlab[c], pos, reach)) continue;
+        const int s = a.cellStart[c], e = a.cellEnd[c];
+        bool found = false;
+        for (int gi = s >> 3; gi <= (e >> 3) && !found; ++gi) {
+            if (!box_overlap(a.groupBox[gi], slx, sly, slz, shx, shy, shz)) continue;
+            const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
+            for (int i = i0; i <= i1; ++i) {
+                if (STATS) ++tests;
+                RayHit cand;
+                if (ray_triangle(pos, dir, load_tri(a.tris, i), cand) && cand.t <= reach) {
+                    h = cand; bestKey = key; bestSlot = i; found = true;
+                    break;
+                }
+            }
+        }
+    }
+    if (bestSlot < 0) return false;
+    // phase B: any hit (necessarily beyond reach) earlier in traversal order?
+    const int plane = g.nx * g.ny;
+    const int cell = (pcz * g.ny + pcy) * g.nx + pcx;
+    for (int x = x0; x <= x1; ++x)
+        for (int y = y0; y <= y1; ++y)
+            for (int z = z0; z <= z1; ++z) {
+                const int key = ((x + 1) * 3 + (y + 1)) * 3 + (z + 1);
+                if (key > bestKey) return true;
+                const int c = cell + z * plane + y * g.nx + x;
+                if (c < 0 || c >= g.cells) continue;
+                if (!ray_box(a.cellBox[c], pos, dir)) continue;
+                const int s = a.cellStart[c];
+                const int e = (key == bestKey) ? bestSlot - 1 : a.cellEnd[c];
+                if (e < s) continue;
+                for (int gi = s >> 3; gi <= (e >> 3); ++gi) {
+                    if (!ray_box(a.groupBox[gi], pos, dir)) continue;
+                    const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
+                    for (int i = i0; i <= i1; ++i) {
+                        if (STATS) ++tests;
+                        RayHit far;
+                        if (ray_triangle(pos, dir, load_tri(a.tris, i), far)) return false;   // masked by an earlier (far) triangle
+                    }
+                }
+            }
+    return true;
 }
 
 // step 2: the particles of the listed blood cells (grid-stride over list entries x particles per cell)
 template <bool STATS>
-__global__ void __launch_bounds__(128) vein_collisions_listed_kernel(const VeinCollideArgs a, const int* __restrict__ list,
+__global__ void __launch_bounds__(128) vein_collisions_listed_kernel(const VeinCollideArgs a, const CullEntry* __restrict__ list,
                                                                     const int* __restrict__ listCount, int maxP)
 {
     unsigned long long myTests = 0;
     const long long items = (long long)(*listCount) * maxP;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
-        const int c = list[w / maxP], k = (int)(w % maxP);
+        const CullEntry ent = list[w / maxP];
+        const int c = ent.cell, k = (int)(w % maxP);
         int t = 0;
         while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
-        if (k < a.types.t[t].P) vein_collide_particle<true, STATS>(a, a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k, myTests);
+        if (k >= a.types.t[t].P) continue;
+        const int pid = a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k;
+        if (ent.cx0 < 0) { vein_collide_particle<true, STATS>(a, pid, myTests); continue; }
+        const GridDev& g = a.tgrid;
+        const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+        const float3 pos = xyz(p4), velocity = xyz(v4);
+        const float3 dir = normalize(velocity);
+        const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
+                  pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
+        if (pcx >= g.nx || pcy >= g.ny || pcz >= g.nz) { vein_collide_particle<true, STATS>(a, pid, myTests); continue; }
+        int x0, x1, y0, y1, z0, z1;
+        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
+        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
+        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
+        RayHit h;
+        h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
+        if (first_hit_marked<STATS>(a, ent, pos, dir, pcx, pcy, pcz, x0, x1, y0, y1, z0, z1, h, myTests))
+            vein_apply_hit(a, pid, p4, v4, dir, h);
     }
     if (STATS) {
         for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
