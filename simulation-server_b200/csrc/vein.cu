@@ -11,6 +11,8 @@
 #include "device_math.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace bcs {
 
 // ------------------------------------------------------------------------------------------------
@@ -616,6 +618,210 @@ __global__ void __launch_bounds__(128) vein_collisions_listed_kernel(const VeinC
     }
 }
 
+// step 2, block-cooperative form.  The thread-per-particle search above spends > 80 % of its issue slots with
+// 5 of 32 lanes active (measured: every particle walks a different number of cells, slot groups and
+// triangles).  Here a CTA takes 128 work items at a time and turns the nested search into three flat,
+// uniformly executed passes over shared-memory queues:
+//   Q1 (particle, triangle cell)   filled per thread from the blood cell's cell mask + particle-level box/slab test
+//   Q2 (particle, slot group)      one warp per Q1 entry, one lane per slot group: segment-box vs group-box
+//   MT tests                        one lane per (Q2 entry, triangle); near hits race with a 64-bit atomicMin on
+//                                   (traversal key, slot) = the first near hit in the reference's order
+//   phase B                         one warp per particle with a near hit: lanes = the 27 stencil cells, then slot
+//                                   groups, then triangles - is there an earlier (far) hit that masks it?
+// Queue overflow (pathological clustering) falls back to the sequential search for that particle.
+constexpr int COOP_THREADS = 128;
+constexpr int Q1_CAP = 768;
+constexpr int Q2_CAP = 1024;
+
+template <bool STATS>
+__global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(const VeinCollideArgs a, const CullEntry* __restrict__ list,
+                                                                           const int* __restrict__ listCount, int maxP)
+{
+    __shared__ float4 sPos[COOP_THREADS], sDir[COOP_THREADS], sLo[COOP_THREADS], sHi[COOP_THREADS];
+    __shared__ int4 sInfo[COOP_THREADS];                       // pcx, pcy, pcz, packed stencil ranges
+    __shared__ unsigned long long sBest[COOP_THREADS];
+    __shared__ int sPid[COOP_THREADS];
+    __shared__ int sFallback[COOP_THREADS];
+    __shared__ int2 q1[Q1_CAP];
+    __shared__ int4 q2[Q2_CAP];
+    __shared__ int q3[COOP_THREADS];
+    __shared__ int q1n, q2n, q3n;
+
+    const GridDev& g = a.tgrid;
+    const float reach = a.phys.impactNear;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int plane = g.nx * g.ny;
+    unsigned long long myTests = 0;
+    const long long items = (long long)(*listCount) * maxP;
+
+    for (long long batch = (long long)blockIdx.x * COOP_THREADS; batch < items; batch += (long long)gridDim.x * COOP_THREADS) {
+        if (tid == 0) { q1n = 0; q2n = 0; q3n = 0; }
+        sBest[tid] = ~0ull;
+        sFallback[tid] = 0;
+        sPid[tid] = -1;
+        __syncthreads();
+
+        // ---- pass 0/1: load the particle, enqueue the triangle cells that can hold a near hit
+        const long long w = batch + tid;
+        if (w < items) {
+            const CullEntry ent = list[w / maxP];
+            const int c = ent.cell, k = (int)(w % maxP);
+            int t = 0;
+            while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+            if (k < a.types.t[t].P) {
+                const int pid = a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k;
+                sPid[tid] = pid;
+                const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+                const float3 pos = xyz(p4);
+                const float3 dir = normalize(xyz(v4));
+                const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
+                          pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
+                if (ent.cx0 < 0 || pcx >= g.nx || pcy >= g.ny || pcz >= g.nz) {
+                    sFallback[tid] = 1;
+                } else {
+                    int x0, x1, y0, y1, z0, z1;
+                    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
+                    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
+                    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
+                    const float3 tip = pos + reach * dir;
+                    const float slx = fminf(pos.x, tip.x), shx = fmaxf(pos.x, tip.x);
+                    const float sly = fminf(pos.y, tip.y), shy = fmaxf(pos.y, tip.y);
+                    const float slz = fminf(pos.z, tip.z), shz = fmaxf(pos.z, tip.z);
+                    sPos[tid] = make_float4(pos.x, pos.y, pos.z, 0.f);
+                    sDir[tid] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                    sLo[tid] = make_float4(slx, sly, slz, 0.f);
+                    sHi[tid] = make_float4(shx, shy, shz, 0.f);
+                    sInfo[tid] = make_int4(pcx, pcy, pcz, (x0 + 1) | ((x1 + 1) << 2) | ((y0 + 1) << 4) | ((y1 + 1) << 6) | ((z0 + 1) << 8) | ((z1 + 1) << 10));
+                    unsigned long long m = ent.mask;
+                    while (m) {
+                        const int bit = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const int dx = ent.cx0 + (bit & 3) - pcx, dy = ent.cy0 + ((bit >> 2) & 3) - pcy, dz = ent.cz0 + (bit >> 4) - pcz;
+                        if (dx < x0 || dx > x1 || dy < y0 || dy > y1 || dz < z0 || dz > z1) continue;
+                        const int tc = ((pcz + dz) * g.ny + (pcy + dy)) * g.nx + (pcx + dx);
+                        if (!box_overlap(a.cellBox[tc], slx, sly, slz, shx, shy, shz) || !slab_near(a.cellSlab[tc], pos, reach)) continue;
+                        if (a.cellEnd[tc] < a.cellStart[tc]) continue;
+                        const int key = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                        const int idx = atomicAdd(&q1n, 1);
+                        if (idx < Q1_CAP) q1[idx] = make_int2(tid | (key << 8), tc);
+                        else sFallback[tid] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 2: one warp per (particle, cell): lanes test the cell's slot groups
+        const int n1 = min(q1n, Q1_CAP);
+        for (int e1 = warp; e1 < n1; e1 += COOP_THREADS / 32) {
+            const int2 it = q1[e1];
+            const int pl = it.x & 255;
+            const int s = a.cellStart[it.y], e = a.cellEnd[it.y];
+            const float4 lo = sLo[pl], hi = sHi[pl];
+            for (int g0 = s >> 3; g0 <= (e >> 3); g0 += 32) {
+                const int gi = g0 + lane;
+                const bool ok = gi <= (e >> 3) && box_overlap(a.groupBox[gi], lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&q2n, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (ok) {
+                        const int idx = base + __popc(m & ((1u << lane) - 1u));
+                        if (idx < Q2_CAP) q2[idx] = make_int4(it.x, max(s, gi << 3), min(e, (gi << 3) + 7), 0);
+                        else sFallback[pl] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 3: one lane per (slot group, triangle): Moeller-Trumbore, near hits race for the first place
+        const int n2 = min(q2n, Q2_CAP);
+        for (int it3 = tid; it3 < n2 * 8; it3 += COOP_THREADS) {
+            const int4 q = q2[it3 >> 3];
+            const int slot = q.y + (it3 & 7);
+            if (slot > q.z) continue;
+            const int pl = q.x & 255, key = q.x >> 8;
+            if (STATS) ++myTests;
+            RayHit cand;
+            if (ray_triangle(xyz(sPos[pl]), xyz(sDir[pl]), load_tri(a.tris, slot), cand) && cand.t <= reach)
+                atomicMin(&sBest[pl], ((unsigned long long)key << 32) | (unsigned)slot);
+        }
+        __syncthreads();
+
+        // ---- pass 4: particles with a near hit go to phase B; overflowed particles take the sequential path
+        if (sPid[tid] >= 0) {
+            if (sFallback[tid]) vein_collide_particle<true, STATS>(a, sPid[tid], myTests);
+            else if (sBest[tid] != ~0ull) q3[atomicAdd(&q3n, 1)] = tid;
+        }
+        __syncthreads();
+
+        // ---- phase B: one warp per particle with a near hit
+        for (int e3 = warp; e3 < q3n; e3 += COOP_THREADS / 32) {
+            const int pl = q3[e3];
+            const float3 pos = xyz(sPos[pl]), dir = xyz(sDir[pl]);
+            const int4 info = sInfo[pl];
+            const int bestKey = (int)(sBest[pl] >> 32), bestSlot = (int)(sBest[pl] & 0xffffffffu);
+            const int x0 = (info.w & 3) - 1, x1 = ((info.w >> 2) & 3) - 1, y0 = ((info.w >> 4) & 3) - 1, y1 = ((info.w >> 6) & 3) - 1,
+                      z0 = ((info.w >> 8) & 3) - 1, z1 = ((info.w >> 10) & 3) - 1;
+            const int cell = (info.z * g.ny + info.y) * g.nx + info.x;
+            // lane == traversal key of one stencil cell (x outer, y, z inner)
+            const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
+            const int c = cell + dz * plane + dy * g.nx + dx;
+            bool visit = lane < 27 && lane <= bestKey && dx >= x0 && dx <= x1 && dy >= y0 && dy <= y1 && dz >= z0 && dz <= z1 && c >= 0 &&
+                         c < g.cells;
+            if (visit) visit = ray_box(a.cellBox[c], pos, dir);
+            unsigned cm = __ballot_sync(0xffffffffu, visit);
+            bool masked = false;
+            while (cm && !masked) {
+                const int key = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const int cc = cell + (key % 3 - 1) * plane + ((key / 3) % 3 - 1) * g.nx + (key / 9 - 1);
+                const int s = a.cellStart[cc];
+                const int e = (key == bestKey) ? bestSlot - 1 : a.cellEnd[cc];
+                if (e < s) continue;
+                for (int g0 = s >> 3; g0 <= (e >> 3) && !masked; g0 += 32) {
+                    const int gi = g0 + lane;
+                    const bool ok = gi <= (e >> 3) && ray_box(a.groupBox[gi], pos, dir);
+                    unsigned gm = __ballot_sync(0xffffffffu, ok);
+                    while (gm && !masked) {
+                        // four slot groups (32 triangles) per round
+                        int grp[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            grp[r] = gm ? g0 + __ffs(gm) - 1 : -1;
+                            gm &= gm - 1;
+                        }
+                        const int mine = grp[lane >> 3];
+                        bool hitFar = false;
+                        if (mine >= 0) {
+                            const int slot = (mine << 3) + (lane & 7);
+                            if (slot >= s && slot <= e) {
+                                if (STATS) ++myTests;
+                                RayHit far;
+                                hitFar = ray_triangle(pos, dir, load_tri(a.tris, slot), far);
+                            }
+                        }
+                        masked = __any_sync(0xffffffffu, hitFar);
+                    }
+                }
+            }
+            if (!masked && lane == 0) {
+                RayHit h;
+                ray_triangle(pos, dir, load_tri(a.tris, bestSlot), h);
+                const int pid = sPid[pl];
+                vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], dir, h);
+            }
+        }
+        __syncthreads();
+    }
+    if (STATS) {
+        for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
+        if (lane == 0 && a.apply) atomicAdd(&a.counters->triTests, myTests);
+    }
+}
+
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
@@ -623,8 +829,14 @@ void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
         BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
         BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
         const int grid = min(blocks, 148 * 16);
-        if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<true><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
-        else BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<false><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+        static const bool sequential = getenv("BCS_VEIN_SEQUENTIAL") != nullptr;
+        if (sequential) {
+            if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<true><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+            else BCS_LAUNCH("vein_collisions", st, vein_collisions_listed_kernel<false><<<grid, threads, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+        } else {
+            if (a.stats) BCS_LAUNCH("vein_collisions", st, vein_collisions_coop_kernel<true><<<grid, COOP_THREADS, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+            else BCS_LAUNCH("vein_collisions", st, vein_collisions_coop_kernel<false><<<grid, COOP_THREADS, 0, st>>>(a, a.cullList, a.cullCount, a.maxP));
+        }
     } else if (a.fast) {
         if (a.stats) BCS_LAUNCH("vein_collisions_all", st, vein_collisions_kernel<true, true><<<blocks, threads, 0, st>>>(a));
         else BCS_LAUNCH("vein_collisions_all", st, vein_collisions_kernel<true, false><<<blocks, threads, 0, st>>>(a));
