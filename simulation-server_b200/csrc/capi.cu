@@ -124,7 +124,7 @@ struct bcs_sim {
     TriPacked* tris = nullptr;
     Aabb *groupBox = nullptr, *cellBox = nullptr;
     CullEntry* cullList = nullptr;
-    CellSlab* cellSlab = nullptr;
+    CellSlab *cellSlab = nullptr, *groupSlab = nullptr;
     int* cullCount = nullptr;
     unsigned* doneBlocks = nullptr;
     int maxP = 1;
@@ -253,7 +253,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
     a.vpos = s->vpos; a.vfrc = s->vfrc; a.vidx = s->vidx;
     a.triIds = s->tids[1]; a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
-    a.tris = s->tris; a.groupBox = s->groupBox; a.cellBox = s->cellBox; a.cellSlab = s->cellSlab; a.fast = !s->exhaustiveVein;
+    a.tris = s->tris; a.groupBox = s->groupBox; a.cellBox = s->cellBox; a.cellSlab = s->cellSlab; a.groupSlab = s->groupSlab; a.fast = !s->exhaustiveVein;
     a.nCells = s->hs.B; a.maxP = s->maxP; a.cullList = s->cullList; a.cullCount = s->cullCount;
     a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
@@ -445,6 +445,7 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
         s->cullList = s->track(dev_alloc<CullEntry>(B));
         s->cellSlab = s->track(dev_alloc<CellSlab>(s->tg.cells));
+        s->groupSlab = s->track(dev_alloc<CellSlab>((T + 7) / 8));
         s->cullCount = s->track(dev_alloc<int>(1));
         s->doneBlocks = s->track(dev_alloc<unsigned>(1));
         for (const HostType& h : hs.types) s->maxP = std::max(s->maxP, h.P);

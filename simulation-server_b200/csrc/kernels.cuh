@@ -122,6 +122,7 @@ struct VeinCollideArgs {
     const int* cellEnd;
     TriPacked* tris;            // [T] packed triangles in sorted-slot order (refit each step)
     Aabb* groupBox;             // [(T+7)/8] padded AABB of each group of 8 sorted slots (refit each step)
+    CellSlab* groupSlab;        // [(T+7)/8] padded slab of the same groups along their mean normal
     Aabb* cellBox;              // [cells]   padded AABB of everything a cell's table range reaches
     CellSlab* cellSlab;         // [cells]   padded slab along the mean triangle normal of the same range
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal

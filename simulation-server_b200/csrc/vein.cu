@@ -94,10 +94,11 @@ constexpr float BOX_PAD = 0.05f;   // covers float error of a Moeller-Trumbore "
 
 __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict__ vpos, const unsigned* __restrict__ vidx,
                                                         const int* __restrict__ triIds, int T, TriPacked* __restrict__ out,
-                                                        Aabb* __restrict__ groupBox)
+                                                        Aabb* __restrict__ groupBox, CellSlab* __restrict__ groupSlab)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
+    float3 nrm = f3(0.f, 0.f, 0.f), c0 = nrm, c1 = nrm, c2 = nrm;
     if (s < T) {
         const int tri = triIds[s];
         const float3 v0 = xyz(vpos[vidx[3 * tri]]), v1 = xyz(vpos[vidx[3 * tri + 1]]), v2 = xyz(vpos[vidx[3 * tri + 2]]);
@@ -110,6 +111,8 @@ __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict
         lox = fminf(v0.x, fminf(v1.x, v2.x)); hix = fmaxf(v0.x, fmaxf(v1.x, v2.x));
         loy = fminf(v0.y, fminf(v1.y, v2.y)); hiy = fmaxf(v0.y, fmaxf(v1.y, v2.y));
         loz = fminf(v0.z, fminf(v1.z, v2.z)); hiz = fmaxf(v0.z, fmaxf(v1.z, v2.z));
+        nrm = cross(e1, e2);   // area-weighted normal
+        c0 = v0; c1 = v1; c2 = v2;
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -117,7 +120,28 @@ __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict
         loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
         loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
     }
-    if ((threadIdx.x & 7) == 0 && s < T) groupBox[s >> 3] = Aabb{lox - BOX_PAD, loy - BOX_PAD, loz - BOX_PAD, hix + BOX_PAD, hiy + BOX_PAD, hiz + BOX_PAD};
+    // slab of the group along its mean normal (a wall patch of 8 triangles is nearly planar)
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        nrm.x += __shfl_xor_sync(0xffffffffu, nrm.x, o); nrm.y += __shfl_xor_sync(0xffffffffu, nrm.y, o);
+        nrm.z += __shfl_xor_sync(0xffffffffu, nrm.z, o);
+    }
+    float3 n = normalize(nrm);
+    if (n.x == 0.f && n.y == 0.f && n.z == 0.f) n = f3(1.f, 0.f, 0.f);
+    float dmin = 3e38f, dmax = -3e38f;
+    if (s < T) {
+        const float d0 = dot(n, c0), d1 = dot(n, c1), d2 = dot(n, c2);
+        dmin = fminf(d0, fminf(d1, d2)); dmax = fmaxf(d0, fmaxf(d1, d2));
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if ((threadIdx.x & 7) == 0 && s < T) {
+        groupBox[s >> 3] = Aabb{lox - BOX_PAD, loy - BOX_PAD, loz - BOX_PAD, hix + BOX_PAD, hiy + BOX_PAD, hiz + BOX_PAD};
+        groupSlab[s >> 3] = CellSlab{n.x, n.y, n.z, dmin - BOX_PAD, dmax + BOX_PAD};
+    }
 }
 
 // Bounds of everything a cell's table range [start,end] can reach: an AABB (union of the slot groups the range
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(128) cell_box_kernel(const int* __restrict__ c
 
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
 {
-    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox));
+    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox, a.groupSlab));
     BCS_LAUNCH("cell_box", st,
                cell_box_kernel<<<(a.tgrid.cells * 32 + 127) / 128, 128, 0, st>>>(a.cellStart, a.cellEnd, a.tgrid.cells, a.groupBox, a.tris,
                                                                                    a.cellBox, a.cellSlab));
@@ -457,6 +481,14 @@ __device__ __forceinline__ bool slab_near(const CellSlab& sl, float3 p, float re
     return d + reach >= sl.dmin && d - reach <= sl.dmax;
 }
 
+// segment p .. p + reach*dir vs slab
+__device__ __forceinline__ bool slab_segment(const CellSlab& sl, float3 p, float3 dir, float reach)
+{
+    const float d0 = sl.nx * p.x + sl.ny * p.y + sl.nz * p.z;
+    const float d1 = d0 + reach * (sl.nx * dir.x + sl.ny * dir.y + sl.nz * dir.z);
+    return fmaxf(d0, d1) + 1e-3f >= sl.dmin && fminf(d0, d1) - 1e-3f <= sl.dmax;
+}
+
 // Production path, step 1: one thread per BLOOD CELL.  The stage can only act on a particle that has a wall
 // triangle within veinImpactDistance along its ray, so a blood cell is skipped as a whole unless its bounding
 // box, widened by that reach, meets the box AND the slab of one of the triangle-grid cells its particles can
@@ -465,54 +497,57 @@ __device__ __forceinline__ bool slab_near(const CellSlab& sl, float3 p, float re
 __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideArgs a, int nCells, CullEntry* __restrict__ list,
                                                              int* __restrict__ listCount)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    CullEntry ent{c, 0, 0, 0, 0ull};
-    if (c < nCells) {
-        int t = 0;
-        while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
-        const TypeDev ty = a.types.t[t];
-        const int first = ty.pStart + (c - ty.cStart) * ty.P;
-        float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
-        for (int k = 0; k < ty.P; ++k) {
-            const float4 p = a.pos[first + k];
-            lox = fminf(lox, p.x); hix = fmaxf(hix, p.x);
-            loy = fminf(loy, p.y); hiy = fmaxf(hiy, p.y);
-            loz = fminf(loz, p.z); hiz = fmaxf(hiz, p.z);
-        }
-        const GridDev& g = a.tgrid;
-        // triangle-grid cells any particle of the blood cell can visit: its own cell +-1 per axis (superset of
-        // the trimmed stencils of vein_collisions.cu:86-230).  A blood cell wider than two triangle cells
-        // (> 4 cells per axis) keeps every cell bit set via the saturating fallback below.
-        const int cx0 = max(0, axis_cell(lox, g.minx, g.lenx, g.csx) - 1), cx1 = min(g.nx - 1, axis_cell(hix, g.minx, g.lenx, g.csx) + 1);
-        const int cy0 = max(0, axis_cell(loy, g.miny, g.leny, g.csy) - 1), cy1 = min(g.ny - 1, axis_cell(hiy, g.miny, g.leny, g.csy) + 1);
-        const int cz0 = max(0, axis_cell(loz, g.minz, g.lenz, g.csz) - 1), cz1 = min(g.nz - 1, axis_cell(hiz, g.minz, g.lenz, g.csz) + 1);
-        ent.cx0 = cx0; ent.cy0 = cy0; ent.cz0 = cz0;
+    // one WARP per blood cell: lanes = particles for the bounding box, then lanes = candidate triangle cells
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nCells) return;
+    int t = 0;
+    while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+    const TypeDev ty = a.types.t[t];
+    const int first = ty.pStart + (c - ty.cStart) * ty.P;
+    float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
+    for (int k = lane; k < ty.P; k += 32) {
+        const float4 p = a.pos[first + k];
+        lox = fminf(lox, p.x); hix = fmaxf(hix, p.x);
+        loy = fminf(loy, p.y); hiy = fmaxf(hiy, p.y);
+        loz = fminf(loz, p.z); hiz = fmaxf(hiz, p.z);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    const GridDev& g = a.tgrid;
+    // triangle-grid cells any particle of the blood cell can visit: its own cell +-1 per axis (superset of
+    // the trimmed stencils of vein_collisions.cu:86-230)
+    const int cx0 = max(0, axis_cell(lox, g.minx, g.lenx, g.csx) - 1), cx1 = min(g.nx - 1, axis_cell(hix, g.minx, g.lenx, g.csx) + 1);
+    const int cy0 = max(0, axis_cell(loy, g.miny, g.leny, g.csy) - 1), cy1 = min(g.ny - 1, axis_cell(hiy, g.miny, g.leny, g.csy) + 1);
+    const int cz0 = max(0, axis_cell(loz, g.minz, g.lenz, g.csz) - 1), cz1 = min(g.nz - 1, axis_cell(hiz, g.minz, g.lenz, g.csz) + 1);
+    CullEntry ent{c, cx0, cy0, cz0, 0ull};
+    if (cx1 - cx0 > 3 || cy1 - cy0 > 3 || cz1 - cz0 > 3) {
+        // stretched blood cell (> 4 triangle cells per axis): no cell-level culling, its particles search their full stencil
+        ent.mask = ~0ull;
+        ent.cx0 = -1;
+    } else {
         const float r = a.phys.impactNear;
         const float3 ctr = f3(0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
         const float rad = 0.5f * sqrtf((hix - lox) * (hix - lox) + (hiy - loy) * (hiy - loy) + (hiz - loz) * (hiz - loz)) + r;
         lox -= r; loy -= r; loz -= r; hix += r; hiy += r; hiz += r;
-        if (cx1 - cx0 > 3 || cy1 - cy0 > 3 || cz1 - cz0 > 3) {
-            ent.mask = ~0ull;   // stretched blood cell: no cell-level culling, particles test their full neighbourhood
-            ent.cx0 = -1;
-        } else {
-            for (int z = cz0; z <= cz1; ++z)
-                for (int y = cy0; y <= cy1; ++y)
-                    for (int x = cx0; x <= cx1; ++x) {
-                        const int tc = (z * g.ny + y) * g.nx + x;
-                        if (box_overlap(a.cellBox[tc], lox, loy, loz, hix, hiy, hiz) && slab_near(a.cellSlab[tc], ctr, rad))
-                            ent.mask |= 1ull << (((z - cz0) * 4 + (y - cy0)) * 4 + (x - cx0));
-                    }
+        unsigned half[2];
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            const int bit = lane + 32 * hb;
+            const int x = cx0 + (bit & 3), y = cy0 + ((bit >> 2) & 3), z = cz0 + (bit >> 4);
+            bool pass = x <= cx1 && y <= cy1 && z <= cz1;
+            if (pass) {
+                const int tc = (z * g.ny + y) * g.nx + x;
+                pass = box_overlap(a.cellBox[tc], lox, loy, loz, hix, hiy, hiz) && slab_near(a.cellSlab[tc], ctr, rad);
+            }
+            half[hb] = __ballot_sync(0xffffffffu, pass);
         }
+        ent.mask = (unsigned long long)half[0] | ((unsigned long long)half[1] << 32);
     }
-    const bool keep = ent.mask != 0ull;
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(listCount, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = ent;
-    }
+    if (lane == 0 && ent.mask != 0ull) list[atomicAdd(listCount, 1)] = ent;
 }
 
 // Phase A restricted to the triangle cells the blood-cell cull marked (any visiting order; the winner is the
@@ -645,7 +680,9 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
     __shared__ int2 q1[Q1_CAP];
     __shared__ int4 q2[Q2_CAP];
     __shared__ int q3[COOP_THREADS];
-    __shared__ int q1n, q2n, q3n;
+    __shared__ int q1n, q2n, q3n, q1Total;
+    __shared__ int q1Off[Q1_CAP];
+    __shared__ int sWarpTot[COOP_THREADS / 32];
 
     const GridDev& g = a.tgrid;
     const float reach = a.phys.impactNear;
@@ -699,7 +736,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
                         const int dx = ent.cx0 + (bit & 3) - pcx, dy = ent.cy0 + ((bit >> 2) & 3) - pcy, dz = ent.cz0 + (bit >> 4) - pcz;
                         if (dx < x0 || dx > x1 || dy < y0 || dy > y1 || dz < z0 || dz > z1) continue;
                         const int tc = ((pcz + dz) * g.ny + (pcy + dy)) * g.nx + (pcx + dx);
-                        if (!box_overlap(a.cellBox[tc], slx, sly, slz, shx, shy, shz) || !slab_near(a.cellSlab[tc], pos, reach)) continue;
+                        if (!box_overlap(a.cellBox[tc], slx, sly, slz, shx, shy, shz) || !slab_segment(a.cellSlab[tc], pos, dir, reach)) continue;
                         if (a.cellEnd[tc] < a.cellStart[tc]) continue;
                         const int key = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
                         const int idx = atomicAdd(&q1n, 1);
@@ -711,27 +748,59 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
         }
         __syncthreads();
 
-        // ---- pass 2: one warp per (particle, cell): lanes test the cell's slot groups
+        // ---- pass 2: one lane per (particle, cell, slot group).  The (entry, group) pairs are flattened with an
+        // exclusive scan over the entries' group counts, so every lane has a box test to do (a warp per entry
+        // left 2/3 of the lanes idle: a 25-unit cell holds ~10 groups).
         const int n1 = min(q1n, Q1_CAP);
-        for (int e1 = warp; e1 < n1; e1 += COOP_THREADS / 32) {
-            const int2 it = q1[e1];
+        {
+            constexpr int PER = (Q1_CAP + COOP_THREADS - 1) / COOP_THREADS;
+            int cnt[PER], sum = 0;
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int e1 = tid * PER + r;
+                cnt[r] = 0;
+                if (e1 < n1) {
+                    const int tc = q1[e1].y;
+                    cnt[r] = (a.cellEnd[tc] >> 3) - (a.cellStart[tc] >> 3) + 1;
+                }
+                sum += cnt[r];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) sWarpTot[warp] = incl;
+            __syncthreads();
+            int run = incl - sum;
+            for (int w2 = 0; w2 < warp; ++w2) run += sWarpTot[w2];
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int e1 = tid * PER + r;
+                if (e1 < n1) q1Off[e1] = run;
+                run += cnt[r];
+            }
+            if (tid == COOP_THREADS - 1) q1Total = run;
+            __syncthreads();
+        }
+        for (int f = tid; f < q1Total; f += COOP_THREADS) {
+            // entry whose range [off, off + groups) contains f
+            int lo1 = 0, hi1 = n1 - 1;
+            while (lo1 < hi1) {
+                const int mid = (lo1 + hi1 + 1) >> 1;
+                if (q1Off[mid] <= f) lo1 = mid; else hi1 = mid - 1;
+            }
+            const int2 it = q1[lo1];
             const int pl = it.x & 255;
             const int s = a.cellStart[it.y], e = a.cellEnd[it.y];
+            const int gi = (s >> 3) + (f - q1Off[lo1]);
             const float4 lo = sLo[pl], hi = sHi[pl];
-            for (int g0 = s >> 3; g0 <= (e >> 3); g0 += 32) {
-                const int gi = g0 + lane;
-                const bool ok = gi <= (e >> 3) && box_overlap(a.groupBox[gi], lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&q2n, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (ok) {
-                        const int idx = base + __popc(m & ((1u << lane) - 1u));
-                        if (idx < Q2_CAP) q2[idx] = make_int4(it.x, max(s, gi << 3), min(e, (gi << 3) + 7), 0);
-                        else sFallback[pl] = 1;
-                    }
-                }
+            if (box_overlap(a.groupBox[gi], lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) &&
+                slab_segment(a.groupSlab[gi], xyz(sPos[pl]), xyz(sDir[pl]), reach)) {
+                const int idx = atomicAdd(&q2n, 1);
+                if (idx < Q2_CAP) q2[idx] = make_int4(it.x, max(s, gi << 3), min(e, (gi << 3) + 7), 0);
+                else sFallback[pl] = 1;
             }
         }
         __syncthreads();
@@ -787,13 +856,13 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
                     unsigned gm = __ballot_sync(0xffffffffu, ok);
                     while (gm && !masked) {
                         // four slot groups (32 triangles) per round
-                        int grp[4];
+                        int mine = -1;
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
-                            grp[r] = gm ? g0 + __ffs(gm) - 1 : -1;
+                            const int gsel = gm ? g0 + __ffs(gm) - 1 : -1;
                             gm &= gm - 1;
+                            if ((lane >> 3) == r) mine = gsel;
                         }
-                        const int mine = grp[lane >> 3];
                         bool hitFar = false;
                         if (mine >= 0) {
                             const int slot = (mine << 3) + (lane & 7);
@@ -827,7 +896,7 @@ void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
     if (a.fast && a.cullList && !a.dbgTri) {
         BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
-        BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
+        BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells * 32 + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
         const int grid = min(blocks, 148 * 16);
         static const bool sequential = getenv("BCS_VEIN_SEQUENTIAL") != nullptr;
         if (sequential) {
