@@ -67,8 +67,10 @@ struct TypeDev {            // one blood-cell type in final (meta-factory) order
     int cStart;             // bloodCellTypesStarts
     int mStart;             // bloodCellModelStarts
     int warpSync;           // reference would use handleVeinEndsWarpSync (no ending-sphere test)
-    int adjStart;           // offset of this type's adjacency (ELL) in adjJ/adjL
+    int adjStart;           // offset of this type's adjacency (ELL) in adjJ/adjL (and of the incidence list adjS)
     int maxDeg;             // ELL width
+    int sprStart;           // offset of this type's undirected spring list in sprAB/sprL
+    int nSpr;               // undirected springs per cell
 };
 
 struct TypesDev {
@@ -153,6 +155,12 @@ struct HostScene {
     std::vector<int32_t> adjJ;              // ELL adjacency per type: [adjStart + d*P + i] = mate index j (or -1)
     std::vector<float> adjL;                // spring length
     std::vector<int> adjStart, maxDeg;
+    // undirected spring list per type (a < b) and, parallel to adjJ, the spring each adjacency entry refers to
+    // (bit 31 set: the particle is the b end, i.e. the stored force enters with a minus sign)
+    std::vector<int32_t> sprAB;             // a | b << 16
+    std::vector<float> sprL;
+    std::vector<int32_t> adjS;
+    std::vector<int> sprStart, nSpr;
     float gmin[3], gmax[3], gsize[3];
     std::vector<float> vx, vy, vz;
     std::vector<uint32_t> vidx;

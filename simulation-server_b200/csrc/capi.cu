@@ -134,8 +134,8 @@ struct bcs_sim {
     float* nbrLen = nullptr;
     // tables
     float *collR = nullptr, *initR = nullptr, *mx = nullptr, *my = nullptr, *mz = nullptr, *endC = nullptr, *endR = nullptr;
-    int* adjJ = nullptr;
-    float* adjL = nullptr;
+    int *adjJ = nullptr, *adjS = nullptr, *sprAB = nullptr;
+    float *adjL = nullptr, *sprL = nullptr;
     Counters* counters = nullptr;
     float* staging = nullptr;   // 3 * maxLen floats
     int stagingLen = 0;
@@ -297,7 +297,7 @@ void stage(bcs_sim* s, int st)
         SpringArgs a{};
         a.types = s->types; a.plan = s->plan; a.phys = s->phys;
         a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
-        a.adjJ = s->adjJ; a.adjL = s->adjL; a.initR = s->initR;
+        a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
         launch_springs(a, s->stream);
         break;
     }
@@ -409,7 +409,7 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->types.n = (int)hs.types.size();
         for (int i = 0; i < s->types.n; ++i) {
             const HostType& h = hs.types[i];
-            s->types.t[i] = TypeDev{h.count, h.P, h.pStart, h.cStart, h.mStart, h.warpSync, hs.adjStart[i], hs.maxDeg[i]};
+            s->types.t[i] = TypeDev{h.count, h.P, h.pStart, h.cStart, h.mStart, h.warpSync, hs.adjStart[i], hs.maxDeg[i], hs.sprStart[i], hs.nSpr[i]};
         }
         s->plan = make_spring_plan(s->types);
         s->pg = make_grid(hs, hs.cellSize, hs.gdims, N);
@@ -455,6 +455,7 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         s->mx = s->track(dev_upload(hs.mx)); s->my = s->track(dev_upload(hs.my)); s->mz = s->track(dev_upload(hs.mz));
         s->endC = s->track(dev_upload(hs.endC)); s->endR = s->track(dev_upload(hs.endR));
         s->adjJ = s->track(dev_upload(hs.adjJ)); s->adjL = s->track(dev_upload(hs.adjL));
+        s->adjS = s->track(dev_upload(hs.adjS)); s->sprAB = s->track(dev_upload(hs.sprAB)); s->sprL = s->track(dev_upload(hs.sprL));
         s->counters = s->track(dev_alloc<Counters>(1));
         s->stagingLen = std::max(std::max(N, V), std::max(B, T));
         s->staging = s->track(dev_alloc<float>(3 * (size_t)s->stagingLen));

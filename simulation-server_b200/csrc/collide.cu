@@ -88,10 +88,10 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
         int cnt = 0;
         unsigned long long sum = 0;
         const int plane = g.nx * g.ny;
-        for (int z = z0; z <= z1; ++z) {
-            for (int y = y0; y <= y1; ++y) {
-                const int row = cell + z * plane + y * g.nx;
-                if (REFERENCE) {
+        if (REFERENCE) {
+            for (int z = z0; z <= z1; ++z) {
+                for (int y = y0; y <= y1; ++y) {
+                    const int row = cell + z * plane + y * g.nx;
                     // tables may hold stale ranges: every cell is scanned on its own, exactly as stored
                     for (int x = x0; x <= x1; ++x) {
                         const int c = row + x;
@@ -107,32 +107,45 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                             if (STATS) ++myTests;
                         }
                     }
-                } else {
-                    // occupancy bits of the row's cells [row+x0, row+x1] (adjacent cell ids, <= 3 of them)
-                    const int c0 = row + x0, nb = x1 - x0 + 1;
-                    if (c0 < 0 || c0 + nb > g.cells) continue;
-                    const int w0 = c0 >> 5, b0 = c0 & 31;
-                    const unsigned m0 = __ldg(a.cellMask + w0);
-                    unsigned bits = m0 >> b0;
-                    if (b0 + nb > 32) bits |= __ldg(a.cellMask + w0 + 1) << (32 - b0);
-                    bits &= (1u << nb) - 1u;
-                    if (!bits) continue;
-                    // occupied cells of a row have consecutive ranks and one contiguous slot range
-                    const int first = c0 + __ffs(bits) - 1;
-                    const int fw = first >> 5;
-                    const unsigned fm = (fw == w0) ? m0 : __ldg(a.cellMask + fw);
-                    const int rank = __ldg(a.cellRank + fw) + __popc(fm & ((1u << (first & 31)) - 1u));
-                    const int lo = __ldg(a.occStart + rank), hi = __ldg(a.occStart + rank + __popc(bits)) - 1;
-                    for (int j = lo; j <= hi; ++j) {
-                        if (j == slot) continue;
-                        const float4 q4 = a.spos[j];
-                        if (DEBUG) {
-                            const int qid = __float_as_int(a.svel[j].w);
-                            ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
-                        }
-                        test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);
-                        if (STATS) ++myTests;
+                }
+            }
+        } else {
+            // pass 1 (branch-free, all lanes alike): occupancy bits of the 9 stencil rows.  A row is the <= 3
+            // x-adjacent cells [row+x0, row+x1]: adjacent cell ids, i.e. adjacent bits of the occupancy mask.
+            const int nb = x1 - x0 + 1;
+            const unsigned nbm = (1u << nb) - 1u;
+            unsigned occ = 0;   // 3 bits per row, row r = (dz+1)*3 + (dy+1)
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const int dz = r / 3 - 1, dy = r % 3 - 1;
+                const int c0 = cell + dz * plane + dy * g.nx + x0;
+                const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
+                unsigned bits = 0;
+                if (in) {
+                    const int w0 = c0 >> 5;
+                    bits = __funnelshift_r(__ldg(a.cellMask + w0), __ldg(a.cellMask + w0 + 1), c0 & 31) & nbm;
+                }
+                occ |= bits << (3 * r);
+            }
+            // pass 2: only the non-empty rows.  Occupied cells of a row have consecutive ranks and ONE contiguous
+            // slot range [occStart[rank(first)], occStart[rank(first) + popc(bits)]).
+            while (occ) {
+                const int r = (__ffs(occ) - 1) / 3;
+                const unsigned bits = (occ >> (3 * r)) & 7u;
+                occ &= ~(7u << (3 * r));
+                const int first = cell + (r / 3 - 1) * plane + (r % 3 - 1) * g.nx + x0 + __ffs(bits) - 1;
+                const int fw = first >> 5;
+                const int rank = __ldg(a.cellRank + fw) + __popc(__ldg(a.cellMask + fw) & ((1u << (first & 31)) - 1u));
+                const int lo = __ldg(a.occStart + rank), hi = __ldg(a.occStart + rank + __popc(bits)) - 1;
+                for (int j = lo; j <= hi; ++j) {
+                    if (j == slot) continue;
+                    const float4 q4 = a.spos[j];
+                    if (DEBUG) {
+                        const int qid = __float_as_int(a.svel[j].w);
+                        ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
                     }
+                    test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);
+                    if (STATS) ++myTests;
                 }
             }
         }

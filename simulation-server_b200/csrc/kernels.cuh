@@ -47,6 +47,7 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st);
 struct SpringPlan {
     int blockStart[BCS_MAX_TYPES + 1];   // first block of each type
     int cellsPerBlock[BCS_MAX_TYPES];
+    bool pairwise[BCS_MAX_TYPES];        // springs evaluated once per undirected spring (shared-memory exchange)
     int totalBlocks;
 };
 SpringPlan make_spring_plan(const TypesDev& types);
@@ -58,8 +59,11 @@ struct SpringArgs {
     const float4* vel;
     float4* frc;
     float4* centers;            // [B]
-    const int* adjJ;
-    const float* adjL;
+    const int* adjJ;            // ELL adjacency: mate index per (degree slot, particle-in-cell)
+    const float* adjL;          //                rest length
+    const int* adjS;            //                undirected spring index (bit 31: minus sign)
+    const int* sprAB;           // undirected springs: a | b << 16
+    const float* sprL;
     const float* initR;         // [nModel]
 };
 void launch_springs(const SpringArgs& a, cudaStream_t st);

@@ -126,6 +126,19 @@ void build_types(const bcs_scene& in, HostScene& hs)
         const size_t base = hs.adjJ.size();
         hs.adjJ.resize(base + (size_t)deg * t.P, -1);
         hs.adjL.resize(base + (size_t)deg * t.P, 0.0f);
+        hs.adjS.resize(base + (size_t)deg * t.P, -1);
+        // undirected springs (a < b), numbered in (a, b) order
+        hs.sprStart.push_back((int)hs.sprAB.size());
+        std::vector<int> springOf((size_t)t.P * t.P, -1);
+        int ns = 0;
+        for (int a = 0; a < t.P; ++a)
+            for (int b = a + 1; b < t.P; ++b)
+                if (g[a * t.P + b] != 0.0f) {
+                    springOf[a * t.P + b] = springOf[b * t.P + a] = ns++;
+                    hs.sprAB.push_back(a | (b << 16));
+                    hs.sprL.push_back(g[a * t.P + b]);
+                }
+        hs.nSpr.push_back(ns);
         for (int i = 0; i < t.P; ++i) {
             int d = 0;
             for (int j = 0; j < t.P; ++j) {
@@ -133,6 +146,9 @@ void build_types(const bcs_scene& in, HostScene& hs)
                 if (L != 0.0f) {
                     hs.adjJ[base + (size_t)d * t.P + i] = j;
                     hs.adjL[base + (size_t)d * t.P + i] = L;
+                    // a spring from a particle to itself (j == i) has no undirected entry; it contributes nothing
+                    // (zero-length direction -> normalize gives 0), like in the reference
+                    hs.adjS[base + (size_t)d * t.P + i] = (i == j) ? -1 : (springOf[i * t.P + j] | (i > j ? (int)0x80000000 : 0));
                     ++d;
                 }
             }

@@ -18,29 +18,54 @@
 namespace bcs {
 
 constexpr int SPRING_THREADS = 256;
+constexpr int SPRING_F_CAP = 2048;   // per-CTA capacity of the shared spring-force array (float3 entries)
 
 SpringPlan make_spring_plan(const TypesDev& types)
 {
     SpringPlan p{};
     int acc = 0;
     for (int t = 0; t < types.n; ++t) {
-        const int g = SPRING_THREADS / types.t[t].P;
-        p.cellsPerBlock[t] = g < 1 ? 1 : g;
+        int g = SPRING_THREADS / types.t[t].P;
+        if (g < 1) g = 1;
+        // pairwise evaluation needs cellsPerBlock * springsPerCell entries of shared memory; a type whose single
+        // cell does not fit falls back to the directed (per-particle) evaluation
+        p.pairwise[t] = types.t[t].nSpr > 0 && types.t[t].nSpr <= SPRING_F_CAP;
+        if (p.pairwise[t]) g = min(g, SPRING_F_CAP / types.t[t].nSpr);
+        p.cellsPerBlock[t] = g;
         p.blockStart[t] = acc;
-        acc += (types.t[t].count + p.cellsPerBlock[t] - 1) / p.cellsPerBlock[t];
+        acc += (types.t[t].count + g - 1) / g;
     }
     for (int t = types.n; t <= BCS_MAX_TYPES; ++t) p.blockStart[t] = acc;
     p.totalBlocks = acc;
     return p;
 }
 
+// spring term of physics.cuh:24-27,53-78 for the pair (i <- j): returns the force on i
+__device__ __forceinline__ float3 spring_force(const PhysDev& ph, float3 pi, float3 vi, float3 fi, float3 pj, float3 vj, float3 fj, float L)
+{
+    const float3 dP = pi - pj;
+    const float3 dv = vi - vj;
+    // length(dP), normalize(dP) and normalize(-1*dP) of the reference share one sqrt: |dP| = sqrtf(dot(dP,dP)),
+    // n = dP/|dP| (NaN -> 0), normalize(-dP) = -n exactly.  The three divisions are one reciprocal and three
+    // products (<= 1 ulp from the divided form, far inside the 1e-5 contract).
+    const float len = sqrtf(dot(dP, dP));
+    const float inv = 1.0f / len;
+    float3 n = f3(dP.x * inv, dP.y * inv, dP.z * inv);
+    if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
+    const float3 dv2 = dv + ph.dt * (fi - fj);
+    const float s = (len - L) * ph.particle_k_sniff + dot(n, dv2) * ph.particle_d_fact;
+    return s * f3(-n.x, -n.y, -n.z);
+}
+
 __global__ void __launch_bounds__(SPRING_THREADS)
 springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, const float4* __restrict__ pos,
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers,
-               const int* __restrict__ adjJ, const float* __restrict__ adjL, const float* __restrict__ initR)
+               const int* __restrict__ adjJ, const float* __restrict__ adjL, const int* __restrict__ adjS,
+               const int* __restrict__ sprAB, const float* __restrict__ sprL, const float* __restrict__ initR)
 {
     __shared__ float4 sp[SPRING_THREADS], sv[SPRING_THREADS], sf[SPRING_THREADS];
     __shared__ float3 sc[SPRING_THREADS];
+    __shared__ float3 sF[SPRING_F_CAP];
 
     int t = 0;
     while (t + 1 < types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
@@ -68,29 +93,45 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
         sc[tid] = c;
         centers[ty.cStart + firstCell + tid] = make_float4(c.x, c.y, c.z, 0.f);
     }
+    const bool pairwise = plan.pairwise[t];
+    if (pairwise) {
+        // every undirected spring once: the force on its b end is the exact negative of the force on its a end
+        // (dP, dv and f_a - f_b all change sign exactly), so the directed evaluation of the reference does each
+        // of these twice
+        const int total = nCells * ty.nSpr;
+        for (int idx = tid; idx < total; idx += SPRING_THREADS) {
+            const int cell = idx / ty.nSpr, k = idx - cell * ty.nSpr;
+            const int ab = __ldg(sprAB + ty.sprStart + k);
+            const int ia = cell * ty.P + (ab & 0xffff), ib = cell * ty.P + (ab >> 16);
+            sF[idx] = spring_force(ph, xyz(sp[ia]), xyz(sv[ia]), xyz(sf[ia]), xyz(sp[ib]), xyz(sv[ib]), xyz(sf[ib]), __ldg(sprL + ty.sprStart + k));
+        }
+    }
     __syncthreads();
     if (tid >= nPart) return;
 
     const int cell = tid / ty.P, inCell = tid - cell * ty.P, cellBase = cell * ty.P;
     const float3 position = xyz(p4), velocity = xyz(v4), initialForce = xyz(f4);
     float3 newForce = f3(0.f, 0.f, 0.f);
-    const int* aj = adjJ + ty.adjStart + inCell;
-    const float* al = adjL + ty.adjStart + inCell;
-    for (int d = 0; d < ty.maxDeg; ++d) {
-        const int j = __ldg(aj + d * ty.P);
-        if (j < 0) break;
-        const float L = __ldg(al + d * ty.P);
-        const int m = cellBase + j;
-        const float3 dP = position - xyz(sp[m]);
-        const float3 dv = velocity - xyz(sv[m]);
-        // length(dP), normalize(dP) and normalize(-1*dP) of the reference share one sqrt and one set of
-        // IEEE divisions: |dP| = sqrtf(dot(dP,dP)), n = dP/|dP| (NaN -> 0), normalize(-dP) = -n exactly
-        const float len = sqrtf(dot(dP, dP));
-        float3 n = dP / len;
-        if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
-        const float3 dv2 = dv + ph.dt * (initialForce - xyz(sf[m]));
-        const float s = (len - L) * ph.particle_k_sniff + dot(n, dv2) * ph.particle_d_fact;
-        newForce = newForce + s * f3(-n.x, -n.y, -n.z);
+    if (pairwise) {
+        // sum in ascending mate order (the reference's summation order)
+        const int* as = adjS + ty.adjStart + inCell;
+        const int* aj = adjJ + ty.adjStart + inCell;
+        for (int d = 0; d < ty.maxDeg; ++d) {
+            if (__ldg(aj + d * ty.P) < 0) break;
+            const int e = __ldg(as + d * ty.P);
+            if (e == -1) continue;
+            const float3 F = sF[cell * ty.nSpr + (e & 0x7fffffff)];
+            newForce = (e < 0) ? newForce - F : newForce + F;
+        }
+    } else {
+        const int* aj = adjJ + ty.adjStart + inCell;
+        const float* al = adjL + ty.adjStart + inCell;
+        for (int d = 0; d < ty.maxDeg; ++d) {
+            const int j = __ldg(aj + d * ty.P);
+            if (j < 0) break;
+            const int m = cellBase + j;
+            newForce = newForce + spring_force(ph, position, velocity, initialForce, xyz(sp[m]), xyz(sv[m]), xyz(sf[m]), __ldg(al + d * ty.P));
+        }
     }
     // gravity + viscous damping (+ brake for over-stretched cells)
     const float ratio = length(position - sc[cell]) / __ldg(initR + ty.mStart + inCell);
@@ -107,7 +148,7 @@ void launch_springs(const SpringArgs& a, cudaStream_t st)
 {
     BCS_LAUNCH("springs", st,
                springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, 0, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
-                                                                             a.adjJ, a.adjL, a.initR));
+                                                                             a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR));
     BCS_CUDA(cudaGetLastError());
 }
 
