@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int* 
 // flag 2 = inclusive prefix over all earlier tiles; one 32-bit word carries flag and value, so no fences
 // are needed.  Tiles are handed out by an atomic ticket, which guarantees that every tile a block waits
 // for has already started.
-constexpr unsigned STATUS_LOCAL = 1u << 30, STATUS_INCL = 2u << 30, STATUS_VALUE = (1u << 30) - 1u;
+#define STATUS_LOCAL (1u << 30)
+#define STATUS_INCL (2u << 30)
+#define STATUS_VALUE ((1u << 30) - 1u)
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const int* __restrict__ keysIn, const int* __restrict__ valsIn,
                                                                       int* __restrict__ keysOut, int* __restrict__ valsOut, int n,
@@ -278,12 +280,24 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const int*
     const unsigned binBase = wb + inclB - myTotalB;
 
     // decoupled look-back over earlier tiles for this thread's digit
+    // (eight predecessors are fetched per round so that the walk costs one L2 round trip per eight tiles)
     unsigned excl = 0;
-    for (int t = tile - 1; t >= 0; --t) {
-        unsigned v;
-        do { v = status[(size_t)t * 256 + tid]; } while ((v >> 30) == 0u);
-        excl += v & STATUS_VALUE;
-        if ((v >> 30) == 2u) break;
+    for (int t = tile - 1; t >= 0;) {
+        constexpr int LOOK = 8;
+        unsigned v[LOOK];
+#pragma unroll
+        for (int k = 0; k < LOOK; ++k) v[k] = (t - k >= 0) ? status[(size_t)(t - k) * 256 + tid] : STATUS_INCL;
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < LOOK; ++k) {
+            if (done) break;
+            unsigned x = v[k];
+            while ((x >> 30) == 0u) x = status[(size_t)(t - k) * 256 + tid];
+            excl += x & STATUS_VALUE;
+            done = (x >> 30) == 2u;
+        }
+        if (done) break;
+        t -= LOOK;
     }
     status[(size_t)tile * 256 + tid] = STATUS_INCL | (excl + total);
     globalBase[tid] = binBase + excl;

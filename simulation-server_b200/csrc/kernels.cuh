@@ -49,6 +49,7 @@ struct SpringPlan {
     int cellsPerBlock[BCS_MAX_TYPES];
     bool pairwise[BCS_MAX_TYPES];        // springs evaluated once per undirected spring (shared-memory exchange)
     int totalBlocks;
+    int sharedBytes;                     // dynamic shared memory of the spring kernel
 };
 SpringPlan make_spring_plan(const TypesDev& types);
 struct SpringArgs {

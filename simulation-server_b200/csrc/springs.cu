@@ -37,6 +37,9 @@ SpringPlan make_spring_plan(const TypesDev& types)
     }
     for (int t = types.n; t <= BCS_MAX_TYPES; ++t) p.blockStart[t] = acc;
     p.totalBlocks = acc;
+    p.sharedBytes = 0;
+    for (int t = 0; t < types.n; ++t)
+        if (p.pairwise[t]) p.sharedBytes = max(p.sharedBytes, (int)(p.cellsPerBlock[t] * types.t[t].nSpr * sizeof(float3)));
     return p;
 }
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ float3 spring_force(const PhysDev& ph, float3 pi, flo
     return s * f3(-n.x, -n.y, -n.z);
 }
 
-__global__ void __launch_bounds__(SPRING_THREADS)
+__global__ void __launch_bounds__(SPRING_THREADS, 6)
 springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, const float4* __restrict__ pos,
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers,
                const int* __restrict__ adjJ, const float* __restrict__ adjL, const int* __restrict__ adjS,
@@ -65,7 +68,7 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
 {
     __shared__ float4 sp[SPRING_THREADS], sv[SPRING_THREADS], sf[SPRING_THREADS];
     __shared__ float3 sc[SPRING_THREADS];
-    __shared__ float3 sF[SPRING_F_CAP];
+    extern __shared__ float3 sF[];   // cellsPerBlock * springsPerCell entries (plan.sharedBytes)
 
     int t = 0;
     while (t + 1 < types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
@@ -147,7 +150,7 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
 void launch_springs(const SpringArgs& a, cudaStream_t st)
 {
     BCS_LAUNCH("springs", st,
-               springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, 0, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
+               springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, a.plan.sharedBytes, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
                                                                              a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR));
     BCS_CUDA(cudaGetLastError());
 }
