@@ -65,5 +65,7 @@ for p in "${pids[@]}"; do wait "$p"; done
 wait
 $NV "$OBJ"/*.o -o "$OUT/ref_headless_$SUFFIX" -lcurand
 "$OUT/ref_scene_dump_$CFG" "$OUT/scene_$CFG.bcsd"
+# the integration shim compiled inside the reference's header tree must produce the same user-level scene
+g++ -std=c++17 -O1 -w $INC "$HERE/ref_harness/shim_check.cpp" -o "$OUT/shim_check_$CFG" && "$OUT/shim_check_$CFG" "$OUT/shim_scene_$CFG.bcsd"
 rm -rf "$OBJ"
 echo "build_ref: built $OUT/ref_headless_$SUFFIX and $OUT/scene_$CFG.bcsd"

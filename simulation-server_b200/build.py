@@ -65,6 +65,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(OBJ, s + ".o") for s in CUDA_SOURCES + HOST_SOURCES]
     if force or jobs or not _newer(LIB, objs):
         run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"])
+    # headless C++ driver over the host mirror of the reference loop (host/bcs_host.hpp)
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(HERE, "bcs_headless")
+    srcs = [os.path.join(host, "headless.cpp"), os.path.join(host, "bcs_host.hpp"), os.path.join(ROOT, "include", "bcsd_io.hpp"), LIB]
+    if force or not _newer(exe, srcs):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        run([gxx, "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + host, srcs[0], "-L" + HERE, "-l:libbcs.so",
+             "-Wl,-rpath,$ORIGIN", "-o", exe])
     return LIB
 
 

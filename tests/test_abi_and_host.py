@@ -165,3 +165,27 @@ def test_oracle_clean_semantics_properties(oracle_lib):
             for sim in (a, b):
                 for stage in range(2, 9):
                     sim.run_stage(stage)
+
+
+def test_reference_shim_reproduces_the_scene_dump():
+    """include/bcs_reference_shim.hpp compiled inside the reference's header tree (oracle/ref_harness/shim_check.cpp,
+    built by oracle/build_ref.sh where /root/reference exists) yields the same user-level scene as the independent dump."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    found = 0
+    for cfg in ("cfg1", "mini3"):
+        a_path, b_path = os.path.join(ref, f"shim_scene_{cfg}.bcsd"), os.path.join(ref, f"scene_{cfg}.bcsd")
+        if not (os.path.exists(a_path) and os.path.exists(b_path)):
+            continue
+        a, b = pkg.bcsd.read(a_path), pkg.bcsd.read(b_path)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (cfg, k)
+        found += 1
+    if not found:
+        pytest.skip("oracle/_ref not built on this machine")
+
+
+def test_headless_driver_is_built():
+    exe = os.path.join(ROOT, "simulation-server_b200", "bcs_headless")
+    assert os.path.exists(exe), "build() must produce the headless C++ driver"
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

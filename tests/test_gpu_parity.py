@@ -173,3 +173,25 @@ def test_graph_and_plain_launch_agree(bcs_lib):
             sim.step(20)
             out.append(refcheck.down(sim, capi.PARTICLE_POS))
     refcheck.assert_close(out[0], out[1], "graph replay vs plain launches", rtol=1e-4, scale=0.0)
+
+
+def test_headless_cpp_driver_matches_python_path(bcs_lib, tmp_path):
+    """The C++ host mirror (same call names and order as main.cu:175-208) driven by bcs_headless vs bcs_step from Python."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    sc = golden_scene("mini3")
+    st, _ = seeded_state("mini3", "wide")
+    scene_path, state_path, out_path = (str(tmp_path / n) for n in ("scene.bcsd", "state.bcsd", "out.bcsd"))
+    sc.save(scene_path)
+    pkg.bcsd.write(state_path, st)
+    exe = os.path.join(ROOT, "simulation-server_b200", "bcs_headless")
+    r = subprocess.run([exe, scene_path, state_path, "25", out_path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Average framerate" in r.stdout
+    out = pkg.bcsd.read(out_path)
+    with make_bcs(sc) as sim:
+        sim.upload_state(st)
+        sim.step(25)
+        pos = refcheck.down(sim, capi.PARTICLE_POS)
+    refcheck.assert_close(np.stack([out["pos_x"], out["pos_y"], out["pos_z"]], 1), pos, "C++ headless loop vs bcs_step", rtol=1e-4, scale=0.0)
