@@ -302,6 +302,38 @@ typedef struct bcs_stats {
 int bcs_get_stats(bcs_sim* sim, bcs_stats* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: slab decomposition along the vein axis (y).  Stands in for the reference's -DMULTI_GPU build
+ * (main.cu:105-117,162-173,194-204: ncclCommInitAll over 4 devices in ONE process, every array replicated,
+ * ncclBroadcast of the state and of both grids + ncclReduce of the forces every frame).  Here: one process
+ * and one bcs_sim per GPU; every rank is created from the same scene, uploads the same initial state and
+ * then advances only the blood cells whose centre lies in its slab [y_lo, y_hi); ghost particles, migrating
+ * blood cells and the vein-vertex halo travel in one grouped ncclSend/ncclRecv per neighbour and step.
+ * Clean semantics only.  bcs_step() is the entry point (the staged calls do not exchange halos).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bcs_slab_opts {
+    uint32_t struct_size;          /* = sizeof(bcs_slab_opts) */
+    int32_t rank;
+    int32_t world;
+    int32_t spawn_rank;            /* rank whose slab contains min_spawn_y (respawned blood cells are sent there) */
+    float y_lo, y_hi;              /* this rank's slab; use -INFINITY / +INFINITY for the outermost faces */
+    float halo_width;              /* particle halo (<= 0: default 32) */
+    float vertex_halo;             /* vein vertex / triangle halo (<= 0: default 2 triangle cells + halo_width + 20) */
+    int32_t migration_capacity;    /* particle records per message (<= 0: default) */
+    int32_t halo_capacity;         /* ghost records per message (<= 0: default) */
+    char nccl_unique_id[128];      /* from bcs_nccl_unique_id() on rank 0, distributed by the caller */
+} bcs_slab_opts;
+
+/* ncclGetUniqueId(); the caller broadcasts the 128 bytes to all ranks (e.g. with torch.distributed). */
+int bcs_nccl_unique_id(char out[128]);
+/* Collective over all ranks (ncclCommInitRank inside). */
+int bcs_create_slab(const bcs_scene* scene, const bcs_opts* opts, const bcs_slab_opts* slab, bcs_sim** out);
+/* owned[c] = 1 if this rank currently owns blood cell c (n_cells entries); state arrays downloaded from a rank are
+ * only meaningful for the blood cells it owns. */
+int bcs_download_ownership(bcs_sim* sim, uint8_t* owned, int32_t n_cells);
+/* Number of active (owned + ghost) particles of the last grid build and of ghosts in the last exchange. */
+int bcs_slab_counts(bcs_sim* sim, int32_t* active_particles, int32_t* ghost_particles, int32_t* owned_cells);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement support (no reference counterpart: the reference only prints a wall-clock average at exit,
  * main.cu:248-253).
  * ------------------------------------------------------------------------------------------- */

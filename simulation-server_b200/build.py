@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbcs.so")
 
-CUDA_SOURCES = ["grid.cu", "springs.cu", "collide.cu", "vein.cu", "integrate.cu", "capi.cu"]
+CUDA_SOURCES = ["grid.cu", "springs.cu", "collide.cu", "vein.cu", "integrate.cu", "slab.cu", "capi.cu"]
 HOST_SOURCES = ["scene_host.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, s + ".o") for s in CUDA_SOURCES + HOST_SOURCES]
     if force or jobs or not _newer(LIB, objs):
-        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"])
+        run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-lnccl"])
     # headless C++ driver over the host mirror of the reference loop (host/bcs_host.hpp)
     host = os.path.join(HERE, "host")
     exe = os.path.join(HERE, "bcs_headless")

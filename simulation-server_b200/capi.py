@@ -68,6 +68,12 @@ class Opts(C.Structure):
                 ("seed", C.c_uint64), ("stream", C.c_void_p)]
 
 
+class SlabOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("spawn_rank", C.c_int32),
+                ("y_lo", C.c_float), ("y_hi", C.c_float), ("halo_width", C.c_float), ("vertex_halo", C.c_float),
+                ("migration_capacity", C.c_int32), ("halo_capacity", C.c_int32), ("nccl_unique_id", C.c_char * 128)]
+
+
 class TypeInfo(C.Structure):
     _fields_ = [("count", C.c_int32), ("particles_in_cell", C.c_int32), ("particle_start", C.c_int32),
                 ("cell_start", C.c_int32), ("model_start", C.c_int32), ("graph_start", C.c_int32),
@@ -175,7 +181,7 @@ class Sim:
 
     def __init__(self, scene: Scene, semantics: int = SEM_CLEAN, device: int = 0, use_graph: bool = True,
                  collect_stats: bool = False, seed: int = 1234, lib: Optional[C.CDLL] = None, prefix: str = "bcs_",
-                 exhaustive_vein_traversal: bool = False):
+                 exhaustive_vein_traversal: bool = False, slab: Optional[dict] = None):
         self.lib = lib if lib is not None else load_library()
         self.prefix = prefix
         self.scene = scene
@@ -183,7 +189,18 @@ class Sim:
         opts = Opts(C.sizeof(Opts), device, semantics, 1 if use_graph else 0, 1 if collect_stats else 0,
                     1 if exhaustive_vein_traversal else 0, seed, None)
         self._h = C.c_void_p()
-        self._call("create", C.byref(self._sh.c), C.byref(opts), C.byref(self._h))
+        if slab is None:
+            self._call("create", C.byref(self._sh.c), C.byref(opts), C.byref(self._h))
+        else:
+            so = SlabOpts()
+            so.struct_size = C.sizeof(SlabOpts)
+            so.rank, so.world, so.spawn_rank = slab["rank"], slab["world"], slab.get("spawn_rank", 0)
+            so.y_lo, so.y_hi = slab["y_lo"], slab["y_hi"]
+            so.halo_width, so.vertex_halo = slab.get("halo_width", 0.0), slab.get("vertex_halo", 0.0)
+            so.migration_capacity, so.halo_capacity = slab.get("migration_capacity", 0), slab.get("halo_capacity", 0)
+            so.nccl_unique_id = bytes(slab["nccl_unique_id"])
+            self._call("create_slab", C.byref(self._sh.c), C.byref(opts), C.byref(so), C.byref(self._h))
+        self.slab = slab
         lay = LayoutC()
         self._call("get_layout", self._h, C.byref(lay))
         self.layout = lay
@@ -327,6 +344,17 @@ class Sim:
         s = Stats()
         self._call("get_stats", self._h, C.byref(s))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def ownership(self) -> np.ndarray:
+        """owned[c] for every blood cell (all ones without slab decomposition)"""
+        out = np.empty(self.n_cells, np.uint8)
+        self._call("download_ownership", self._h, out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(self.n_cells))
+        return out
+
+    def slab_counts(self):
+        a, g, o = C.c_int32(), C.c_int32(), C.c_int32()
+        self._call("slab_counts", self._h, C.byref(a), C.byref(g), C.byref(o))
+        return {"active_particles": a.value, "ghost_particles": g.value, "owned_cells": o.value}
 
     def launch_count(self) -> int:
         v = C.c_uint64()

@@ -109,6 +109,14 @@ struct PhysDev {
     int nEndings;
 };
 
+// slab decomposition along y (multi-GPU): this rank owns the blood cells whose centre lies in [yLo, yHi)
+struct SlabDev {
+    int enabled;
+    int rank, world, spawnRank;   // spawnRank: the rank whose slab contains minSpawnY (respawned cells go there)
+    float yLo, yHi;               // the top slab has yHi = +inf, the bottom slab yLo = -inf
+    float haloWidth;              // particles within this distance of a face are mirrored on the neighbour
+};
+
 struct Counters {               // device-resident, see bcs_stats
     unsigned long long pairTests, pairHits, triTests, veinHits, teleported, oob;
     unsigned long long step;    // completed steps (drives the respawn RNG counter)

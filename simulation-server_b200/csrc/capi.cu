@@ -13,6 +13,7 @@
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include "slab.cuh"
 
 namespace bcs {
 
@@ -148,6 +149,7 @@ struct bcs_sim {
     cudaGraphExec_t graphExec = nullptr;
     LaunchCtx ctx;
     unsigned long long kernelsPerGraph = 0;
+    SlabState* slab = nullptr;   // multi-GPU slab mode
     std::vector<void*> owned;
 
     template <class T> T* track(T* p) { owned.push_back((void*)p); return p; }
@@ -219,6 +221,7 @@ GridBuildArgs particle_grid_args(bcs_sim* s)
     a.occStart = s->occStart; a.occKey = s->occKey; a.numOcc = s->numOcc;
     a.reorder = true;
     a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
+    if (s->slab) { a.pflag = s->slab->pflag; a.nDev = s->slab->nActive; a.nDevOut = s->slab->nActive; }
     return a;
 }
 
@@ -242,6 +245,7 @@ VeinArgs vein_args(bcs_sim* s)
     a.V = s->hs.V; a.T = s->hs.T; a.phys = s->phys;
     a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc;
     a.nbrIds = s->nbrIds; a.nbrLen = s->nbrLen; a.vidx = s->vidx;
+    a.vOwned = s->slab ? s->slab->vOwned : nullptr;
     return a;
 }
 
@@ -257,6 +261,10 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.nCells = s->hs.B; a.maxP = s->maxP; a.cullList = s->cullList; a.cullCount = s->cullCount;
     a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
+    if (s->slab) {
+        a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.ownedCell = s->slab->ownedCell;
+        a.ghostList = s->slab->ghostList; a.ghostCount = s->slab->ghostCount;
+    }
     return a;
 }
 
@@ -270,6 +278,7 @@ CollideArgs collide_args(bcs_sim* s)
     a.frc = s->frc; a.counters = s->counters;
     a.reference = s->semantics == BCS_SEM_REFERENCE; a.stats = s->stats;
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
+    a.nDev = s->slab ? s->slab->nActive : nullptr;
     return a;
 }
 
@@ -280,6 +289,7 @@ IntegrateArgs integrate_args(bcs_sim* s)
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
     a.mx = s->mx; a.my = s->my; a.mz = s->mz; a.endC = s->endC; a.endR = s->endR;
     a.counters = s->counters; a.seed = s->seed;
+    if (s->slab) { a.slab = s->slab->dev; a.ownedCell = s->slab->ownedCell; a.moveTo = s->slab->moveTo; }
     return a;
 }
 
@@ -298,6 +308,7 @@ void stage(bcs_sim* s, int st)
         a.types = s->types; a.plan = s->plan; a.phys = s->phys;
         a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
         a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
+        a.ownedCell = s->slab ? s->slab->ownedCell : nullptr;
         launch_springs(a, s->stream);
         break;
     }
@@ -318,13 +329,24 @@ void stage(bcs_sim* s, int st)
     }
 }
 
+SlabCtx slab_ctx(bcs_sim* s)
+{
+    SlabCtx c{};
+    c.types = s->types; c.N = s->hs.N; c.B = s->hs.B; c.V = s->hs.V; c.T = s->hs.T;
+    c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel;
+    c.stream = s->stream;
+    return c;
+}
+
 void enqueue_step(bcs_sim* s)
 {
+    if (s->slab && !s->slab->primed) slab_prime(s->slab, slab_ctx(s));
     // same stage order as the staged entry points; the tail (integrate particles, vein end, step counter) is one
     // fused kernel, and the vein integrator - independent of it - follows
     for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
     launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, s->stream);
     stage(s, BCS_STAGE_INTEGRATE_VEIN);
+    if (s->slab) slab_end_of_step(s->slab, slab_ctx(s));   // migration + halo exchange for the next step
 }
 
 struct Array {
@@ -352,6 +374,7 @@ void destroy(bcs_sim* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
+    slab_destroy(s->slab);
     for (void* p : s->owned) cudaFree(p);
     s->sortP.release();
     s->sortT.release();
@@ -379,7 +402,7 @@ extern "C" {
 const char* bcs_last_error(void) { return g_lastError.c_str(); }
 int bcs_abi_version(void) { return BCS_ABI_VERSION; }
 
-int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
+static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_slab_opts* slabOpts, bcs_sim** out)
 {
     bcs_sim* s = nullptr;
     try {
@@ -473,6 +496,22 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
             build_triangle_grid(s);
             BCS_CUDA(cudaStreamSynchronize(s->stream));
         }
+        if (slabOpts) {
+            BCS_REQUIRE(slabOpts->struct_size == sizeof(bcs_slab_opts), BCS_ERR_INVALID, "bcs_slab_opts.struct_size mismatch");
+            BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN, BCS_ERR_UNSUPPORTED, "slab decomposition needs clean semantics");
+            SlabInit in{};
+            in.rank = slabOpts->rank; in.world = slabOpts->world; in.spawnRank = slabOpts->spawn_rank;
+            in.yLo = slabOpts->y_lo; in.yHi = slabOpts->y_hi;
+            in.haloWidth = slabOpts->halo_width > 0 ? slabOpts->halo_width : 32.0f;
+            in.vertexHalo = slabOpts->vertex_halo > 0 ? slabOpts->vertex_halo : 2.0f * hs.triCellSize[1] + in.haloWidth + 20.0f;
+            // defaults: 4x the expected number of particles in a halo layer / 2 % of the particles migrating at once
+            const float extentY = hs.gsize[1] > 1.f ? hs.gsize[1] : 1.f;
+            const int perHalo = (int)(4.0 * N * in.haloWidth / extentY) + 4096;
+            in.capHalo = slabOpts->halo_capacity > 0 ? slabOpts->halo_capacity : std::min(N, perHalo);
+            in.capMig = slabOpts->migration_capacity > 0 ? slabOpts->migration_capacity : std::min(N, N / 50 + 2048);
+            in.ncclId = slabOpts->nccl_unique_id;
+            s->slab = slab_create(in, hs, s->tg, s->tids[1], s->tcellStart, s->tcellEnd, slab_ctx(s));
+        }
         *out = s;
         return BCS_OK;
     } catch (const bcs::Error& e) {
@@ -484,6 +523,59 @@ int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out)
         destroy(s);
         return BCS_ERR_INVALID;
     }
+}
+
+int bcs_create(const bcs_scene* scene, const bcs_opts* opts, bcs_sim** out) { return create_impl(scene, opts, nullptr, out); }
+
+int bcs_create_slab(const bcs_scene* scene, const bcs_opts* opts, const bcs_slab_opts* slab, bcs_sim** out)
+{
+    if (!slab) {
+        bcs::set_error("null slab options");
+        return BCS_ERR_INVALID;
+    }
+    return create_impl(scene, opts, slab, out);
+}
+
+int bcs_nccl_unique_id(char out[128])
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(out, BCS_ERR_INVALID, "null argument");
+    slab_unique_id(out);
+    BCS_API_END
+}
+
+int bcs_download_ownership(bcs_sim* s, uint8_t* owned, int32_t n)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && owned && n == s->hs.B, BCS_ERR_INVALID, "bad argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    if (!s->slab) {
+        std::memset(owned, 1, n);
+    } else {
+        CtxScope scope(&s->ctx);
+        if (!s->slab->primed) slab_prime(s->slab, slab_ctx(s));
+        BCS_CUDA(cudaMemcpyAsync(owned, s->slab->ownedCell, n, cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    BCS_API_END
+}
+
+int bcs_slab_counts(bcs_sim* s, int32_t* active, int32_t* ghosts, int32_t* ownedCells)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && active && ghosts && ownedCells, BCS_ERR_INVALID, "null argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    if (!s->slab) { *active = s->hs.N; *ghosts = 0; *ownedCells = s->hs.B; return BCS_OK; }
+    std::vector<unsigned char> o(s->hs.B);
+    BCS_CUDA(cudaMemcpyAsync(active, s->slab->nActive, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(ghosts, s->slab->ghostCount, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaMemcpyAsync(o.data(), s->slab->ownedCell, s->hs.B, cudaMemcpyDeviceToHost, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    int k = 0;
+    for (unsigned char v : o) k += v;
+    *ownedCells = k;
+    BCS_REQUIRE(!slab_check_error(s->slab, s->stream), BCS_ERR_STATE, "a halo / migration message overflowed its capacity (raise bcs_slab_opts capacities)");
+    BCS_API_END
 }
 
 void bcs_destroy(bcs_sim* s) { destroy(s); }
@@ -560,6 +652,7 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     BCS_CUDA(cudaMemcpyAsync(sz, z, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, a.ptr, n, s->types, s->collR, a.isParticlePos ? 1 : 0);
     BCS_CUDA(cudaGetLastError());
+    if (s->slab && which == BCS_PARTICLE_POS) s->slab->primed = false;   // ownership is re-derived from the new positions
     BCS_API_END
 }
 
@@ -652,7 +745,7 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
     BCS_REQUIRE(s && nsteps >= 0, BCS_ERR_INVALID, "bad argument");
     CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
-    if (!s->useGraph) {
+    if (!s->useGraph || s->slab) {
         for (int i = 0; i < nsteps; ++i) enqueue_step(s);
     } else {
         if (!s->graphExec) {

@@ -59,11 +59,14 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myTests = 0;
     int myHits = 0;
-    if (slot < a.n) {
+    // slab mode: the active count lives on the device and ghost slots (bit 31 of the id) are candidates only
+    const int nActive = a.nDev ? *a.nDev : a.n;
+    if (slot < nActive && __float_as_int(a.svel[slot].w) >= 0) {
         const GridDev& g = a.grid;
         const float4 p4 = a.spos[slot];
         const float4 v4 = a.svel[slot];
-        const int pid = __float_as_int(v4.w);
+        const int tag = __float_as_int(v4.w);
+        const int pid = tag & 0x7fffffff;
         const float3 p1 = xyz(p4), v1 = xyz(v4);
         const int cell = a.keys[slot];
         int x0, x1, y0, y1, z0, z1;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                     if (j == slot) continue;
                     const float4 q4 = a.spos[j];
                     if (DEBUG) {
-                        const int qid = __float_as_int(a.svel[j].w);
+                        const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
                         ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
                     }
                     test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);

@@ -210,10 +210,12 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const int* 
 #define STATUS_VALUE ((1u << 30) - 1u)
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const int* __restrict__ keysIn, const int* __restrict__ valsIn,
-                                                                      int* __restrict__ keysOut, int* __restrict__ valsOut, int n,
-                                                                      int shift, const unsigned* __restrict__ digitTotals,
-                                                                      volatile unsigned* status, unsigned* ticket)
+                                                                      int* __restrict__ keysOut, int* __restrict__ valsOut, int nArg,
+                                                                      const int* __restrict__ nDev, int shift,
+                                                                      const unsigned* __restrict__ digitTotals, volatile unsigned* status,
+                                                                      unsigned* ticket)
 {
+    const int n = nDev ? *nDev : nArg;   // slab mode: the number of active (owned + ghost) particles lives on the device
     __shared__ unsigned warpCnt[SORT_WARPS][256];
     __shared__ unsigned binStart[256];
     __shared__ unsigned globalBase[256];
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_onesweep_kernel(const int*
     __syncthreads();
     const int tile = (int)sTile;
     const int tileStart = tile * SORT_TILE;
+    if (tileStart >= n) return;   // launched for capacity; tiles past the data are never waited for
 
     int key[SORT_ITEMS], val[SORT_ITEMS];
     unsigned rank[SORT_ITEMS];
@@ -349,8 +352,10 @@ __global__ void __launch_bounds__(256) clear_cells_kernel(const int* __restrict_
 __device__ __forceinline__ void reorder_slot(int slot, int id, bool reference, const float4* __restrict__ pos,
                                              const float4* __restrict__ vel, float4* __restrict__ spos, float4* __restrict__ svel)
 {
-    float4 p = pos[id];
-    float4 v = vel[id];
+    // slab mode tags ghost particles in bit 31 of the sorted value; the tag travels on in svel.w
+    const int pid = id & 0x7fffffff;
+    float4 p = pos[pid];
+    float4 v = vel[pid];
     // canonical pos4.w already carries the particle's own collision radius (set at upload, preserved by
     // the integrator); the reference-compatible radius lookup needs the particle id instead
     if (reference) p.w = __int_as_float(id);
@@ -401,8 +406,10 @@ constexpr int FIN_THREADS = 256;
 constexpr int FIN_ITEMS = 4;
 constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
 
-__global__ void __launch_bounds__(FIN_THREADS) count_cell_starts_kernel(const int* __restrict__ keys, int n, int* __restrict__ tileCount)
+__global__ void __launch_bounds__(FIN_THREADS) count_cell_starts_kernel(const int* __restrict__ keys, int nArg, const int* __restrict__ nDev,
+                                                                        int* __restrict__ tileCount)
 {
+    const int n = nDev ? *nDev : nArg;
     __shared__ int warpSum[FIN_THREADS / 32];
     const int base = blockIdx.x * FIN_TILE + threadIdx.x * FIN_ITEMS;
     int c = 0;
@@ -428,8 +435,8 @@ __global__ void __launch_bounds__(FIN_THREADS) count_cell_starts_kernel(const in
 }
 
 template <bool REORDER>
-__global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int* __restrict__ keys, const int* __restrict__ ids, int n,
-                                                                       const int* __restrict__ tileCount, unsigned* __restrict__ cellMask,
+__global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int* __restrict__ keys, const int* __restrict__ ids, int nArg,
+                                                                       const int* __restrict__ nDev, const int* __restrict__ tileCount, unsigned* __restrict__ cellMask,
                                                                        int* __restrict__ cellRank, int* __restrict__ occStart,
                                                                        int* __restrict__ occKey, int* __restrict__ numOcc,
                                                                        const float4* __restrict__ pos, const float4* __restrict__ vel,
@@ -437,7 +444,13 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int
 {
     __shared__ int warpSum[FIN_THREADS / 32];
     __shared__ int tileBase;
+    const int n = nDev ? *nDev : nArg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n == 0) {
+        if (blockIdx.x == 0 && tid == 0) { occStart[0] = 0; *numOcc = 0; }
+        return;
+    }
+    if ((int)blockIdx.x * FIN_TILE >= n) return;
     // occupied cells before this tile
     int acc = 0;
     for (int b = tid; b < (int)blockIdx.x; b += FIN_THREADS) acc += tileCount[b];
@@ -503,6 +516,98 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int
 }
 
 // ------------------------------------------------------------------------------------------------
+// slab mode: cell keys of the active particles (pflag bit 0 = owned, bit 1 = ghost), compacted in ascending
+// particle id so that the stable sort still ends in (cell id, particle id) order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FIN_THREADS) slab_count_active_kernel(const unsigned char* __restrict__ pflag, int n, int* __restrict__ tileCount)
+{
+    __shared__ int warpSum[FIN_THREADS / 32];
+    const int base = blockIdx.x * FIN_TILE + threadIdx.x * FIN_ITEMS;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k)
+        if (base + k < n) c += pflag[base + k] != 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) s += warpSum[w];
+        tileCount[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) slab_keys_kernel(const float4* __restrict__ pos, const unsigned char* __restrict__ pflag, GridDev g,
+                                                                const int* __restrict__ tileCount, int* __restrict__ keys, int* __restrict__ ids,
+                                                                unsigned* __restrict__ digitTotals, int passes, int* __restrict__ nActive,
+                                                                Counters* __restrict__ counters)
+{
+    __shared__ unsigned hist[4][256];
+    __shared__ int warpSum[FIN_THREADS / 32];
+    __shared__ int tileBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4 * 256; i += FIN_THREADS) (&hist[0][0])[i] = 0;
+    int acc = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += FIN_THREADS) acc += tileCount[b];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) warpSum[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) s += warpSum[w];
+        tileBase = s;
+    }
+    __syncthreads();
+    const int base = blockIdx.x * FIN_TILE + tid * FIN_ITEMS;
+    unsigned char f[FIN_ITEMS];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k) {
+        f[k] = (base + k < g.n) ? pflag[base + k] : 0;
+        mine += f[k] != 0;
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warpSum[w];
+    int out = tileBase + wbase + incl - mine;
+#pragma unroll
+    for (int k = 0; k < FIN_ITEMS; ++k) {
+        if (!f[k]) continue;
+        const int i = base + k;
+        const float4 p = pos[i];
+        const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
+        int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
+                  axis_cell(p.x, g.minx, g.lenx, g.csx);
+        if (oob) {
+            if (f[k] & 1) atomicAdd(&counters->oob, 1ull);
+            key = max(0, min(key, g.cells - 1));
+        } else if (key >= g.cells) {
+            key = g.cells - 1;
+        }
+        keys[out] = key;
+        ids[out] = (f[k] & 1) ? i : (i | (int)0x80000000);   // ghost tag
+        ++out;
+        for (int p2 = 0; p2 < passes; ++p2) atomicAdd(&hist[p2][(key >> (8 * p2)) & 255], 1u);
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == FIN_THREADS - 1) *nActive = out;
+    __syncthreads();
+    for (int i = tid; i < passes * 256; i += FIN_THREADS) {
+        const unsigned v = (&hist[0][0])[i];
+        if (v) atomicAdd(&digitTotals[i], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side driver
 // ------------------------------------------------------------------------------------------------
 void SortScratch::allocate(int n)
@@ -540,6 +645,14 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
     if (!a.scratch->classic)
         BCS_CUDA(cudaMemsetAsync(a.scratch->status, 0, (size_t)passes * a.scratch->numTiles * 256 * sizeof(unsigned), st));
     const int keyBlocks = min(blocks, 148 * 8);
+    if (a.pflag) {
+        // slab mode: keys of the ACTIVE (owned + ghost) particles only, compacted in ascending particle id
+        const int tiles = (n + FIN_TILE - 1) / FIN_TILE;
+        BCS_LAUNCH("slab_count_active", st, slab_count_active_kernel<<<tiles, FIN_THREADS, 0, st>>>(a.pflag, n, a.scratch->finTileCount));
+        BCS_LAUNCH("cell_keys", st,
+                   slab_keys_kernel<<<tiles, FIN_THREADS, 0, st>>>(a.objPos, a.pflag, g, a.scratch->finTileCount, a.keys[cur], a.ids[cur],
+                                                                    a.scratch->digitTotals, passes, a.nDevOut, a.counters));
+    } else
     BCS_LAUNCH("cell_keys", st,
                cell_keys_kernel<<<keyBlocks, 256, 0, st>>>(a.objPos, g, a.keys[cur], a.ids[cur], a.scratch->digitTotals, passes, a.counters));
     for (int p = 0; p < passes; ++p) {
@@ -547,7 +660,7 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
         if (!a.scratch->classic) {
             BCS_LAUNCH("radix_onesweep", st,
                        radix_onesweep_kernel<<<a.scratch->numTiles, SORT_THREADS, 0, st>>>(
-                           a.keys[cur], a.ids[cur], a.keys[cur ^ 1], a.ids[cur ^ 1], n, shift, a.scratch->digitTotals + 256 * p,
+                           a.keys[cur], a.ids[cur], a.keys[cur ^ 1], a.ids[cur ^ 1], n, a.nDev, shift, a.scratch->digitTotals + 256 * p,
                            a.scratch->status + (size_t)p * a.scratch->numTiles * 256, a.scratch->digitTotals + 4 * 256 + p));
             cur ^= 1;
             continue;
@@ -564,15 +677,15 @@ void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
     // cur == 1 here
     if (a.compact) {
         const int tiles = (n + FIN_TILE - 1) / FIN_TILE;
-        BCS_LAUNCH("count_cell_starts", st, count_cell_starts_kernel<<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], n, a.scratch->finTileCount));
+        BCS_LAUNCH("count_cell_starts", st, count_cell_starts_kernel<<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], n, a.nDev, a.scratch->finTileCount));
         if (a.reorder)
             BCS_LAUNCH("finalize_grid", st,
-                       finalize_compact_kernel<true><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.scratch->finTileCount, a.cellMask,
+                       finalize_compact_kernel<true><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.nDev, a.scratch->finTileCount, a.cellMask,
                                                                                      a.cellRank, a.occStart, a.occKey, a.numOcc, a.pos, a.vel,
                                                                                      a.spos, a.svel));
         else
             BCS_LAUNCH("finalize_grid", st,
-                       finalize_compact_kernel<false><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.scratch->finTileCount, a.cellMask,
+                       finalize_compact_kernel<false><<<tiles, FIN_THREADS, 0, st>>>(a.keys[1], a.ids[1], n, a.nDev, a.scratch->finTileCount, a.cellMask,
                                                                                       a.cellRank, a.occStart, a.occKey, a.numOcc, nullptr,
                                                                                       nullptr, nullptr, nullptr));
     } else if (a.reference) {

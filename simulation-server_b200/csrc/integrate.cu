@@ -95,9 +95,16 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     const int tid = threadIdx.x;
     const unsigned long long step = a.counters->step;   // read before any block can advance it (see below)
 
+    // slab mode: only owned blood cells are advanced
+    __shared__ unsigned char sOwn[FINISH_THREADS];
+    __shared__ float sY[FINISH_THREADS];
+    if (tid < nCells) sOwn[tid] = a.ownedCell ? a.ownedCell[ty.cStart + firstCell + tid] : 1;
+    __syncthreads();
+    const bool mine = tid < nPart && sOwn[tid / ty.P];
+
     float4 x = make_float4(0, 0, 0, 0), v = x;
     bool out = false;
-    if (tid < nPart) {
+    if (mine) {
         const float4 F = a.frc[basePart + tid];
         v = a.vel[basePart + tid];
         x = a.pos[basePart + tid];
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
         if (any) atomicAdd(&a.counters->teleported, 1ull);
     }
     __syncthreads();
-    if (tid < nPart) {
+    if (mine) {
         const int cell = tid / ty.P, k = tid - cell * ty.P;
         if (sCell[cell]) {
             unsigned ctr[4] = {(unsigned)(ty.cStart + firstCell + cell), (unsigned)step, (unsigned)(step >> 32), 0u};
@@ -137,6 +144,22 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
         }
         a.pos[basePart + tid] = x;
         a.vel[basePart + tid] = v;
+    }
+    if (a.slab.enabled) {
+        // ownership follows the blood cell's centre: which slab does it lie in after this step?
+        sY[tid] = x.y;
+        __syncthreads();
+        if (tid < nCells && sOwn[tid]) {
+            float cy = 0.f;
+            for (int k = 0; k < ty.P; ++k) cy += sY[tid * ty.P + k];
+            cy /= (float)ty.P;
+            int target = -1;
+            if (sCell[tid]) target = a.slab.spawnRank;                               // respawned at the top of the vein
+            else if (cy >= a.slab.yHi && a.slab.rank > 0) target = a.slab.rank - 1;
+            else if (cy < a.slab.yLo && a.slab.rank < a.slab.world - 1) target = a.slab.rank + 1;
+            if (target == a.slab.rank) target = -1;
+            a.moveTo[ty.cStart + firstCell + tid] = (signed char)target;
+        }
     }
     // the last CTA to finish advances the step counter: by then every CTA has read `step`
     if (tid == 0) {

@@ -35,6 +35,9 @@ struct GridBuildArgs {
     int* occStart;            // [n + 1]
     int* occKey;              // [n]
     int* numOcc;              // device scalar
+    const unsigned char* pflag;  // slab mode: per-particle flags (bit 0 owned, bit 1 ghost); null otherwise
+    const int* nDev;          // slab mode: number of active particles (device scalar read by the sort / finalize kernels)
+    int* nDevOut;             //            ... written by the key kernel
     bool reorder;             // also write sorted-order copies of pos/vel
     const float4* pos;
     const float4* vel;
@@ -66,6 +69,7 @@ struct SpringArgs {
     const int* sprAB;           // undirected springs: a | b << 16
     const float* sprL;
     const float* initR;         // [nModel]
+    const unsigned char* ownedCell;   // slab mode: [B] 1 = this rank owns the blood cell; null = all
 };
 void launch_springs(const SpringArgs& a, cudaStream_t st);
 
@@ -75,6 +79,7 @@ struct CollideArgs {
     TypesDev types;
     PhysDev phys;
     int n;
+    const int* nDev;            // slab mode: number of active sorted slots (device scalar); null otherwise
     const int* keys;            // sorted cell ids
     const float4* spos;         // sorted positions  (w: radius | particle id bits in reference mode)
     const float4* svel;         // sorted velocities (w: particle id bits)
@@ -105,6 +110,7 @@ struct VeinArgs {
     const int* nbrIds;          // [9][V]
     const float* nbrLen;
     const unsigned* vidx;       // [3T]
+    const unsigned char* vOwned;   // slab mode: [V] 1 = vertex integrated by this rank; null = all
 };
 void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st);
 void launch_vein_gather(const VeinArgs& a, cudaStream_t st);
@@ -130,6 +136,11 @@ struct VeinCollideArgs {
     CellSlab* groupSlab;        // [(T+7)/8] padded slab of the same groups along their mean normal
     Aabb* cellBox;              // [cells]   padded AABB of everything a cell's table range reaches
     CellSlab* cellSlab;         // [cells]   padded slab along the mean triangle normal of the same range
+    const unsigned char* groupLocal;    // slab mode: [(T+7)/8] slot groups refitted by this rank; null = all
+    const unsigned char* triCellLocal;  // slab mode: [cells] triangle-grid cells refitted by this rank; null = all
+    const unsigned char* ownedCell;     // slab mode: [B] blood cells this rank owns; null = all
+    const int* ghostList;               // slab mode: ghost particle ids (splat-only pass) and their count
+    const int* ghostCount;
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
     int nCells;                 // blood cells
     int maxP;                   // largest particles-per-cell over the types
@@ -161,6 +172,10 @@ struct IntegrateArgs {
     const float* endR;
     Counters* counters;
     unsigned long long seed;
+    // slab mode
+    SlabDev slab;
+    const unsigned char* ownedCell;   // [B]
+    signed char* moveTo;              // [B] out: rank the blood cell migrates to after this step, -1 = stays
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter

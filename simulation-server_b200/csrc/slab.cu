@@ -1,0 +1,409 @@
+// Multi-GPU mode: slab decomposition along the vein axis (y) with ghost-particle halo exchange and whole-blood-cell
+// migration over NCCL.  One process / one bcs_sim per GPU.
+//
+// Replaces the reference's -DMULTI_GPU scheme (replicate every array on 4 GPUs, split kernels by INDEX range,
+// ncclBroadcast the full state + the 55 MB grid tables and ncclReduce the force arrays every frame:
+// main.cu:162-204, blood_cells.cu:190-219, uniform_grid.cu:162-175, vein_triangles.cu:169-195), whose
+// per-step traffic grows with the whole state.  Here:
+//   * every rank allocates arrays indexed by GLOBAL particle / vertex id (1 M particles = 48 MB: trivial on
+//     180 GB), but only advances the blood cells whose centre lies in its y-slab and the vein vertices whose
+//     rest position lies in it;
+//   * after each step ONE grouped ncclSend/ncclRecv per neighbour carries (a) the blood cells that crossed the
+//     face (full state, ownership moves with them), (b) the owned particles within haloWidth of the face
+//     (position + velocity: they become ghosts = collision candidates and wall-splat sources on the other
+//     side; forces are only ever applied to owned particles, as in particle_collisions.cuh:36), (c) the vein
+//     vertices within the vertex halo (position + velocity);  respawned cells (vein_end.cu) are routed to the
+//     rank that owns the top of the vein;
+//   * messages have a fixed capacity (header + records), so no size handshake and no host synchronisation is
+//     needed per step; an overflow raises a sticky error flag checked by bcs_synchronize/bcs_get_stats.
+// Cell ids, the (cell id, particle id) order of every rank's sorted list and the candidate sets are those of the
+// single-GPU run restricted to the rank's active particles.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "bcs_internal.cuh"
+#include "device_math.cuh"
+#include "kernels.cuh"
+#include "slab.cuh"
+
+namespace bcs {
+
+#define BCS_NCCL(expr)                                                                                              \
+    do {                                                                                                            \
+        ncclResult_t _r = (expr);                                                                                   \
+        if (_r != ncclSuccess)                                                                                      \
+            throw ::bcs::Error{BCS_ERR_NCCL, std::string(#expr) + ": " + ncclGetErrorString(_r) + " (" + __FILE__ + ":" + \
+                                                 std::to_string(__LINE__) + ")"};                                   \
+    } while (0)
+
+__device__ __forceinline__ int cell_of_particle(const TypesDev& types, int i, int* typeOut = nullptr)
+{
+    int t = 0;
+    while (t + 1 < types.n && i >= types.t[t + 1].pStart) ++t;
+    if (typeOut) *typeOut = t;
+    return types.t[t].cStart + (i - types.t[t].pStart) / types.t[t].P;
+}
+
+// ownership from the current positions (after the initial upload): a blood cell belongs to the slab its centre is in
+__global__ void __launch_bounds__(128) slab_init_ownership_kernel(TypesDev types, int nCells, SlabDev slab, const float4* __restrict__ pos,
+                                                                 unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
+                                                                 signed char* __restrict__ moveTo)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    int t = 0;
+    while (t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
+    const TypeDev ty = types.t[t];
+    const int first = ty.pStart + (c - ty.cStart) * ty.P;
+    float cy = 0.f;
+    for (int k = 0; k < ty.P; ++k) cy += pos[first + k].y;
+    cy /= (float)ty.P;
+    const bool mine = cy >= slab.yLo && cy < slab.yHi;
+    ownedCell[c] = mine ? 1 : 0;
+    moveTo[c] = -1;
+    for (int k = 0; k < ty.P; ++k) pflag[first + k] = mine ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) slab_init_vertices_kernel(int V, SlabDev slab, const float4* __restrict__ vpos,
+                                                                unsigned char* __restrict__ vOwned)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float y = vpos[v].y;
+    vOwned[v] = (y >= slab.yLo && y < slab.yHi) ? 1 : 0;
+}
+
+// ---- pack ---------------------------------------------------------------------------------------------------
+// destination index: 0 = up (rank-1), 1 = down (rank+1), 2 = spawn rank (when it is not a neighbour)
+__device__ __forceinline__ int dest_of(const SlabDev& s, int target)
+{
+    if (target == s.rank - 1) return 0;
+    if (target == s.rank + 1) return 1;
+    return 2;
+}
+
+__global__ void __launch_bounds__(256) slab_pack_kernel(TypesDev types, int n, SlabDev slab, const float4* __restrict__ pos,
+                                                       const float4* __restrict__ vel, const float4* __restrict__ frc,
+                                                       unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
+                                                       const signed char* __restrict__ moveTo, SlabBuffers buf, int* __restrict__ ghostList,
+                                                       int* __restrict__ ghostCount, int* __restrict__ errorFlag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char f = pflag[i];
+    if (!(f & 1)) {
+        if (f) pflag[i] = 0;   // last step's ghost expires
+        return;
+    }
+    int t;
+    const int c = cell_of_particle(types, i, &t);
+    const int target = moveTo[c];
+    const float4 p = pos[i], v = vel[i];
+    if (target >= 0) {
+        // the blood cell leaves: full state goes to its new owner
+        const int d = dest_of(slab, target);
+        const int k = atomicAdd(&buf.send[d]->nMig, 1);
+        if (k < buf.capMig) {
+            MigRecord r;
+            r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z;
+            const float4 F = frc[i];
+            r.fx = F.x; r.fy = F.y; r.fz = F.z;
+            buf.mig[d][k] = r;
+        } else {
+            atomicExch(errorFlag, 1);
+        }
+        // on this side its particles stay around as ghosts for the next step if they are near the face they crossed
+        const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth) || (d == 1 && p.y < slab.yLo + slab.haloWidth);
+        pflag[i] = keep ? 2 : 0;
+        if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
+        if (i == types.t[t].pStart + (c - types.t[t].cStart) * types.t[t].P) ownedCell[c] = 0;
+        return;
+    }
+    // stays: mirror it on the neighbours whose slab it is close to
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const bool near = d == 0 ? (slab.rank > 0 && p.y >= slab.yHi - slab.haloWidth) : (slab.rank < slab.world - 1 && p.y < slab.yLo + slab.haloWidth);
+        if (!near) continue;
+        const int k = atomicAdd(&buf.send[d]->nHalo, 1);
+        if (k < buf.capHalo) {
+            HaloRecord r;
+            r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z; r.pad = 0.f;
+            buf.halo[d][k] = r;
+        } else {
+            atomicExch(errorFlag, 1);
+        }
+    }
+}
+
+// vein vertices of the static halo lists (owned vertices near a face)
+__global__ void __launch_bounds__(256) slab_pack_vertices_kernel(const int* __restrict__ list, int count, const float4* __restrict__ vpos,
+                                                                const float4* __restrict__ vvel, VertexRecord* __restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int v = list[k];
+    const float4 p = vpos[v], w = vvel[v];
+    VertexRecord r;
+    r.id = v; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = w.x; r.vy = w.y; r.vz = w.z; r.pad = 0.f;
+    out[k] = r;
+}
+
+__global__ void slab_reset_headers_kernel(SlabBuffers buf, int* ghostCount, int nv0, int nv1)
+{
+    if (threadIdx.x < 3) { buf.send[threadIdx.x]->nMig = 0; buf.send[threadIdx.x]->nHalo = 0; buf.send[threadIdx.x]->nVerts = 0; }
+    if (threadIdx.x == 0) { *ghostCount = 0; buf.send[0]->nVerts = nv0; buf.send[1]->nVerts = nv1; }
+}
+
+// ---- unpack -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) slab_unpack_kernel(TypesDev types, const SlabHeader* __restrict__ hdr, const MigRecord* __restrict__ mig,
+                                                         const HaloRecord* __restrict__ halo, const VertexRecord* __restrict__ verts, int nVerts,
+                                                         int capMig, int capHalo, float4* __restrict__ pos, float4* __restrict__ vel,
+                                                         float4* __restrict__ frc, float4* __restrict__ vpos, float4* __restrict__ vvel,
+                                                         unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
+                                                         int* __restrict__ ghostList, int* __restrict__ ghostCount)
+{
+    const int nMig = min(hdr->nMig, capMig), nHalo = min(hdr->nHalo, capHalo);
+    nVerts = min(nVerts, hdr->nVerts);
+    const int total = nMig + nHalo + nVerts;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        if (k < nMig) {
+            const MigRecord r = mig[k];
+            pos[r.id] = make_float4(r.px, r.py, r.pz, pos[r.id].w);   // .w = collision radius, static per particle
+            vel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
+            frc[r.id] = make_float4(r.fx, r.fy, r.fz, 0.f);
+            pflag[r.id] = 1;
+            ownedCell[cell_of_particle(types, r.id)] = 1;
+        } else if (k < nMig + nHalo) {
+            const HaloRecord r = halo[k - nMig];
+            pos[r.id] = make_float4(r.px, r.py, r.pz, pos[r.id].w);
+            vel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
+            pflag[r.id] = 2;
+            ghostList[atomicAdd(ghostCount, 1)] = r.id;
+        } else {
+            const VertexRecord r = verts[k - nMig - nHalo];
+            vpos[r.id] = make_float4(r.px, r.py, r.pz, 0.f);
+            vvel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+void SlabState::exchange(cudaStream_t st)
+{
+    ncclComm_t c = (ncclComm_t)comm;
+    const SlabDev& s = dev;
+    BCS_NCCL(ncclGroupStart());
+    if (s.rank > 0) {
+        BCS_NCCL(ncclSend(sendRaw[0], msgBytes, ncclChar, s.rank - 1, c, st));
+        BCS_NCCL(ncclRecv(recvRaw[0], msgBytes, ncclChar, s.rank - 1, c, st));
+    }
+    if (s.rank < s.world - 1) {
+        BCS_NCCL(ncclSend(sendRaw[1], msgBytes, ncclChar, s.rank + 1, c, st));
+        BCS_NCCL(ncclRecv(recvRaw[1], msgBytes, ncclChar, s.rank + 1, c, st));
+    }
+    // respawned cells from ranks that are not neighbours of the spawn rank
+    if (s.rank == s.spawnRank) {
+        for (int r = 0; r < s.world; ++r)
+            if (r != s.rank && r != s.rank - 1 && r != s.rank + 1) BCS_NCCL(ncclRecv(spawnRecvRaw[r], spawnBytes, ncclChar, r, c, st));
+    } else if (s.spawnRank != s.rank - 1 && s.spawnRank != s.rank + 1) {
+        BCS_NCCL(ncclSend(sendRaw[2], spawnBytes, ncclChar, s.spawnRank, c, st));
+    }
+    BCS_NCCL(ncclGroupEnd());
+}
+
+template <class T>
+static T* salloc(SlabState* s, size_t count)
+{
+    T* p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) throw Error{BCS_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
+    BCS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    s->owned.push_back((void*)p);
+    return p;
+}
+
+void slab_unique_id(char out[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    BCS_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(out, &id, 128);
+}
+
+SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev& tg, const int* dTriIds, const int* dTriCellStart,
+                       const int* dTriCellEnd, const SlabCtx& ctx)
+{
+    BCS_REQUIRE(init.world >= 1 && init.rank >= 0 && init.rank < init.world, BCS_ERR_INVALID, "bad rank / world size");
+    BCS_REQUIRE(init.spawnRank >= 0 && init.spawnRank < init.world, BCS_ERR_INVALID, "bad spawn rank");
+    BCS_REQUIRE(init.yLo < init.yHi, BCS_ERR_INVALID, "empty slab");
+    auto* s = new SlabState();
+    try {
+        s->dev = SlabDev{1, init.rank, init.world, init.spawnRank, init.yLo, init.yHi, init.haloWidth};
+        s->capMig = init.capMig; s->capHalo = init.capHalo;
+        s->ownedCell = salloc<unsigned char>(s, ctx.B);
+        s->pflag = salloc<unsigned char>(s, ctx.N);
+        s->vOwned = salloc<unsigned char>(s, ctx.V);
+        s->moveTo = salloc<signed char>(s, ctx.B);
+        s->ghostList = salloc<int>(s, ctx.N);
+        s->ghostCount = salloc<int>(s, 1);
+        s->nActive = salloc<int>(s, 1);
+        s->errorFlag = salloc<int>(s, 1);
+
+        // static vein decomposition from the rest positions: owned vertices, halo lists, triangles to refit
+        std::vector<unsigned char> vOwned(ctx.V);
+        std::vector<int> vlist[2];
+        for (int v = 0; v < ctx.V; ++v) {
+            const float y = hs.vy[v];
+            vOwned[v] = (y >= init.yLo && y < init.yHi) ? 1 : 0;
+            if (!vOwned[v]) continue;
+            if (init.rank > 0 && y >= init.yHi - init.vertexHalo) vlist[0].push_back(v);
+            if (init.rank < init.world - 1 && y < init.yLo + init.vertexHalo) vlist[1].push_back(v);
+        }
+        BCS_CUDA(cudaMemcpy(s->vOwned, vOwned.data(), ctx.V, cudaMemcpyHostToDevice));
+        for (int d = 0; d < 2; ++d) {
+            s->vertCount[d] = (int)vlist[d].size();
+            s->vertList[d] = salloc<int>(s, vlist[d].size());
+            if (!vlist[d].empty()) BCS_CUDA(cudaMemcpy(s->vertList[d], vlist[d].data(), vlist[d].size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        // every rank must be able to hold its neighbours' vertex halo: capacity = the largest list over all faces,
+        // computed identically everywhere from the rest positions would need the other ranks' bounds; a vertex halo
+        // cannot exceed the vertices within vertexHalo of one plane, so bound it by scanning all planes we know of
+        s->capVert = std::max(s->vertCount[0], s->vertCount[1]);
+        {
+            // the neighbours' lists toward us: vertices just outside our faces
+            int up = 0, down = 0;
+            for (int v = 0; v < ctx.V; ++v) {
+                const float y = hs.vy[v];
+                if (y >= init.yHi && y < init.yHi + init.vertexHalo) ++up;
+                if (y < init.yLo && y >= init.yLo - init.vertexHalo) ++down;
+            }
+            s->capVert = std::max(s->capVert, std::max(up, down));
+        }
+        // triangles (sorted slots) whose boxes this rank keeps fresh: everything a local or ghost particle can reach
+        {
+            std::vector<int> triIds(ctx.T), cs(tg.cells), ce(tg.cells);
+            BCS_CUDA(cudaMemcpy(triIds.data(), dTriIds, ctx.T * sizeof(int), cudaMemcpyDeviceToHost));
+            BCS_CUDA(cudaMemcpy(cs.data(), dTriCellStart, tg.cells * sizeof(int), cudaMemcpyDeviceToHost));
+            BCS_CUDA(cudaMemcpy(ce.data(), dTriCellEnd, tg.cells * sizeof(int), cudaMemcpyDeviceToHost));
+            const int nGroups = (ctx.T + 7) / 8;
+            std::vector<unsigned char> gl(nGroups, 0), cl(tg.cells, 0);
+            const float lo = init.yLo - init.vertexHalo, hi = init.yHi + init.vertexHalo;
+            for (int slot = 0; slot < ctx.T; ++slot) {
+                const int tri = triIds[slot];
+                float ymin = 3e38f, ymax = -3e38f;
+                for (int k = 0; k < 3; ++k) {
+                    const float y = hs.vy[hs.vidx[3 * tri + k]];
+                    ymin = std::min(ymin, y); ymax = std::max(ymax, y);
+                }
+                if (ymax >= lo && ymin <= hi) gl[slot >> 3] = 1;
+            }
+            for (int c = 0; c < tg.cells; ++c) {
+                if (ce[c] < cs[c]) { cl[c] = 1; continue; }   // empty cells keep an (empty) box: trivial
+                for (int g = cs[c] >> 3; g <= (ce[c] >> 3); ++g)
+                    if (gl[g]) { cl[c] = 1; break; }
+            }
+            s->groupLocal = salloc<unsigned char>(s, nGroups);
+            s->triCellLocal = salloc<unsigned char>(s, tg.cells);
+            BCS_CUDA(cudaMemcpy(s->groupLocal, gl.data(), nGroups, cudaMemcpyHostToDevice));
+            BCS_CUDA(cudaMemcpy(s->triCellLocal, cl.data(), tg.cells, cudaMemcpyHostToDevice));
+        }
+
+        // message buffers
+        s->msgBytes = sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord) + (size_t)s->capHalo * sizeof(HaloRecord) +
+                      (size_t)s->capVert * sizeof(VertexRecord);
+        s->spawnBytes = sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord);
+        for (int d = 0; d < 3; ++d) s->sendRaw[d] = salloc<char>(s, d < 2 ? s->msgBytes : s->spawnBytes);
+        for (int d = 0; d < 2; ++d) s->recvRaw[d] = salloc<char>(s, s->msgBytes);
+        s->spawnRecvRaw.assign(init.world, nullptr);
+        if (init.rank == init.spawnRank)
+            for (int r = 0; r < init.world; ++r)
+                if (r != init.rank && r != init.rank - 1 && r != init.rank + 1) s->spawnRecvRaw[r] = salloc<char>(s, s->spawnBytes);
+        for (int d = 0; d < 3; ++d) {
+            s->buf.send[d] = (SlabHeader*)s->sendRaw[d];
+            s->buf.mig[d] = (MigRecord*)(s->sendRaw[d] + sizeof(SlabHeader));
+            if (d < 2) s->buf.halo[d] = (HaloRecord*)(s->sendRaw[d] + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord));
+        }
+        s->buf.capMig = s->capMig; s->buf.capHalo = s->capHalo;
+
+        if (init.world > 1) {
+            ncclUniqueId id;
+            std::memcpy(&id, init.ncclId, 128);
+            ncclComm_t comm;
+            BCS_NCCL(ncclCommInitRank(&comm, init.world, id, init.rank));
+            s->comm = (void*)comm;
+        }
+        return s;
+    } catch (...) {
+        slab_destroy(s);
+        throw;
+    }
+}
+
+void slab_destroy(SlabState* s)
+{
+    if (!s) return;
+    if (s->comm) ncclCommDestroy((ncclComm_t)s->comm);
+    for (void* p : s->owned) cudaFree(p);
+    delete s;
+}
+
+static VertexRecord* vertex_region(const SlabState* s, char* raw)
+{
+    return (VertexRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord) + (size_t)s->capHalo * sizeof(HaloRecord));
+}
+
+static void unpack_one(SlabState* s, const SlabCtx& ctx, char* raw, bool full)
+{
+    const SlabHeader* hdr = (const SlabHeader*)raw;
+    const MigRecord* mig = (const MigRecord*)(raw + sizeof(SlabHeader));
+    const HaloRecord* halo = (const HaloRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord));
+    BCS_LAUNCH("slab_unpack", ctx.stream,
+               slab_unpack_kernel<<<64, 256, 0, ctx.stream>>>(ctx.types, hdr, mig, halo, full ? vertex_region(s, raw) : nullptr,
+                                                              full ? s->capVert : 0, s->capMig, full ? s->capHalo : 0, ctx.pos, ctx.vel,
+                                                              ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount));
+}
+
+void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
+{
+    cudaStream_t st = ctx.stream;
+    BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
+    BCS_LAUNCH("slab_pack", st,
+               slab_pack_kernel<<<(ctx.N + 255) / 256, 256, 0, st>>>(ctx.types, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell, s->pflag,
+                                                                      s->moveTo, s->buf, s->ghostList, s->ghostCount, s->errorFlag));
+    for (int d = 0; d < 2; ++d)
+        if (s->vertCount[d])
+            BCS_LAUNCH("slab_pack_vertices", st,
+                       slab_pack_vertices_kernel<<<(s->vertCount[d] + 255) / 256, 256, 0, st>>>(s->vertList[d], s->vertCount[d], ctx.vpos,
+                                                                                              ctx.vvel, vertex_region(s, s->sendRaw[d])));
+    BCS_CUDA(cudaGetLastError());
+    if (s->dev.world > 1) {
+        s->exchange(st);
+        if (s->dev.rank > 0) unpack_one(s, ctx, s->recvRaw[0], true);
+        if (s->dev.rank < s->dev.world - 1) unpack_one(s, ctx, s->recvRaw[1], true);
+        for (char* raw : s->spawnRecvRaw)
+            if (raw) unpack_one(s, ctx, raw, false);
+    }
+    BCS_CUDA(cudaGetLastError());
+}
+
+void slab_prime(SlabState* s, const SlabCtx& ctx)
+{
+    cudaStream_t st = ctx.stream;
+    BCS_LAUNCH("slab_init_ownership", st,
+               slab_init_ownership_kernel<<<(ctx.B + 127) / 128, 128, 0, st>>>(ctx.types, ctx.B, s->dev, ctx.pos, s->ownedCell, s->pflag, s->moveTo));
+    slab_end_of_step(s, ctx);   // nothing migrates (moveTo = -1): plain halo exchange
+    s->primed = true;
+}
+
+int slab_check_error(SlabState* s, cudaStream_t st)
+{
+    int flag = 0;
+    BCS_CUDA(cudaMemcpyAsync(&flag, s->errorFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BCS_CUDA(cudaStreamSynchronize(st));
+    return flag;
+}
+
+}  // namespace bcs

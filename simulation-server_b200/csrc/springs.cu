@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(SPRING_THREADS, 6)
 springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, const float4* __restrict__ pos,
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers,
                const int* __restrict__ adjJ, const float* __restrict__ adjL, const int* __restrict__ adjS,
-               const int* __restrict__ sprAB, const float* __restrict__ sprL, const float* __restrict__ initR)
+               const int* __restrict__ sprAB, const float* __restrict__ sprL, const float* __restrict__ initR,
+               const unsigned char* __restrict__ ownedCell)
 {
     __shared__ float4 sp[SPRING_THREADS], sv[SPRING_THREADS], sf[SPRING_THREADS];
     __shared__ float3 sc[SPRING_THREADS];
@@ -80,15 +81,19 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
     const int basePart = ty.pStart + firstCell * ty.P;
     const int tid = threadIdx.x;
 
+    // slab mode: only blood cells this rank owns are advanced (the others may hold stale data)
+    __shared__ unsigned char sOwn[SPRING_THREADS];
+    if (tid < nCells) sOwn[tid] = ownedCell ? ownedCell[ty.cStart + firstCell + tid] : 1;
+    __syncthreads();
     float4 p4 = make_float4(0, 0, 0, 0), v4 = p4, f4 = p4;
-    if (tid < nPart) {
+    if (tid < nPart && sOwn[tid / ty.P]) {
         p4 = pos[basePart + tid];
         v4 = vel[basePart + tid];
         f4 = frc[basePart + tid];
         sp[tid] = p4; sv[tid] = v4; sf[tid] = f4;
     }
     __syncthreads();
-    if (tid < nCells) {
+    if (tid < nCells && sOwn[tid]) {
         // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60)
         float3 c = f3(0.f, 0.f, 0.f);
         for (int k = 0; k < ty.P; ++k) c = c + xyz(sp[tid * ty.P + k]);
@@ -104,13 +109,14 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
         const int total = nCells * ty.nSpr;
         for (int idx = tid; idx < total; idx += SPRING_THREADS) {
             const int cell = idx / ty.nSpr, k = idx - cell * ty.nSpr;
+            if (!sOwn[cell]) continue;
             const int ab = __ldg(sprAB + ty.sprStart + k);
             const int ia = cell * ty.P + (ab & 0xffff), ib = cell * ty.P + (ab >> 16);
             sF[idx] = spring_force(ph, xyz(sp[ia]), xyz(sv[ia]), xyz(sf[ia]), xyz(sp[ib]), xyz(sv[ib]), xyz(sf[ib]), __ldg(sprL + ty.sprStart + k));
         }
     }
     __syncthreads();
-    if (tid >= nPart) return;
+    if (tid >= nPart || !sOwn[tid / ty.P]) return;
 
     const int cell = tid / ty.P, inCell = tid - cell * ty.P, cellBase = cell * ty.P;
     const float3 position = xyz(p4), velocity = xyz(v4), initialForce = xyz(f4);
@@ -151,7 +157,7 @@ void launch_springs(const SpringArgs& a, cudaStream_t st)
 {
     BCS_LAUNCH("springs", st,
                springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, a.plan.sharedBytes, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
-                                                                             a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR));
+                                                                             a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.ownedCell));
     BCS_CUDA(cudaGetLastError());
 }
 

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= a.V) return;
+    if (a.vOwned && !a.vOwned[id]) return;   // slab mode: only vertices of this rank's slab
     const float3 p = xyz(a.vpos[id]), v = xyz(a.vvel[id]);
     float3 F = f3(0.f, 0.f, 0.f);
 #pragma unroll
@@ -69,6 +70,11 @@ __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= a.V) return;
+    if (a.vOwned && !a.vOwned[id]) {
+        // slab mode: not ours - state arrives with the vertex halo; forget the partial splats we accumulated on it
+        a.vfrc[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     float4 x = a.vpos[id], v = a.vvel[id];
     const float4 F = a.vfrc[id];
     const float dt = a.phys.dt;
@@ -94,8 +100,11 @@ constexpr float BOX_PAD = 0.05f;   // covers float error of a Moeller-Trumbore "
 
 __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict__ vpos, const unsigned* __restrict__ vidx,
                                                         const int* __restrict__ triIds, int T, TriPacked* __restrict__ out,
-                                                        Aabb* __restrict__ groupBox, CellSlab* __restrict__ groupSlab)
+                                                        Aabb* __restrict__ groupBox, CellSlab* __restrict__ groupSlab,
+                                                        const unsigned char* __restrict__ groupLocal)
 {
+    // slab mode: only slot groups near this rank's slab are refitted (whole groups of 8 lanes leave together)
+    if (groupLocal && (int)(blockIdx.x * blockDim.x + threadIdx.x) < T && !groupLocal[(blockIdx.x * blockDim.x + threadIdx.x) >> 3]) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
     float3 nrm = f3(0.f, 0.f, 0.f), c0 = nrm, c1 = nrm, c2 = nrm;
@@ -152,10 +161,12 @@ __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict
 // zero-initialised ranges of the reference-compatible mode.  One warp per cell.
 __global__ void __launch_bounds__(128) cell_box_kernel(const int* __restrict__ cellStart, const int* __restrict__ cellEnd, int cells,
                                                        const Aabb* __restrict__ groupBox, const TriPacked* __restrict__ tris,
-                                                       Aabb* __restrict__ cellBox, CellSlab* __restrict__ cellSlab)
+                                                       Aabb* __restrict__ cellBox, CellSlab* __restrict__ cellSlab,
+                                                       const unsigned char* __restrict__ cellLocal)
 {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cells) return;
+    if (cellLocal && !cellLocal[c]) return;
     const int s = cellStart[c], e = cellEnd[c];
     Aabb b{3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f};
     float3 nsum = f3(0.f, 0.f, 0.f);
@@ -203,10 +214,10 @@ __global__ void __launch_bounds__(128) cell_box_kernel(const int* __restrict__ c
 
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
 {
-    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox, a.groupSlab));
+    BCS_LAUNCH("tri_refit", st, tri_refit_kernel<<<(a.T + 255) / 256, 256, 0, st>>>(a.vpos, a.vidx, a.triIds, a.T, a.tris, a.groupBox, a.groupSlab, a.groupLocal));
     BCS_LAUNCH("cell_box", st,
                cell_box_kernel<<<(a.tgrid.cells * 32 + 127) / 128, 128, 0, st>>>(a.cellStart, a.cellEnd, a.tgrid.cells, a.groupBox, a.tris,
-                                                                                   a.cellBox, a.cellSlab));
+                                                                                   a.cellBox, a.cellSlab, a.triCellLocal));
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -394,7 +405,7 @@ __device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const
 
 // what the stage does once the traversal has ended on triangle h (vein_collisions.cu:234-276)
 __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid, const float4 p4, const float4 v4, const float3 dir,
-                                               const RayHit& h)
+                                               const RayHit& h, bool splatOnly = false)
 {
     const PhysDev& ph = a.phys;
     const float3 pos = xyz(p4), velocity = xyz(v4);
@@ -403,7 +414,7 @@ __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid
     const float3 rel = pos - (pos + h.t * dir);
     const float d2 = length_squared(rel);
     if (a.apply && hit && d2 <= ph.impact2) {
-        if (d2 > ph.minForce2) {
+        if (!splatOnly && d2 > ph.minForce2) {
             const float4 F4 = a.frc[pid];
             const float3 F = xyz(F4);
             float3 add;
@@ -421,9 +432,11 @@ __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid
             }
             a.frc[pid] = make_float4(F.x + add.x, F.y + add.y, F.z + add.z, F4.w);
         }
-        const float speed = length(velocity);
-        const float3 dv = 1.0f * ((ph.velocity_collision_damping * speed) * h.refl - velocity);   // gpuCount = 1
-        a.vel[pid] = make_float4(velocity.x + dv.x, velocity.y + dv.y, velocity.z + dv.z, v4.w);
+        if (!splatOnly) {
+            const float speed = length(velocity);
+            const float3 dv = 1.0f * ((ph.velocity_collision_damping * speed) * h.refl - velocity);   // gpuCount = 1
+            a.vel[pid] = make_float4(velocity.x + dv.x, velocity.y + dv.y, velocity.z + dv.z, v4.w);
+        }
         const float3 ds = ph.vein_collision_force_intensity * velocity;
         const unsigned i0 = a.vidx[3 * h.tri], i1 = a.vidx[3 * h.tri + 1], i2 = a.vidx[3 * h.tri + 2];
         const float3 b = barycentric(pos + h.t * dir, xyz(a.vpos[i0]), xyz(a.vpos[i1]), xyz(a.vpos[i2]));
@@ -431,13 +444,13 @@ __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid
         atomicAdd(&a.vfrc[i0].x, b.x * ds.x); atomicAdd(&a.vfrc[i0].y, b.x * ds.y); atomicAdd(&a.vfrc[i0].z, b.x * ds.z);
         atomicAdd(&a.vfrc[i1].x, b.y * ds.x); atomicAdd(&a.vfrc[i1].y, b.y * ds.y); atomicAdd(&a.vfrc[i1].z, b.y * ds.z);
         atomicAdd(&a.vfrc[i2].x, b.z * ds.x); atomicAdd(&a.vfrc[i2].y, b.z * ds.y); atomicAdd(&a.vfrc[i2].z, b.z * ds.z);
-        atomicAdd(&a.counters->veinHits, 1ull);
+        if (!splatOnly) atomicAdd(&a.counters->veinHits, 1ull);
     }
 }
 
 // one particle of the vein-collision stage (vein_collisions.cu:63-277)
 template <bool FAST, bool STATS>
-__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests)
+__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests, bool splatOnly = false)
 {
     const GridDev& g = a.tgrid;
     const PhysDev& ph = a.phys;
@@ -458,7 +471,7 @@ __device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, 
         a.dbgTri[pid] = hit ? h.tri : -1;
         a.dbgT[pid] = hit ? h.t : 1e10f;
     }
-    if (hit) vein_apply_hit(a, pid, p4, v4, dir, h);
+    if (hit) vein_apply_hit(a, pid, p4, v4, dir, h, splatOnly);
 }
 
 // every particle (exhaustive cross-check mode and the debug view)
@@ -500,6 +513,7 @@ __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideA
     // one WARP per blood cell: lanes = particles for the bounding box, then lanes = candidate triangle cells
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= nCells) return;
+    if (a.ownedCell && !a.ownedCell[c]) return;
     int t = 0;
     while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
     const TypeDev ty = a.types.t[t];
@@ -891,8 +905,19 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
     }
 }
 
+// slab mode: ghost particles (owned by a neighbouring rank) only deposit their wall-force splat here, so that every
+// rank sees all contributions to the vein vertices it integrates; the particle itself is updated by its owner
+__global__ void __launch_bounds__(128) vein_ghost_splat_kernel(const VeinCollideArgs a)
+{
+    unsigned long long tests = 0;
+    const int n = *a.ghostCount;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        vein_collide_particle<true, false>(a, a.ghostList[k], tests, true);
+}
+
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
+    if (a.ghostList && a.apply && !a.dbgTri) BCS_LAUNCH("vein_ghost_splat", st, vein_ghost_splat_kernel<<<64, 128, 0, st>>>(a));
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
     if (a.fast && a.cullList && !a.dbgTri) {
         BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
