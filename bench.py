@@ -92,16 +92,23 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
     The spring and collision figures are SURVEY.md 8(d)'s contract numbers."""
     table = {
         "cell_keys": 20 * N,                       # R pos 12N, W key+id 8N
-        "radix_tile_hist": 4 * N,                  # R keys
+        "slab_count_active": N,
+        "radix_onesweep": 16 * N,                  # R key+id 8N, W key+id 8N (one launch = one 8-bit pass)
+        "radix_tile_hist": 4 * N,                  # (classic 3-kernel passes, BCS_SORT=classic)
         "radix_scan": 0,
-        "radix_scatter": 16 * N,                   # R key+id 8N, W key+id 8N
+        "radix_scatter": 16 * N,
         "clear_cells": 4 * N + 8 * c_occ,
-        "finalize_grid": 8 * N + 16 * c_occ + 48 * N,   # R key+id, W start/end per occupied cell, reorder pos+vel R+W
+        "count_cell_starts": 4 * N,
+        "finalize_grid": 8 * N + 12 * c_occ + 48 * N,   # R key+id; W start+key (+mask bit) per occupied cell; reorder pos+vel R+W
         "vein_gather": 120 * V,
         "springs": 48 * N + 12 * B,                # R pos,vel,frc 36N, W frc 12N, W centres 12B
         "particle_collisions": 56 * N + 8 * c_occ,
-        "tri_refit": 96 * T,
+        "tri_refit": 96 * T,                       # R 3 idx + 3 vertices (48), W packed triangle (48)
+        "cell_box": 48 * T,                        # R packed triangles
+        "vein_cull_cells": 12 * N,                 # R positions
         "vein_collisions": 24 * N + 120 * hits,
+        "vein_ghost_splat": 0,
+        "finish_step": 72 * N,                     # integrate (R 36N, W 24N) + vein-end test (12N)
         "integrate_particles": 60 * N,
         "vein_integrate": 72 * V,
         "vein_end": 12 * N,
@@ -170,45 +177,73 @@ def run_product(args):
     import torch.distributed as dist
 
     pkg, capi, workloads = _pkg()
+    dd = importlib.import_module("simulation-server_b200.distributed")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU slab decomposition is not available in this build of bench.py")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sc, st, info = workloads.long_vein(args.particles)
-    sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, device=local_rank, use_graph=True)
+    if world > 1:
+        # slab decomposition along the vein axis: STRONG scaling, the same 1 M-particle scene split over the ranks
+        planes = dd.slab_boundaries(sc, st, world)
+        sim = dd.create_slab_sim(sc, st, rank, world, local_rank, dd.broadcast_unique_id(rank), planes)
+    else:
+        sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, device=local_rank, use_graph=True)
+        sim.upload_state(st)
     N, B, V, T = sim.n_particles, sim.n_cells, sim.n_vertices, sim.n_triangles
-    sim.upload_state(st)
     view = sim.device_view()
     stream = torch.cuda.ExternalStream(view.stream, device=local_rank)
 
-    # ---- device-resident throughput: W warm-up steps, then exactly K steps between two events
+    # ---- device-resident throughput: W warm-up steps, then exactly K steps between two events (max over ranks)
     sim.step(args.warmup)
     sim.synchronize()
     launches0 = sim.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        barrier()
         torch.cuda.synchronize()
         start.record(stream)
         sim.step(args.steps)
         end.record(stream)
         sim.synchronize()
         torch.cuda.synchronize()
-    ms = start.elapsed_time(end) / args.steps
+        barrier()
+    ms = max_over_ranks(start.elapsed_time(end) / args.steps)
     launches = sim.launch_count() - launches0
     value = N / (ms * 1e-3)
+    slab_info = sim.slab_counts() if world > 1 else None
 
     # ---- per-kernel times (CUDA events around every launch, plain launches) and the roofline of the dominant kernel
-    keys, _ = sim.grid(0)
+    if world > 1:
+        active = sim.slab_counts()["active_particles"]
+        keys = sim.grid(0)[0][:active]
+    else:
+        keys, _ = sim.grid(0)
     c_occ = int(np.unique(keys).size)
     hits0 = sim.stats()["vein_hits"]
     prof_steps = 5
     prof = sim.profile_steps(prof_steps)
     hits = (sim.stats()["vein_hits"] - hits0) // prof_steps
+    if world > 1:
+        N_alg, B_alg = sim.slab_counts()["active_particles"], sim.slab_counts()["owned_cells"]   # this rank's share
+    else:
+        N_alg, B_alg = N, B
     total_ms = sum(v[0] for v in prof.values())
     kernels = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps, "share": v[0] / total_ms}
                for k, v in prof.items()}
@@ -217,14 +252,14 @@ def run_product(args):
 
     def roof(name):
         per_launch_ms = prof[name][0] / prof[name][1]
-        b = algorithmic_bytes(name, N, B, V, T, c_occ, hits)
+        b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits)
         gbs = b / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                 "traffic": None, "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms, "peak_source": peak_src}
 
     roofline = roof(dominant)
     roofline["contract_kernels"] = {k: roof(k) for k in ("springs", "particle_collisions") if k in prof}
-    step_bytes = sum(algorithmic_bytes(k, N, B, V, T, c_occ, hits) * v[1] / prof_steps for k, v in prof.items())
+    step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits) * v[1] / prof_steps for k, v in prof.items())
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
@@ -245,34 +280,43 @@ def run_product(args):
     for _ in range(3):
         e2e_step()
     sim.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     sim.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    barrier()
     e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 36 * N, "d2h_bytes_per_step": 12 * N,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
 
     # ---- CPU baseline (rank 0, N=1): the host-core port on a bounded sample
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cv, cms, cores, cn, _ = time_oracle(min(args.particles, args.reference_sample), 3, 1)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cms,
                "sample": f"{cn}-particle section of the workload (same density), 3 steps after 1 warm-up, OpenMP on {cores} threads"}
 
     ws_mb = (16 * 3 * N + 16 * 2 * N + 16 * N + 64 * c_occ + 48 * V + 48 * T) / 1e6
     config = dict(info)
-    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step",
+    if world > 1:
+        config["parallelism"] = f"y-slab decomposition over {world} ranks, NCCL halo exchange + blood-cell migration (one grouped send/recv per neighbour and step)"
+        config["rank0_slab"] = slab_info
+    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step" if world == 1 else "plain launches + NCCL p2p per step",
                    "l2": f"no flush: per-step working set ~{ws_mb:.0f} MB exceeds the 126 MB L2 (inputs larger than L2)",
                    "occupied_grid_cells": c_occ, "grid_cells": int(sim.layout.grid_cells)})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
     }
     sim.close()
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -71,7 +71,7 @@ class Opts(C.Structure):
 class SlabOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("spawn_rank", C.c_int32),
                 ("y_lo", C.c_float), ("y_hi", C.c_float), ("halo_width", C.c_float), ("vertex_halo", C.c_float),
-                ("migration_capacity", C.c_int32), ("halo_capacity", C.c_int32), ("nccl_unique_id", C.c_char * 128)]
+                ("migration_capacity", C.c_int32), ("halo_capacity", C.c_int32), ("nccl_unique_id", C.c_ubyte * 128)]
 
 
 class TypeInfo(C.Structure):
@@ -198,7 +198,9 @@ class Sim:
             so.y_lo, so.y_hi = slab["y_lo"], slab["y_hi"]
             so.halo_width, so.vertex_halo = slab.get("halo_width", 0.0), slab.get("vertex_halo", 0.0)
             so.migration_capacity, so.halo_capacity = slab.get("migration_capacity", 0), slab.get("halo_capacity", 0)
-            so.nccl_unique_id = bytes(slab["nccl_unique_id"])
+            uid = bytes(slab["nccl_unique_id"])
+            assert len(uid) == 128
+            so.nccl_unique_id = (C.c_ubyte * 128).from_buffer_copy(uid)   # (a c_char array would stop at the first NUL)
             self._call("create_slab", C.byref(self._sh.c), C.byref(opts), C.byref(so), C.byref(self._h))
         self.slab = slab
         lay = LayoutC()
