@@ -117,6 +117,17 @@ struct SlabDev {
     float haloWidth;              // particles within this distance of a face are mirrored on the neighbour
 };
 
+// slab mode: the blood cells this rank owns, compacted per type every step (device resident).  Type t's cells sit in
+// cells[typeFirst[t] .. typeFirst[t] + count[t]) in no particular order; blockStart is the exclusive prefix of
+// ceil(count[t] / cellsPerBlock[t]) used by the kernels that give a CTA a group of whole blood cells.
+struct OwnedLists {
+    const int* cells;          // null = no slab decomposition (all cells, identity order)
+    const int* count;          // [n_types]
+    const int* blockStart;     // [n_types + 1]
+    const int* cellPrefix;     // [n_types + 1] exclusive prefix of count
+    int typeFirst[BCS_MAX_TYPES];
+};
+
 struct Counters {               // device-resident, see bcs_stats
     unsigned long long pairTests, pairHits, triTests, veinHits, teleported, oob;
     unsigned long long step;    // completed steps (drives the respawn RNG counter)

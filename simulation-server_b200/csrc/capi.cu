@@ -262,7 +262,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
     if (s->slab) {
-        a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.ownedCell = s->slab->ownedCell;
+        a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.lists = slab_lists(s->slab, s->types);
         a.ghostList = s->slab->ghostList; a.ghostCount = s->slab->ghostCount;
     }
     return a;
@@ -289,7 +289,7 @@ IntegrateArgs integrate_args(bcs_sim* s)
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
     a.mx = s->mx; a.my = s->my; a.mz = s->mz; a.endC = s->endC; a.endR = s->endR;
     a.counters = s->counters; a.seed = s->seed;
-    if (s->slab) { a.slab = s->slab->dev; a.ownedCell = s->slab->ownedCell; a.moveTo = s->slab->moveTo; }
+    if (s->slab) { a.slab = s->slab->dev; a.lists = slab_lists(s->slab, s->types); a.moveTo = s->slab->moveTo; }
     return a;
 }
 
@@ -308,7 +308,7 @@ void stage(bcs_sim* s, int st)
         a.types = s->types; a.plan = s->plan; a.phys = s->phys;
         a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
         a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
-        a.ownedCell = s->slab ? s->slab->ownedCell : nullptr;
+        if (s->slab) a.lists = slab_lists(s->slab, s->types);
         launch_springs(a, s->stream);
         break;
     }
@@ -334,6 +334,7 @@ SlabCtx slab_ctx(bcs_sim* s)
     SlabCtx c{};
     c.types = s->types; c.N = s->hs.N; c.B = s->hs.B; c.V = s->hs.V; c.T = s->hs.T;
     c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel;
+    c.plan = s->plan;
     c.stream = s->stream;
     return c;
 }
@@ -466,7 +467,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->tris = s->track(dev_alloc<TriPacked>(T));
         s->groupBox = s->track(dev_alloc<Aabb>((T + 7) / 8));
         s->cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
-        s->cullList = s->track(dev_alloc<CullEntry>(B));
+        s->cullList = s->track(dev_alloc<CullEntry>((size_t)B + N));   // blood cells + (slab mode) ghost particles
         s->cellSlab = s->track(dev_alloc<CellSlab>(s->tg.cells));
         s->groupSlab = s->track(dev_alloc<CellSlab>((T + 7) / 8));
         s->cullCount = s->track(dev_alloc<int>(1));

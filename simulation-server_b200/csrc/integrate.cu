@@ -84,30 +84,42 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     __shared__ int sOut[FINISH_THREADS];
     __shared__ int sCell[FINISH_THREADS];
     const PhysDev& ph = a.phys;
-    int t = 0;
-    while (t + 1 < a.types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
+    __shared__ int sCellId[FINISH_THREADS];
+    __shared__ float sY[FINISH_THREADS];
+    const OwnedLists& lists = a.lists;
+    int t = 0, firstIdx, nCells;
+    bool active = true;
+    if (lists.cells) {
+        // slab mode: groups of this rank's owned blood cells; surplus CTAs only take part in the step-counter hand-off
+        active = (int)blockIdx.x < lists.blockStart[a.types.n];
+        if (active) {
+            while (t + 1 < a.types.n && (int)blockIdx.x >= lists.blockStart[t + 1]) ++t;
+            firstIdx = ((int)blockIdx.x - lists.blockStart[t]) * plan.cellsPerBlock[t];
+            nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
+        } else {
+            firstIdx = 0; nCells = 0;
+        }
+    } else {
+        while (t + 1 < a.types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
+        firstIdx = ((int)blockIdx.x - plan.blockStart[t]) * plan.cellsPerBlock[t];
+        nCells = min(plan.cellsPerBlock[t], a.types.t[t].count - firstIdx);
+    }
     const TypeDev ty = a.types.t[t];
-    const int G = plan.cellsPerBlock[t];
-    const int firstCell = ((int)blockIdx.x - plan.blockStart[t]) * G;
-    const int nCells = min(G, ty.count - firstCell);
     const int nPart = nCells * ty.P;
-    const int basePart = ty.pStart + firstCell * ty.P;
     const int tid = threadIdx.x;
     const unsigned long long step = a.counters->step;   // read before any block can advance it (see below)
-
-    // slab mode: only owned blood cells are advanced
-    __shared__ unsigned char sOwn[FINISH_THREADS];
-    __shared__ float sY[FINISH_THREADS];
-    if (tid < nCells) sOwn[tid] = a.ownedCell ? a.ownedCell[ty.cStart + firstCell + tid] : 1;
+    if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
     __syncthreads();
-    const bool mine = tid < nPart && sOwn[tid / ty.P];
+    const bool mine = tid < nPart;
+    const int myCell = mine ? tid / ty.P : 0;
+    const int gidx = ty.pStart + (sCellId[myCell] - ty.cStart) * ty.P + (tid - myCell * ty.P);
 
     float4 x = make_float4(0, 0, 0, 0), v = x;
     bool out = false;
     if (mine) {
-        const float4 F = a.frc[basePart + tid];
-        v = a.vel[basePart + tid];
-        x = a.pos[basePart + tid];
+        const float4 F = a.frc[gidx];
+        v = a.vel[gidx];
+        x = a.pos[gidx];
         const float3 v0 = f3(v.x, v.y, v.z);
         const float3 v1 = v0 + ph.dt * xyz(F);
         const float3 dx = (0.5f * ph.dt) * (v1 + v0);
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     if (mine) {
         const int cell = tid / ty.P, k = tid - cell * ty.P;
         if (sCell[cell]) {
-            unsigned ctr[4] = {(unsigned)(ty.cStart + firstCell + cell), (unsigned)step, (unsigned)(step >> 32), 0u};
+            unsigned ctr[4] = {(unsigned)sCellId[cell], (unsigned)step, (unsigned)(step >> 32), 0u};
             philox4x32_10(ctr, (unsigned)a.seed, (unsigned)(a.seed >> 32));
             const float u1 = u01(ctr[0]), u2 = u01(ctr[1]);
             const float bx = (u1 - 0.5f) * 1.2f * ph.cylinder_radius, bz = (u2 - 0.5f) * 1.2f * ph.cylinder_radius;
@@ -142,14 +154,14 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
                             bz + a.mz[ty.mStart + k] - a.mz[ty.mStart], x.w);
             v = make_float4(ph.initvx, ph.initvy, ph.initvz, v.w);
         }
-        a.pos[basePart + tid] = x;
-        a.vel[basePart + tid] = v;
+        a.pos[gidx] = x;
+        a.vel[gidx] = v;
     }
     if (a.slab.enabled) {
         // ownership follows the blood cell's centre: which slab does it lie in after this step?
         sY[tid] = x.y;
         __syncthreads();
-        if (tid < nCells && sOwn[tid]) {
+        if (tid < nCells) {
             float cy = 0.f;
             for (int k = 0; k < ty.P; ++k) cy += sY[tid * ty.P + k];
             cy /= (float)ty.P;
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
             else if (cy >= a.slab.yHi && a.slab.rank > 0) target = a.slab.rank - 1;
             else if (cy < a.slab.yLo && a.slab.rank < a.slab.world - 1) target = a.slab.rank + 1;
             if (target == a.slab.rank) target = -1;
-            a.moveTo[ty.cStart + firstCell + tid] = (signed char)target;
+            a.moveTo[sCellId[tid]] = (signed char)target;
         }
     }
     // the last CTA to finish advances the step counter: by then every CTA has read `step`

@@ -69,7 +69,7 @@ struct SpringArgs {
     const int* sprAB;           // undirected springs: a | b << 16
     const float* sprL;
     const float* initR;         // [nModel]
-    const unsigned char* ownedCell;   // slab mode: [B] 1 = this rank owns the blood cell; null = all
+    OwnedLists lists;           // slab mode: owned blood cells (lists.cells == null otherwise)
 };
 void launch_springs(const SpringArgs& a, cudaStream_t st);
 
@@ -138,7 +138,7 @@ struct VeinCollideArgs {
     CellSlab* cellSlab;         // [cells]   padded slab along the mean triangle normal of the same range
     const unsigned char* groupLocal;    // slab mode: [(T+7)/8] slot groups refitted by this rank; null = all
     const unsigned char* triCellLocal;  // slab mode: [cells] triangle-grid cells refitted by this rank; null = all
-    const unsigned char* ownedCell;     // slab mode: [B] blood cells this rank owns; null = all
+    OwnedLists lists;                   // slab mode: owned blood cells (lists.cells == null otherwise)
     const int* ghostList;               // slab mode: ghost particle ids (splat-only pass) and their count
     const int* ghostCount;
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
@@ -174,7 +174,7 @@ struct IntegrateArgs {
     unsigned long long seed;
     // slab mode
     SlabDev slab;
-    const unsigned char* ownedCell;   // [B]
+    OwnedLists lists;                 // owned blood cells
     signed char* moveTo;              // [B] out: rank the blood cell migrates to after this step, -1 = stays
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);

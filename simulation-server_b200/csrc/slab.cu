@@ -75,6 +75,29 @@ __global__ void __launch_bounds__(256) slab_init_vertices_kernel(int V, SlabDev 
     vOwned[v] = (y >= slab.yLo && y < slab.yHi) ? 1 : 0;
 }
 
+// ---- owned-cell lists (rebuilt every step after the exchange) ---------------------------------------------------
+__global__ void __launch_bounds__(256) slab_list_cells_kernel(TypesDev types, int nCells, const unsigned char* __restrict__ ownedCell,
+                                                             int* __restrict__ cells, int* __restrict__ count)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells || !ownedCell[c]) return;
+    int t = 0;
+    while (t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
+    cells[types.t[t].cStart + atomicAdd(&count[t], 1)] = c;   // type t's segment starts at cStart_t (capacity = all its cells)
+}
+
+__global__ void slab_list_prefix_kernel(int nTypes, SpringPlan plan, const int* __restrict__ count, int* __restrict__ blockStart,
+                                        int* __restrict__ cellPrefix)
+{
+    int b = 0, c = 0;
+    for (int t = 0; t < nTypes; ++t) {
+        blockStart[t] = b; cellPrefix[t] = c;
+        b += (count[t] + plan.cellsPerBlock[t] - 1) / plan.cellsPerBlock[t];
+        c += count[t];
+    }
+    blockStart[nTypes] = b; cellPrefix[nTypes] = c;
+}
+
 // ---- pack ---------------------------------------------------------------------------------------------------
 // destination index: 0 = up (rank-1), 1 = down (rank+1), 2 = spawn rank (when it is not a neighbour)
 __device__ __forceinline__ int dest_of(const SlabDev& s, int target)
@@ -251,6 +274,10 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
         s->ghostCount = salloc<int>(s, 1);
         s->nActive = salloc<int>(s, 1);
         s->errorFlag = salloc<int>(s, 1);
+        s->listCells = salloc<int>(s, ctx.B);
+        s->listCount = salloc<int>(s, BCS_MAX_TYPES);
+        s->listBlockStart = salloc<int>(s, BCS_MAX_TYPES + 1);
+        s->listCellPrefix = salloc<int>(s, BCS_MAX_TYPES + 1);
 
         // static vein decomposition from the rest positions: owned vertices, halo lists, triangles to refit
         std::vector<unsigned char> vOwned(ctx.V);
@@ -386,7 +413,27 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
         for (char* raw : s->spawnRecvRaw)
             if (raw) unpack_one(s, ctx, raw, false);
     }
+    slab_build_lists(s, ctx);
     BCS_CUDA(cudaGetLastError());
+}
+
+void slab_build_lists(SlabState* s, const SlabCtx& ctx)
+{
+    cudaStream_t st = ctx.stream;
+    BCS_CUDA(cudaMemsetAsync(s->listCount, 0, BCS_MAX_TYPES * sizeof(int), st));
+    BCS_LAUNCH("slab_list_cells", st,
+               slab_list_cells_kernel<<<(ctx.B + 255) / 256, 256, 0, st>>>(ctx.types, ctx.B, s->ownedCell, s->listCells, s->listCount));
+    BCS_LAUNCH("slab_list_prefix", st,
+               slab_list_prefix_kernel<<<1, 1, 0, st>>>(ctx.types.n, ctx.plan, s->listCount, s->listBlockStart, s->listCellPrefix));
+    BCS_CUDA(cudaGetLastError());
+}
+
+OwnedLists slab_lists(const SlabState* s, const TypesDev& types)
+{
+    OwnedLists l{};
+    l.cells = s->listCells; l.count = s->listCount; l.blockStart = s->listBlockStart; l.cellPrefix = s->listCellPrefix;
+    for (int t = 0; t < types.n; ++t) l.typeFirst[t] = types.t[t].cStart;
+    return l;
 }
 
 void slab_prime(SlabState* s, const SlabCtx& ctx)
@@ -394,7 +441,7 @@ void slab_prime(SlabState* s, const SlabCtx& ctx)
     cudaStream_t st = ctx.stream;
     BCS_LAUNCH("slab_init_ownership", st,
                slab_init_ownership_kernel<<<(ctx.B + 127) / 128, 128, 0, st>>>(ctx.types, ctx.B, s->dev, ctx.pos, s->ownedCell, s->pflag, s->moveTo));
-    slab_end_of_step(s, ctx);   // nothing migrates (moveTo = -1): plain halo exchange
+    slab_end_of_step(s, ctx);   // nothing migrates (moveTo = -1): plain halo exchange (+ owned-cell lists)
     s->primed = true;
 }
 

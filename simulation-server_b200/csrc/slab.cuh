@@ -1,6 +1,7 @@
 // Slab (multi-GPU) mode: message formats and host-side state.  See slab.cu.
 #pragma once
 #include "bcs_internal.cuh"
+#include "kernels.cuh"
 
 namespace bcs {
 
@@ -31,6 +32,7 @@ struct SlabCtx {             // what the slab code needs from the simulation han
     TypesDev types;
     int N, B, V, T;
     float4 *pos, *vel, *frc, *vpos, *vvel;
+    SpringPlan plan;         // cells per CTA of the cell-group kernels
     cudaStream_t stream;
 };
 
@@ -49,6 +51,7 @@ struct SlabState {
     unsigned char *ownedCell = nullptr, *pflag = nullptr, *vOwned = nullptr, *groupLocal = nullptr, *triCellLocal = nullptr;
     signed char* moveTo = nullptr;
     int *ghostList = nullptr, *ghostCount = nullptr, *nActive = nullptr, *errorFlag = nullptr;
+    int *listCells = nullptr, *listCount = nullptr, *listBlockStart = nullptr, *listCellPrefix = nullptr;   // owned-cell lists
     char* sendRaw[3] = {nullptr, nullptr, nullptr};
     char* recvRaw[2] = {nullptr, nullptr};
     std::vector<char*> spawnRecvRaw;
@@ -69,6 +72,8 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
 void slab_destroy(SlabState* s);
 void slab_prime(SlabState* s, const SlabCtx& ctx);          // ownership from the uploaded state + first halo exchange
 void slab_end_of_step(SlabState* s, const SlabCtx& ctx);    // pack -> exchange -> unpack
+OwnedLists slab_lists(const SlabState* s, const TypesDev& types);
+void slab_build_lists(SlabState* s, const SlabCtx& ctx);       // compacted owned blood cells for the cell-group kernels
 void slab_unique_id(char out[128]);
 int slab_check_error(SlabState* s, cudaStream_t st);        // 1 if a message overflowed since creation
 

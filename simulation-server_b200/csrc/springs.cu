@@ -65,41 +65,50 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers,
                const int* __restrict__ adjJ, const float* __restrict__ adjL, const int* __restrict__ adjS,
                const int* __restrict__ sprAB, const float* __restrict__ sprL, const float* __restrict__ initR,
-               const unsigned char* __restrict__ ownedCell)
+               const OwnedLists lists)
 {
     __shared__ float4 sp[SPRING_THREADS], sv[SPRING_THREADS], sf[SPRING_THREADS];
     __shared__ float3 sc[SPRING_THREADS];
     extern __shared__ float3 sF[];   // cellsPerBlock * springsPerCell entries (plan.sharedBytes)
 
-    int t = 0;
-    while (t + 1 < types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
+    // which blood cells does this CTA own?  Whole-scene mode: consecutive cells of one type.  Slab mode: a group of
+    // entries of the rank's owned-cell list of one type (device-side counts: surplus CTAs leave at once).
+    __shared__ int sCellId[SPRING_THREADS];
+    int t = 0, firstIdx, nCells;
+    if (lists.cells) {
+        if ((int)blockIdx.x >= lists.blockStart[types.n]) return;
+        while (t + 1 < types.n && (int)blockIdx.x >= lists.blockStart[t + 1]) ++t;
+        firstIdx = ((int)blockIdx.x - lists.blockStart[t]) * plan.cellsPerBlock[t];
+        nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
+    } else {
+        while (t + 1 < types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
+        firstIdx = ((int)blockIdx.x - plan.blockStart[t]) * plan.cellsPerBlock[t];
+        nCells = min(plan.cellsPerBlock[t], types.t[t].count - firstIdx);
+    }
     const TypeDev ty = types.t[t];
-    const int G = plan.cellsPerBlock[t];
-    const int firstCell = ((int)blockIdx.x - plan.blockStart[t]) * G;
-    const int nCells = min(G, ty.count - firstCell);
     const int nPart = nCells * ty.P;
-    const int basePart = ty.pStart + firstCell * ty.P;
     const int tid = threadIdx.x;
-
-    // slab mode: only blood cells this rank owns are advanced (the others may hold stale data)
-    __shared__ unsigned char sOwn[SPRING_THREADS];
-    if (tid < nCells) sOwn[tid] = ownedCell ? ownedCell[ty.cStart + firstCell + tid] : 1;
+    if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
     __syncthreads();
+    // global particle index of this thread's particle
+    const int myCell = tid < nPart ? tid / ty.P : 0;
+    const int gidx = ty.pStart + (sCellId[myCell] - ty.cStart) * ty.P + (tid - myCell * ty.P);
+
     float4 p4 = make_float4(0, 0, 0, 0), v4 = p4, f4 = p4;
-    if (tid < nPart && sOwn[tid / ty.P]) {
-        p4 = pos[basePart + tid];
-        v4 = vel[basePart + tid];
-        f4 = frc[basePart + tid];
+    if (tid < nPart) {
+        p4 = pos[gidx];
+        v4 = vel[gidx];
+        f4 = frc[gidx];
         sp[tid] = p4; sv[tid] = v4; sf[tid] = f4;
     }
     __syncthreads();
-    if (tid < nCells && sOwn[tid]) {
+    if (tid < nCells) {
         // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60)
         float3 c = f3(0.f, 0.f, 0.f);
         for (int k = 0; k < ty.P; ++k) c = c + xyz(sp[tid * ty.P + k]);
         c = c / (float)ty.P;
         sc[tid] = c;
-        centers[ty.cStart + firstCell + tid] = make_float4(c.x, c.y, c.z, 0.f);
+        centers[sCellId[tid]] = make_float4(c.x, c.y, c.z, 0.f);
     }
     const bool pairwise = plan.pairwise[t];
     if (pairwise) {
@@ -109,14 +118,13 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
         const int total = nCells * ty.nSpr;
         for (int idx = tid; idx < total; idx += SPRING_THREADS) {
             const int cell = idx / ty.nSpr, k = idx - cell * ty.nSpr;
-            if (!sOwn[cell]) continue;
             const int ab = __ldg(sprAB + ty.sprStart + k);
             const int ia = cell * ty.P + (ab & 0xffff), ib = cell * ty.P + (ab >> 16);
             sF[idx] = spring_force(ph, xyz(sp[ia]), xyz(sv[ia]), xyz(sf[ia]), xyz(sp[ib]), xyz(sv[ib]), xyz(sf[ib]), __ldg(sprL + ty.sprStart + k));
         }
     }
     __syncthreads();
-    if (tid >= nPart || !sOwn[tid / ty.P]) return;
+    if (tid >= nPart) return;
 
     const int cell = tid / ty.P, inCell = tid - cell * ty.P, cellBase = cell * ty.P;
     const float3 position = xyz(p4), velocity = xyz(v4), initialForce = xyz(f4);
@@ -150,14 +158,14 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
     else env = G3 - ph.viscous_damping * velocity;
     newForce = newForce + env;
     const float3 out = (initialForce + newForce) / 2.0f;
-    frc[basePart + tid] = make_float4(out.x, out.y, out.z, 0.f);
+    frc[gidx] = make_float4(out.x, out.y, out.z, 0.f);
 }
 
 void launch_springs(const SpringArgs& a, cudaStream_t st)
 {
     BCS_LAUNCH("springs", st,
                springs_kernel<<<a.plan.totalBlocks, SPRING_THREADS, a.plan.sharedBytes, st>>>(a.types, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers,
-                                                                             a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.ownedCell));
+                                                                             a.adjJ, a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.lists));
     BCS_CUDA(cudaGetLastError());
 }
 

@@ -511,11 +511,17 @@ __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideA
                                                              int* __restrict__ listCount)
 {
     // one WARP per blood cell: lanes = particles for the bounding box, then lanes = candidate triangle cells
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= nCells) return;
-    if (a.ownedCell && !a.ownedCell[c]) return;
-    int t = 0;
-    while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int c = w, t = 0;
+    if (a.lists.cells) {
+        // slab mode: the w-th owned blood cell
+        if (w >= a.lists.cellPrefix[a.types.n]) return;
+        while (t + 1 < a.types.n && w >= a.lists.cellPrefix[t + 1]) ++t;
+        c = a.lists.cells[a.lists.typeFirst[t] + (w - a.lists.cellPrefix[t])];
+    } else {
+        if (c >= nCells) return;
+        while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+    }
     const TypeDev ty = a.types.t[t];
     const int first = ty.pStart + (c - ty.cStart) * ty.P;
     float lox = 3e38f, loy = 3e38f, loz = 3e38f, hix = -3e38f, hiy = -3e38f, hiz = -3e38f;
@@ -562,6 +568,33 @@ __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideA
         ent.mask = (unsigned long long)half[0] | ((unsigned long long)half[1] << 32);
     }
     if (lane == 0 && ent.mask != 0ull) list[atomicAdd(listCount, 1)] = ent;
+}
+
+// slab mode: ghost particles (owned by a neighbouring rank) enter the same work list as single-particle entries
+// (cell = -(particle id + 1)); they only deposit their wall-force splat, so that every rank sees all contributions
+// to the vein vertices it integrates, while the particle itself is updated by its owner.
+__global__ void __launch_bounds__(128) vein_cull_ghosts_kernel(const VeinCollideArgs a, CullEntry* __restrict__ list, int* __restrict__ listCount)
+{
+    const int n = *a.ghostCount;
+    const GridDev& g = a.tgrid;
+    const float r = a.phys.impactNear;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int pid = a.ghostList[k];
+        const float4 p = a.pos[pid];
+        const int pcx = axis_cell(p.x, g.minx, g.lenx, g.csx), pcy = axis_cell(p.y, g.miny, g.leny, g.csy), pcz = axis_cell(p.z, g.minz, g.lenz, g.csz);
+        if (pcx >= g.nx || pcy >= g.ny || pcz >= g.nz) continue;
+        const int cx0 = max(0, pcx - 1), cy0 = max(0, pcy - 1), cz0 = max(0, pcz - 1);
+        const int cx1 = min(g.nx - 1, pcx + 1), cy1 = min(g.ny - 1, pcy + 1), cz1 = min(g.nz - 1, pcz + 1);
+        CullEntry ent{-(pid + 1), cx0, cy0, cz0, 0ull};
+        for (int z = cz0; z <= cz1; ++z)
+            for (int y = cy0; y <= cy1; ++y)
+                for (int x = cx0; x <= cx1; ++x) {
+                    const int tc = (z * g.ny + y) * g.nx + x;
+                    if (box_overlap(a.cellBox[tc], p.x - r, p.y - r, p.z - r, p.x + r, p.y + r, p.z + r) && slab_near(a.cellSlab[tc], xyz(p), r))
+                        ent.mask |= 1ull << (((z - cz0) * 4 + (y - cy0)) * 4 + (x - cx0));
+                }
+        if (ent.mask) list[atomicAdd(listCount, 1)] = ent;
+    }
 }
 
 // Phase A restricted to the triangle cells the blood-cell cull marked (any visiting order; the winner is the
@@ -691,6 +724,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
     __shared__ unsigned long long sBest[COOP_THREADS];
     __shared__ int sPid[COOP_THREADS];
     __shared__ int sFallback[COOP_THREADS];
+    __shared__ unsigned char sSplatOnly[COOP_THREADS];   // ghost particle: wall-force splat only
     __shared__ int2 q1[Q1_CAP];
     __shared__ int4 q2[Q2_CAP];
     __shared__ int q3[COOP_THREADS];
@@ -718,10 +752,11 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
             const CullEntry ent = list[w / maxP];
             const int c = ent.cell, k = (int)(w % maxP);
             int t = 0;
-            while (t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
-            if (k < a.types.t[t].P) {
-                const int pid = a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k;
+            while (c >= 0 && t + 1 < a.types.n && c >= a.types.t[t + 1].cStart) ++t;
+            if (c < 0 ? k == 0 : k < a.types.t[t].P) {
+                const int pid = c < 0 ? -c - 1 : a.types.t[t].pStart + (c - a.types.t[t].cStart) * a.types.t[t].P + k;
                 sPid[tid] = pid;
+                sSplatOnly[tid] = c < 0;
                 const float4 p4 = a.pos[pid], v4 = a.vel[pid];
                 const float3 pos = xyz(p4);
                 const float3 dir = normalize(xyz(v4));
@@ -835,7 +870,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
 
         // ---- pass 4: particles with a near hit go to phase B; overflowed particles take the sequential path
         if (sPid[tid] >= 0) {
-            if (sFallback[tid]) vein_collide_particle<true, STATS>(a, sPid[tid], myTests);
+            if (sFallback[tid]) vein_collide_particle<true, STATS>(a, sPid[tid], myTests, sSplatOnly[tid] != 0);
             else if (sBest[tid] != ~0ull) q3[atomicAdd(&q3n, 1)] = tid;
         }
         __syncthreads();
@@ -894,7 +929,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
                 RayHit h;
                 ray_triangle(pos, dir, load_tri(a.tris, bestSlot), h);
                 const int pid = sPid[pl];
-                vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], dir, h);
+                vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], dir, h, sSplatOnly[pl] != 0);
             }
         }
         __syncthreads();
@@ -917,11 +952,14 @@ __global__ void __launch_bounds__(128) vein_ghost_splat_kernel(const VeinCollide
 
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
 {
-    if (a.ghostList && a.apply && !a.dbgTri) BCS_LAUNCH("vein_ghost_splat", st, vein_ghost_splat_kernel<<<64, 128, 0, st>>>(a));
+    static const bool sequentialEnv = getenv("BCS_VEIN_SEQUENTIAL") != nullptr;
+    const bool coop = a.fast && a.cullList && !a.dbgTri && !sequentialEnv;
+    if (a.ghostList && a.apply && !a.dbgTri && !coop) BCS_LAUNCH("vein_ghost_splat", st, vein_ghost_splat_kernel<<<64, 128, 0, st>>>(a));
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
     if (a.fast && a.cullList && !a.dbgTri) {
         BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
         BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells * 32 + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
+        if (a.ghostList && a.apply && coop) BCS_LAUNCH("vein_cull_ghosts", st, vein_cull_ghosts_kernel<<<32, 128, 0, st>>>(a, a.cullList, a.cullCount));
         const int grid = min(blocks, 148 * 16);
         static const bool sequential = getenv("BCS_VEIN_SEQUENTIAL") != nullptr;
         if (sequential) {
