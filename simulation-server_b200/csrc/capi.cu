@@ -746,7 +746,8 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
     BCS_REQUIRE(s && nsteps >= 0, BCS_ERR_INVALID, "bad argument");
     CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
-    if (!s->useGraph || s->slab) {
+    if (s->slab && !s->slab->primed) slab_prime(s->slab, slab_ctx(s));   // ownership + first halo exchange, outside any capture
+    if (!s->useGraph) {
         for (int i = 0; i < nsteps; ++i) enqueue_step(s);
     } else {
         if (!s->graphExec) {

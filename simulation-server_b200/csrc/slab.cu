@@ -80,10 +80,19 @@ __global__ void __launch_bounds__(256) slab_list_cells_kernel(TypesDev types, in
                                                              int* __restrict__ cells, int* __restrict__ count)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCells || !ownedCell[c]) return;
+    const bool own = c < nCells && ownedCell[c];
     int t = 0;
-    while (t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
-    cells[types.t[t].cStart + atomicAdd(&count[t], 1)] = c;   // type t's segment starts at cStart_t (capacity = all its cells)
+    while (own && t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
+    // warp-aggregated append: one atomic per (warp, type) instead of one per blood cell
+    const unsigned active = __ballot_sync(0xffffffffu, own);
+    if (own) {
+        const unsigned peers = __match_any_sync(active, t);
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&count[t], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        cells[types.t[t].cStart + base + __popc(peers & ((1u << lane) - 1u))] = c;   // type t's segment starts at cStart_t
+    }
 }
 
 __global__ void slab_list_prefix_kernel(int nTypes, SpringPlan plan, const int* __restrict__ count, int* __restrict__ blockStart,

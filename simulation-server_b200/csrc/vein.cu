@@ -575,25 +575,28 @@ __global__ void __launch_bounds__(128) vein_cull_cells_kernel(const VeinCollideA
 // to the vein vertices it integrates, while the particle itself is updated by its owner.
 __global__ void __launch_bounds__(128) vein_cull_ghosts_kernel(const VeinCollideArgs a, CullEntry* __restrict__ list, int* __restrict__ listCount)
 {
+    // one warp per ghost: lane = one of the 27 triangle cells around it
     const int n = *a.ghostCount;
     const GridDev& g = a.tgrid;
     const float r = a.phys.impactNear;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, warpsTotal = (gridDim.x * blockDim.x) >> 5;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warpsTotal) {
         const int pid = a.ghostList[k];
         const float4 p = a.pos[pid];
         const int pcx = axis_cell(p.x, g.minx, g.lenx, g.csx), pcy = axis_cell(p.y, g.miny, g.leny, g.csy), pcz = axis_cell(p.z, g.minz, g.lenz, g.csz);
         if (pcx >= g.nx || pcy >= g.ny || pcz >= g.nz) continue;
         const int cx0 = max(0, pcx - 1), cy0 = max(0, pcy - 1), cz0 = max(0, pcz - 1);
-        const int cx1 = min(g.nx - 1, pcx + 1), cy1 = min(g.ny - 1, pcy + 1), cz1 = min(g.nz - 1, pcz + 1);
-        CullEntry ent{-(pid + 1), cx0, cy0, cz0, 0ull};
-        for (int z = cz0; z <= cz1; ++z)
-            for (int y = cy0; y <= cy1; ++y)
-                for (int x = cx0; x <= cx1; ++x) {
-                    const int tc = (z * g.ny + y) * g.nx + x;
-                    if (box_overlap(a.cellBox[tc], p.x - r, p.y - r, p.z - r, p.x + r, p.y + r, p.z + r) && slab_near(a.cellSlab[tc], xyz(p), r))
-                        ent.mask |= 1ull << (((z - cz0) * 4 + (y - cy0)) * 4 + (x - cx0));
-                }
-        if (ent.mask) list[atomicAdd(listCount, 1)] = ent;
+        const int x = cx0 + lane % 3, y = cy0 + (lane / 3) % 3, z = cz0 + lane / 9;
+        bool pass = lane < 27 && x <= min(g.nx - 1, pcx + 1) && y <= min(g.ny - 1, pcy + 1) && z <= min(g.nz - 1, pcz + 1);
+        if (pass) {
+            const int tc = (z * g.ny + y) * g.nx + x;
+            pass = box_overlap(a.cellBox[tc], p.x - r, p.y - r, p.z - r, p.x + r, p.y + r, p.z + r) && slab_near(a.cellSlab[tc], xyz(p), r);
+        }
+        // bit layout of CullEntry::mask: ((dz*4 + dy)*4 + dx)
+        unsigned long long mine = pass ? 1ull << (((z - cz0) * 4 + (y - cy0)) * 4 + (x - cx0)) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) list[atomicAdd(listCount, 1)] = CullEntry{-(pid + 1), cx0, cy0, cz0, mine};
     }
 }
 
@@ -959,7 +962,7 @@ void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st)
     if (a.fast && a.cullList && !a.dbgTri) {
         BCS_CUDA(cudaMemsetAsync(a.cullCount, 0, sizeof(int), st));
         BCS_LAUNCH("vein_cull_cells", st, vein_cull_cells_kernel<<<(a.nCells * 32 + 127) / 128, 128, 0, st>>>(a, a.nCells, a.cullList, a.cullCount));
-        if (a.ghostList && a.apply && coop) BCS_LAUNCH("vein_cull_ghosts", st, vein_cull_ghosts_kernel<<<32, 128, 0, st>>>(a, a.cullList, a.cullCount));
+        if (a.ghostList && a.apply && coop) BCS_LAUNCH("vein_cull_ghosts", st, vein_cull_ghosts_kernel<<<148, 128, 0, st>>>(a, a.cullList, a.cullCount));
         const int grid = min(blocks, 148 * 16);
         static const bool sequential = getenv("BCS_VEIN_SEQUENTIAL") != nullptr;
         if (sequential) {
