@@ -483,7 +483,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->counters = s->track(dev_alloc<Counters>(1));
         s->stagingLen = std::max(std::max(N, V), std::max(B, T));
         s->staging = s->track(dev_alloc<float>(3 * (size_t)s->stagingLen));
-        s->sortP.allocate(N);
+        s->sortP.allocate(N, s->pg.cells / 32 + 2);
         s->sortT.allocate(T);
 
         // vein vertices -> device, triangle centres (calculateCentersKernel, run once), static triangle grid

@@ -8,6 +8,7 @@
 #include "device_math.cuh"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
@@ -516,6 +517,179 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_compact_kernel(const int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Occupancy-rank counting sort (clean semantics, particle grid; BCS_GRID=radix selects the radix path above).
+// The compact cell index already knows the sorted order of the occupied cells: rank(cell) = number of set
+// occupancy bits before it.  So the (cell id, particle id) order needs no key sort at all:
+//   1 mark      key per particle, occupancy bit set (atomicOr)
+//   2 rank      exclusive prefix popcount over the mask words            -> cellRank, numOcc
+//   3 count     per particle: r = rank(cell); place = atomicAdd(count[r]) (arbitrary order inside a cell)
+//   4 starts    exclusive scan of count[0..numOcc)                       -> occStart
+//   5 scatter   tmp[occStart[r] + place] = particle                      (cells contiguous, unordered inside)
+//   6 order     per slot: position inside its cell = #ids of the cell smaller than its own (cells hold ~1-12
+//               particles) -> final slot; write keys / ids / occKey and gather pos+vel into slot order
+// Every pass is a plain streaming kernel (no look-back chains, no tile tickets), which is what matters when a
+// rank of the slab decomposition holds only ~100 k particles.  Outputs are identical to the radix path.
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_sum(int v, int* warpSum)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int s = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) s += warpSum[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(256) cs_mark_kernel(const float4* __restrict__ pos, const unsigned char* __restrict__ pflag, GridDev g,
+                                                      int* __restrict__ keyOf, unsigned* __restrict__ cellMask, Counters* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const unsigned char f = pflag ? pflag[i] : 1;
+    if (!f) return;
+    const float4 p = pos[i];
+    const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
+    int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
+              axis_cell(p.x, g.minx, g.lenx, g.csx);
+    if (oob) {
+        if (f & 1) atomicAdd(&counters->oob, 1ull);
+        key = max(0, min(key, g.cells - 1));
+    } else if (key >= g.cells) {
+        key = g.cells - 1;
+    }
+    keyOf[i] = key;
+    const unsigned bit = 1u << (key & 31);
+    if (!(cellMask[key >> 5] & bit)) atomicOr(&cellMask[key >> 5], bit);
+}
+
+// per-tile totals of popc(mask word) (MODE 0) or of the per-cell counts (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) cs_tile_totals_kernel(const unsigned* __restrict__ in, int nArg, const int* __restrict__ nDev,
+                                                                      int* __restrict__ tileTotal)
+{
+    __shared__ int warpSum[SCAN_THREADS / 32];
+    const int n = nDev ? *nDev : nArg;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int c = 0;
+    if (base < n) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < n) c += MODE == 0 ? __popc(in[base + k]) : (int)in[base + k];
+    }
+    const int s = block_sum(c, warpSum);
+    if (threadIdx.x == 0) tileTotal[blockIdx.x] = s;
+}
+
+// exclusive scan: out[i] = sum of f(in[j]) for j < i; out[n] (MODE 1) / *total = grand total
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* __restrict__ in, int nArg, const int* __restrict__ nDev,
+                                                               const int* __restrict__ tileTotal, int* __restrict__ out, int* __restrict__ total,
+                                                               int finalValue, const int* __restrict__ finalValueDev)
+{
+    __shared__ int warpSum[SCAN_THREADS / 32];
+    __shared__ int sBase;
+    const int n = nDev ? *nDev : nArg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int)blockIdx.x * SCAN_TILE >= n && !(blockIdx.x == 0)) return;
+    int acc = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += SCAN_THREADS) acc += tileTotal[b];
+    const int tileBase = block_sum(acc, warpSum);
+    const int base = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
+    int v[SCAN_ITEMS], mine = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? (MODE == 0 ? __popc(in[base + k]) : (int)in[base + k]) : 0;
+        mine += v[k];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += warpSum[w];
+    int run = tileBase + wbase + incl - mine;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    // the thread holding element n-1 (or thread 0 of block 0 when n == 0) publishes the grand total
+    const bool last = (n > 0) ? (base <= n - 1 && n - 1 < base + SCAN_ITEMS) : (blockIdx.x == 0 && tid == 0);
+    if (last) {
+        if (total) *total = run;
+        if (MODE == 1) out[n] = finalValueDev ? *finalValueDev : finalValue;   // occStart[numOcc] = number of sorted slots
+    }
+    (void)sBase;
+}
+
+__global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ keyOf,
+                                                       const unsigned* __restrict__ cellMask, const int* __restrict__ cellRank,
+                                                       unsigned* __restrict__ cellCount, int* __restrict__ rankOf, int* __restrict__ placeOf,
+                                                       int* __restrict__ nActive)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = i < n && (pflag ? pflag[i] != 0 : true);
+    if (act) {
+        const int key = keyOf[i];
+        const int r = cellRank[key >> 5] + __popc(cellMask[key >> 5] & ((1u << (key & 31)) - 1u));
+        rankOf[i] = r;
+        placeOf[i] = (int)atomicAdd(&cellCount[r], 1u);
+    }
+    if (nActive) {
+        // number of active particles (slab mode), warp-aggregated
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(nActive, __popc(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) cs_scatter_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ rankOf,
+                                                         const int* __restrict__ placeOf, const int* __restrict__ occStart,
+                                                         int* __restrict__ tmpIds, int* __restrict__ tmpRank)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char f = pflag ? pflag[i] : 1;
+    if (!f) return;
+    const int r = rankOf[i];
+    const int slot = occStart[r] + placeOf[i];
+    tmpIds[slot] = (f & 1) ? i : (i | (int)0x80000000);   // ghost tag (slab mode)
+    tmpRank[slot] = r;
+}
+
+template <bool REORDER>
+__global__ void __launch_bounds__(256) cs_order_kernel(int nArg, const int* __restrict__ nDev, const int* __restrict__ tmpIds,
+                                                       const int* __restrict__ tmpRank, const int* __restrict__ occStart, const int* __restrict__ keyOf,
+                                                       int* __restrict__ keys, int* __restrict__ ids, int* __restrict__ occKey,
+                                                       const float4* __restrict__ pos, const float4* __restrict__ vel, float4* __restrict__ spos,
+                                                       float4* __restrict__ svel)
+{
+    const int n = nDev ? *nDev : nArg;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int r = tmpRank[j];
+    const int s = occStart[r], e = occStart[r + 1];
+    const int tag = tmpIds[j], pid = tag & 0x7fffffff;
+    int before = 0;
+    for (int k = s; k < e; ++k) before += (tmpIds[k] & 0x7fffffff) < pid;
+    const int slot = s + before;
+    const int key = keyOf[pid];
+    keys[slot] = key;
+    ids[slot] = tag;
+    if (before == 0) occKey[r] = key;
+    if (REORDER) reorder_slot(slot, tag, false, pos, vel, spos, svel);
+}
+
+// ------------------------------------------------------------------------------------------------
 // slab mode: cell keys of the active particles (pflag bit 0 = owned, bit 1 = ghost), compacted in ascending
 // particle id so that the stable sort still ends in (cell id, particle id) order
 // ------------------------------------------------------------------------------------------------
@@ -610,7 +784,7 @@ __global__ void __launch_bounds__(FIN_THREADS) slab_keys_kernel(const float4* __
 // ------------------------------------------------------------------------------------------------
 // host-side driver
 // ------------------------------------------------------------------------------------------------
-void SortScratch::allocate(int n)
+void SortScratch::allocate(int n, int maskWordsHint)
 {
     numTiles = (n + SORT_TILE - 1) / SORT_TILE;
     BCS_CUDA(cudaMalloc(&tileHist, (size_t)numTiles * 256 * sizeof(unsigned)));
@@ -618,6 +792,16 @@ void SortScratch::allocate(int n)
     BCS_CUDA(cudaMalloc(&status, (size_t)4 * numTiles * 256 * sizeof(unsigned)));
     const char* mode = getenv("BCS_SORT");
     classic = mode && std::string(mode) == "classic";
+    const char* gridMode = getenv("BCS_GRID");
+    radixForCompact = gridMode && std::string(gridMode) == "radix";
+    // counting-sort scratch
+    BCS_CUDA(cudaMalloc(&keyOf, (size_t)n * sizeof(int)));
+    BCS_CUDA(cudaMalloc(&rankOf, (size_t)n * sizeof(int)));
+    BCS_CUDA(cudaMalloc(&placeOf, (size_t)n * sizeof(int)));
+    BCS_CUDA(cudaMalloc(&tmpIds, (size_t)n * sizeof(int)));
+    BCS_CUDA(cudaMalloc(&tmpRank, (size_t)n * sizeof(int)));
+    BCS_CUDA(cudaMalloc(&cellCount, ((size_t)n + 1) * sizeof(unsigned)));
+    BCS_CUDA(cudaMalloc(&scanTotals, (size_t)(std::max(n, maskWordsHint) / SCAN_TILE + 2) * sizeof(int)));
     BCS_CUDA(cudaMalloc(&finTileCount, (size_t)((n + FIN_TILE - 1) / FIN_TILE + 1) * sizeof(int)));
 }
 void SortScratch::release()
@@ -626,13 +810,51 @@ void SortScratch::release()
     cudaFree(digitTotals);
     cudaFree(finTileCount);
     cudaFree(status);
+    cudaFree(keyOf); cudaFree(rankOf); cudaFree(placeOf); cudaFree(tmpIds); cudaFree(tmpRank); cudaFree(cellCount); cudaFree(scanTotals);
+    keyOf = rankOf = placeOf = tmpIds = tmpRank = scanTotals = nullptr;
+    cellCount = nullptr;
     status = nullptr;
     tileHist = digitTotals = nullptr;
     finTileCount = nullptr;
 }
 
+static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
+{
+    const GridDev& g = a.grid;
+    const int n = g.n, blocks = (n + 255) / 256;
+    SortScratch* sc = a.scratch;
+    BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
+    BCS_CUDA(cudaMemsetAsync(sc->cellCount, 0, ((size_t)n + 1) * sizeof(unsigned), st));
+    if (a.nDevOut) BCS_CUDA(cudaMemsetAsync(a.nDevOut, 0, sizeof(int), st));
+    BCS_LAUNCH("cell_keys", st, cs_mark_kernel<<<blocks, 256, 0, st>>>(a.objPos, a.pflag, g, sc->keyOf, a.cellMask, a.counters));
+    const int maskTiles = (a.maskWords + SCAN_TILE - 1) / SCAN_TILE;
+    BCS_LAUNCH("cell_rank_totals", st, cs_tile_totals_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals));
+    BCS_LAUNCH("cell_rank_scan", st,
+               cs_scan_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals, a.cellRank, a.numOcc, 0, nullptr));
+    BCS_LAUNCH("cell_count", st,
+               cs_count_kernel<<<blocks, 256, 0, st>>>(a.pflag, n, sc->keyOf, a.cellMask, a.cellRank, sc->cellCount, sc->rankOf, sc->placeOf, a.nDevOut));
+    const int cntTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    BCS_LAUNCH("cell_start_totals", st, cs_tile_totals_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals));
+    BCS_LAUNCH("cell_start_scan", st,
+               cs_scan_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals, a.occStart, nullptr, n, a.nDev));
+    BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<blocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank));
+    if (a.reorder)
+        BCS_LAUNCH("finalize_grid", st,
+                   cs_order_kernel<true><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
+                                                                 a.pos, a.vel, a.spos, a.svel));
+    else
+        BCS_LAUNCH("finalize_grid", st,
+                   cs_order_kernel<false><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
+                                                                  nullptr, nullptr, nullptr, nullptr));
+    BCS_CUDA(cudaGetLastError());
+}
+
 void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
 {
+    if (a.compact && !a.scratch->radixForCompact) {
+        launch_grid_build_counting(a, st);
+        return;
+    }
     const GridDev& g = a.grid;
     const int n = g.n;
     const int passes = (g.keyBits + 7) / 8;

@@ -10,10 +10,14 @@ struct SortScratch {
     unsigned* tileHist = nullptr;      // [numTiles][256] per-tile digit counts -> global offsets
     unsigned* digitTotals = nullptr;   // [4][256] whole-array digit counts per pass
     int numTiles = 0;
+    // occupancy-rank counting sort (compact cell index)
+    bool radixForCompact = false;      // BCS_GRID=radix: build the compact index from a radix sort instead
+    int *keyOf = nullptr, *rankOf = nullptr, *placeOf = nullptr, *tmpIds = nullptr, *tmpRank = nullptr, *scanTotals = nullptr;
+    unsigned* cellCount = nullptr;
     int* finTileCount = nullptr;       // occupied-cell starts per finalize tile (compact index build)
     unsigned* status = nullptr;        // [4][numTiles][256] look-back status words of the onesweep passes
     bool classic = false;              // BCS_SORT=classic: 3-kernel passes (histogram, scan, scatter) instead of onesweep
-    void allocate(int n);
+    void allocate(int n, int maskWordsHint = 0);
     void release();
 };
 

@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "bcs_internal.cuh"
@@ -364,7 +365,8 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
         }
         s->buf.capMig = s->capMig; s->buf.capHalo = s->capHalo;
 
-        if (init.world > 1) {
+        // BCS_SLAB_NO_COMM=1: profiling aid - one rank of an N-rank decomposition runs alone (no NCCL, no halos)
+        if (init.world > 1 && !getenv("BCS_SLAB_NO_COMM")) {
             ncclUniqueId id;
             std::memcpy(&id, init.ncclId, 128);
             ncclComm_t comm;
@@ -415,7 +417,7 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
                        slab_pack_vertices_kernel<<<(s->vertCount[d] + 255) / 256, 256, 0, st>>>(s->vertList[d], s->vertCount[d], ctx.vpos,
                                                                                               ctx.vvel, vertex_region(s, s->sendRaw[d])));
     BCS_CUDA(cudaGetLastError());
-    if (s->dev.world > 1) {
+    if (s->dev.world > 1 && s->comm) {
         s->exchange(st);
         if (s->dev.rank > 0) unpack_one(s, ctx, s->recvRaw[0], true);
         if (s->dev.rank < s->dev.world - 1) unpack_one(s, ctx, s->recvRaw[1], true);
