@@ -128,6 +128,15 @@ struct OwnedLists {
     int typeFirst[BCS_MAX_TYPES];
 };
 
+// slab mode: enumeration of this rank's ACTIVE particles (owned blood cells x particles, then the ghosts) so that the
+// per-particle kernels of the grid build and of the exchange touch N_local instead of N entries
+struct ActiveItems {
+    OwnedLists lists;          // lists.cells == null: not in slab mode (kernels index all particles)
+    const int* ghostList;
+    const int* ghostCount;
+    int maxP;
+};
+
 struct Counters {               // device-resident, see bcs_stats
     unsigned long long pairTests, pairHits, triTests, veinHits, teleported, oob;
     unsigned long long step;    // completed steps (drives the respawn RNG counter)

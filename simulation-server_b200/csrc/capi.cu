@@ -221,7 +221,13 @@ GridBuildArgs particle_grid_args(bcs_sim* s)
     a.occStart = s->occStart; a.occKey = s->occKey; a.numOcc = s->numOcc;
     a.reorder = true;
     a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
-    if (s->slab) { a.pflag = s->slab->pflag; a.nDev = s->slab->nActive; a.nDevOut = s->slab->nActive; }
+    if (s->slab) {
+        a.pflag = s->slab->pflag; a.nDev = s->slab->nActive; a.nDevOut = s->slab->nActive;
+        a.items.lists = slab_lists(s->slab, s->types); a.items.ghostList = s->slab->ghostList; a.items.ghostCount = s->slab->ghostCount;
+        a.items.maxP = s->maxP;
+        a.itemCapacity = (long long)s->hs.B * s->maxP + s->hs.N;
+        a.types = s->types;
+    }
     return a;
 }
 
@@ -335,6 +341,7 @@ SlabCtx slab_ctx(bcs_sim* s)
     c.types = s->types; c.N = s->hs.N; c.B = s->hs.B; c.V = s->hs.V; c.T = s->hs.T;
     c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel;
     c.plan = s->plan;
+    c.maxP = s->maxP;
     c.stream = s->stream;
     return c;
 }

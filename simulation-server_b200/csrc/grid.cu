@@ -547,12 +547,18 @@ __device__ __forceinline__ int block_sum(int v, int* warpSum)
 }
 
 __global__ void __launch_bounds__(256) cs_mark_kernel(const float4* __restrict__ pos, const unsigned char* __restrict__ pflag, GridDev g,
-                                                      int* __restrict__ keyOf, unsigned* __restrict__ cellMask, Counters* __restrict__ counters)
+                                                      int* __restrict__ keyOf, unsigned* __restrict__ cellMask, Counters* __restrict__ counters,
+                                                      const ActiveItems act, const TypesDev types)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n) return;
-    const unsigned char f = pflag ? pflag[i] : 1;
-    if (!f) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
+    if (act.lists.cells) {
+        i = active_item(act, types, i, f);
+        if (i < 0) return;
+    } else {
+        if (i >= g.n) return;
+        f = pflag ? pflag[i] : 1;
+        if (!f) return;
+    }
     const float4 p = pos[i];
     const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
     int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
@@ -577,8 +583,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_tile_totals_kernel(const unsi
     const int n = nDev ? *nDev : nArg;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int c = 0;
-    if (base < n) {
+    if (base + SCAN_ITEMS <= n) {
+        const uint4* in4 = reinterpret_cast<const uint4*>(in + base);   // base is a multiple of 16 words
 #pragma unroll
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            const uint4 q = in4[k];
+            c += MODE == 0 ? __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w) : (int)(q.x + q.y + q.z + q.w);
+        }
+    } else if (base < n) {
         for (int k = 0; k < SCAN_ITEMS; ++k)
             if (base + k < n) c += MODE == 0 ? __popc(in[base + k]) : (int)in[base + k];
     }
@@ -602,11 +614,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* _
     const int tileBase = block_sum(acc, warpSum);
     const int base = blockIdx.x * SCAN_TILE + tid * SCAN_ITEMS;
     int v[SCAN_ITEMS], mine = 0;
+    if (base + SCAN_ITEMS <= n) {
+        const uint4* in4 = reinterpret_cast<const uint4*>(in + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < n) ? (MODE == 0 ? __popc(in[base + k]) : (int)in[base + k]) : 0;
-        mine += v[k];
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            const uint4 q = in4[k];
+            v[4 * k] = MODE == 0 ? __popc(q.x) : (int)q.x; v[4 * k + 1] = MODE == 0 ? __popc(q.y) : (int)q.y;
+            v[4 * k + 2] = MODE == 0 ? __popc(q.z) : (int)q.z; v[4 * k + 3] = MODE == 0 ? __popc(q.w) : (int)q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? (MODE == 0 ? __popc(in[base + k]) : (int)in[base + k]) : 0;
     }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) mine += v[k];
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -618,10 +639,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* _
     int wbase = 0;
     for (int w = 0; w < warp; ++w) wbase += warpSum[w];
     int run = tileBase + wbase + incl - mine;
+    if (base + SCAN_ITEMS <= n) {
+        int4* out4 = reinterpret_cast<int4*>(out + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < n) out[base + k] = run;
-        run += v[k];
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            int4 o;
+            o.x = run; run += v[4 * k]; o.y = run; run += v[4 * k + 1]; o.z = run; run += v[4 * k + 2]; o.w = run; run += v[4 * k + 3];
+            out4[k] = o;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < n) out[base + k] = run;
+            run += v[k];
+        }
     }
     // the thread holding element n-1 (or thread 0 of block 0 when n == 0) publishes the grand total
     const bool last = (n > 0) ? (base <= n - 1 && n - 1 < base + SCAN_ITEMS) : (blockIdx.x == 0 && tid == 0);
@@ -635,10 +666,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* _
 __global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ keyOf,
                                                        const unsigned* __restrict__ cellMask, const int* __restrict__ cellRank,
                                                        unsigned* __restrict__ cellCount, int* __restrict__ rankOf, int* __restrict__ placeOf,
-                                                       int* __restrict__ nActive)
+                                                       int* __restrict__ nActive, const ActiveItems items, const TypesDev types)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = i < n && (pflag ? pflag[i] != 0 : true);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool act;
+    if (items.lists.cells) {
+        int f;
+        i = active_item(items, types, i, f);
+        act = i >= 0;
+    } else {
+        act = i < n && (pflag ? pflag[i] != 0 : true);
+    }
     if (act) {
         const int key = keyOf[i];
         const int r = cellRank[key >> 5] + __popc(cellMask[key >> 5] & ((1u << (key & 31)) - 1u));
@@ -646,20 +684,26 @@ __global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __re
         placeOf[i] = (int)atomicAdd(&cellCount[r], 1u);
     }
     if (nActive) {
-        // number of active particles (slab mode), warp-aggregated
-        const unsigned m = __ballot_sync(0xffffffffu, act);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(nActive, __popc(m));
+        // number of active particles (slab mode): one atomic per CTA
+        const int blockActive = __syncthreads_count(act);
+        if (threadIdx.x == 0 && blockActive) atomicAdd(nActive, blockActive);
     }
 }
 
 __global__ void __launch_bounds__(256) cs_scatter_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ rankOf,
                                                          const int* __restrict__ placeOf, const int* __restrict__ occStart,
-                                                         int* __restrict__ tmpIds, int* __restrict__ tmpRank)
+                                                         int* __restrict__ tmpIds, int* __restrict__ tmpRank, const ActiveItems items,
+                                                         const TypesDev types)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned char f = pflag ? pflag[i] : 1;
-    if (!f) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
+    if (items.lists.cells) {
+        i = active_item(items, types, i, f);
+        if (i < 0) return;
+    } else {
+        if (i >= n) return;
+        f = pflag ? pflag[i] : 1;
+        if (!f) return;
+    }
     const int r = rankOf[i];
     const int slot = occStart[r] + placeOf[i];
     tmpIds[slot] = (f & 1) ? i : (i | (int)0x80000000);   // ghost tag (slab mode)
@@ -822,22 +866,26 @@ static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
 {
     const GridDev& g = a.grid;
     const int n = g.n, blocks = (n + 255) / 256;
+    // slab mode enumerates owned cells x maxP (padding included) + ghosts: launched for that capacity, CTAs past the
+    // device-side item count leave at once
+    const int itemBlocks = a.items.lists.cells ? (int)(((long long)a.itemCapacity + 255) / 256) : blocks;
     SortScratch* sc = a.scratch;
     BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
     BCS_CUDA(cudaMemsetAsync(sc->cellCount, 0, ((size_t)n + 1) * sizeof(unsigned), st));
     if (a.nDevOut) BCS_CUDA(cudaMemsetAsync(a.nDevOut, 0, sizeof(int), st));
-    BCS_LAUNCH("cell_keys", st, cs_mark_kernel<<<blocks, 256, 0, st>>>(a.objPos, a.pflag, g, sc->keyOf, a.cellMask, a.counters));
+    BCS_LAUNCH("cell_keys", st, cs_mark_kernel<<<itemBlocks, 256, 0, st>>>(a.objPos, a.pflag, g, sc->keyOf, a.cellMask, a.counters, a.items, a.types));
     const int maskTiles = (a.maskWords + SCAN_TILE - 1) / SCAN_TILE;
     BCS_LAUNCH("cell_rank_totals", st, cs_tile_totals_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals));
     BCS_LAUNCH("cell_rank_scan", st,
                cs_scan_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals, a.cellRank, a.numOcc, 0, nullptr));
     BCS_LAUNCH("cell_count", st,
-               cs_count_kernel<<<blocks, 256, 0, st>>>(a.pflag, n, sc->keyOf, a.cellMask, a.cellRank, sc->cellCount, sc->rankOf, sc->placeOf, a.nDevOut));
+               cs_count_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->keyOf, a.cellMask, a.cellRank, sc->cellCount, sc->rankOf, sc->placeOf, a.nDevOut,
+                                                       a.items, a.types));
     const int cntTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     BCS_LAUNCH("cell_start_totals", st, cs_tile_totals_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals));
     BCS_LAUNCH("cell_start_scan", st,
                cs_scan_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals, a.occStart, nullptr, n, a.nDev));
-    BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<blocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank));
+    BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank, a.items, a.types));
     if (a.reorder)
         BCS_LAUNCH("finalize_grid", st,
                    cs_order_kernel<true><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,

@@ -121,14 +121,22 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(TypesDev types, int n, S
                                                        const float4* __restrict__ vel, const float4* __restrict__ frc,
                                                        unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                        const signed char* __restrict__ moveTo, SlabBuffers buf, int* __restrict__ ghostList,
-                                                       int* __restrict__ ghostCount, int* __restrict__ errorFlag)
+                                                       int* __restrict__ ghostCount, int* __restrict__ errorFlag, const ActiveItems items)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned char f = pflag[i];
-    if (!(f & 1)) {
-        if (f) pflag[i] = 0;   // last step's ghost expires
-        return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (items.lists.cells) {
+        // enumerate the owned particles through the owned-cell lists (ghost flags were expired by slab_expire_ghosts)
+        if ((long long)i >= (long long)items.lists.cellPrefix[types.n] * items.maxP) return;
+        int fl = 0;
+        i = active_item(items, types, i, fl);
+        if (i < 0 || fl != 1) return;
+    } else {
+        if (i >= n) return;
+        const unsigned char f = pflag[i];
+        if (!(f & 1)) {
+            if (f) pflag[i] = 0;   // last step's ghost expires
+            return;
+        }
     }
     int t;
     const int c = cell_of_particle(types, i, &t);
@@ -167,6 +175,16 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(TypesDev types, int n, S
         } else {
             atomicExch(errorFlag, 1);
         }
+    }
+}
+
+__global__ void __launch_bounds__(256) slab_expire_ghosts_kernel(const int* __restrict__ ghostList, const int* __restrict__ ghostCount,
+                                                               unsigned char* __restrict__ pflag)
+{
+    const int n = *ghostCount;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int pid = ghostList[k];
+        if (!(pflag[pid] & 1)) pflag[pid] = 0;
     }
 }
 
@@ -407,10 +425,17 @@ static void unpack_one(SlabState* s, const SlabCtx& ctx, char* raw, bool full)
 void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
 {
     cudaStream_t st = ctx.stream;
+    ActiveItems items{};
+    if (s->listsValid) {
+        items.lists = slab_lists(s, ctx.types); items.ghostList = s->ghostList; items.ghostCount = s->ghostCount; items.maxP = ctx.maxP;
+        BCS_LAUNCH("slab_expire_ghosts", st, slab_expire_ghosts_kernel<<<32, 256, 0, st>>>(s->ghostList, s->ghostCount, s->pflag));
+    }
     BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
+    const long long packItems = s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N;
     BCS_LAUNCH("slab_pack", st,
-               slab_pack_kernel<<<(ctx.N + 255) / 256, 256, 0, st>>>(ctx.types, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell, s->pflag,
-                                                                      s->moveTo, s->buf, s->ghostList, s->ghostCount, s->errorFlag));
+               slab_pack_kernel<<<(int)((packItems + 255) / 256), 256, 0, st>>>(ctx.types, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
+                                                                                 s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
+                                                                                 s->errorFlag, items));
     for (int d = 0; d < 2; ++d)
         if (s->vertCount[d])
             BCS_LAUNCH("slab_pack_vertices", st,
@@ -425,6 +450,7 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
             if (raw) unpack_one(s, ctx, raw, false);
     }
     slab_build_lists(s, ctx);
+    s->listsValid = true;
     BCS_CUDA(cudaGetLastError());
 }
 
@@ -450,6 +476,7 @@ OwnedLists slab_lists(const SlabState* s, const TypesDev& types)
 void slab_prime(SlabState* s, const SlabCtx& ctx)
 {
     cudaStream_t st = ctx.stream;
+    s->listsValid = false;
     BCS_LAUNCH("slab_init_ownership", st,
                slab_init_ownership_kernel<<<(ctx.B + 127) / 128, 128, 0, st>>>(ctx.types, ctx.B, s->dev, ctx.pos, s->ownedCell, s->pflag, s->moveTo));
     slab_end_of_step(s, ctx);   // nothing migrates (moveTo = -1): plain halo exchange (+ owned-cell lists)

@@ -33,6 +33,7 @@ struct SlabCtx {             // what the slab code needs from the simulation han
     int N, B, V, T;
     float4 *pos, *vel, *frc, *vpos, *vvel;
     SpringPlan plan;         // cells per CTA of the cell-group kernels
+    int maxP;                // largest particles-per-cell
     cudaStream_t stream;
 };
 
@@ -61,6 +62,7 @@ struct SlabState {
     int* vertList[2] = {nullptr, nullptr};
     int vertCount[2] = {0, 0};
     bool primed = false;
+    bool listsValid = false;   // owned-cell lists describe the current ownership
     std::vector<void*> owned;
 
     void exchange(cudaStream_t st);

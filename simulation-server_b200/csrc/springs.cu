@@ -60,7 +60,7 @@ __device__ __forceinline__ float3 spring_force(const PhysDev& ph, float3 pi, flo
     return s * f3(-n.x, -n.y, -n.z);
 }
 
-__global__ void __launch_bounds__(SPRING_THREADS, 6)
+__global__ void __launch_bounds__(SPRING_THREADS, 5)
 springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, const float4* __restrict__ pos,
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers,
                const int* __restrict__ adjJ, const float* __restrict__ adjL, const int* __restrict__ adjS,
@@ -116,6 +116,8 @@ springs_kernel(const TypesDev types, const SpringPlan plan, const PhysDev ph, co
         // (dP, dv and f_a - f_b all change sign exactly), so the directed evaluation of the reference does each
         // of these twice
         const int total = nCells * ty.nSpr;
+        // independent springs: unrolled so that their sqrt / reciprocal latencies overlap
+#pragma unroll 4
         for (int idx = tid; idx < total; idx += SPRING_THREADS) {
             const int cell = idx / ty.nSpr, k = idx - cell * ty.nSpr;
             const int ab = __ldg(sprAB + ty.sprStart + k);

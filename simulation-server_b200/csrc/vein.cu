@@ -41,18 +41,19 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
     float3 F = f3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < BCS_VEIN_MAX_NEIGHBORS; ++s) {
-        const int nb = __ldg(a.nbrIds + (size_t)s * a.V + id);
-        if (nb != -1) {
-            const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
-            const float3 q = xyz(a.vpos[nb]);
-            // one sqrt + one set of IEEE divisions: q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q)
-            const float3 d = p - q;
-            const float len = sqrtf(dot(d, d));
-            float3 n = d / len;
-            if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
-            const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
-            F = F + sf * f3(-n.x, -n.y, -n.z);
-        }
+        // branch-free so that the nine neighbour gathers are in flight together: an absent slot (-1) reads the
+        // vertex itself, whose zero separation normalises to the zero vector and contributes exactly +0
+        const int nbRaw = __ldg(a.nbrIds + (size_t)s * a.V + id);
+        const int nb = nbRaw < 0 ? id : nbRaw;
+        const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
+        const float3 q = xyz(a.vpos[nb]);
+        // one sqrt + one set of IEEE divisions: q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q)
+        const float3 d = p - q;
+        const float len = sqrtf(dot(d, d));
+        float3 n = d / len;
+        if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
+        const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
+        F = F + sf * f3(-n.x, -n.y, -n.z);
     }
     float4 f = a.vfrc[id];
     f.x += F.x; f.y += F.y; f.z += F.z;
