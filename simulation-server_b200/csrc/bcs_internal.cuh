@@ -130,10 +130,12 @@ struct OwnedLists {
 
 // slab mode: enumeration of this rank's ACTIVE particles (owned blood cells x particles, then the ghosts) so that the
 // per-particle kernels of the grid build and of the exchange touch N_local instead of N entries
-struct ActiveItems {
-    OwnedLists lists;          // lists.cells == null: not in slab mode (kernels index all particles)
+struct ActiveItems {           // small on purpose: passed by value to streaming kernels
+    const int* cells;          // null: not in slab mode (kernels index all particles)
+    const int* cellPrefix;     // [n_types + 1] exclusive prefix of the owned-cell counts
     const int* ghostList;
     const int* ghostCount;
+    const TypesDev* types;     // device copy of the type table
     int maxP;
 };
 

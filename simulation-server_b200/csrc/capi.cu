@@ -128,6 +128,7 @@ struct bcs_sim {
     CellSlab *cellSlab = nullptr, *groupSlab = nullptr;
     int* cullCount = nullptr;
     unsigned* doneBlocks = nullptr;
+    TypesDev* typesDev = nullptr;   // device copy of `types` for kernels that index it through a pointer
     int maxP = 1;
     bool exhaustiveVein = false;
     unsigned* vidx = nullptr;
@@ -223,10 +224,10 @@ GridBuildArgs particle_grid_args(bcs_sim* s)
     a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
     if (s->slab) {
         a.pflag = s->slab->pflag; a.nDev = s->slab->nActive; a.nDevOut = s->slab->nActive;
-        a.items.lists = slab_lists(s->slab, s->types); a.items.ghostList = s->slab->ghostList; a.items.ghostCount = s->slab->ghostCount;
-        a.items.maxP = s->maxP;
+        a.items.cells = s->slab->listCells; a.items.cellPrefix = s->slab->listCellPrefix;
+        a.items.ghostList = s->slab->ghostList; a.items.ghostCount = s->slab->ghostCount;
+        a.items.types = s->typesDev; a.items.maxP = s->maxP;
         a.itemCapacity = (long long)s->hs.B * s->maxP + s->hs.N;
-        a.types = s->types;
     }
     return a;
 }
@@ -342,6 +343,7 @@ SlabCtx slab_ctx(bcs_sim* s)
     c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel;
     c.plan = s->plan;
     c.maxP = s->maxP;
+    c.typesDev = s->typesDev;
     c.stream = s->stream;
     return c;
 }
@@ -479,6 +481,8 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->groupSlab = s->track(dev_alloc<CellSlab>((T + 7) / 8));
         s->cullCount = s->track(dev_alloc<int>(1));
         s->doneBlocks = s->track(dev_alloc<unsigned>(1));
+        s->typesDev = s->track(dev_alloc<TypesDev>(1));
+        BCS_CUDA(cudaMemcpy(s->typesDev, &s->types, sizeof(TypesDev), cudaMemcpyHostToDevice));
         for (const HostType& h : hs.types) s->maxP = std::max(s->maxP, h.P);
         s->vidx = s->track(dev_upload(hs.vidx));
         s->nbrIds = s->track(dev_upload(hs.nbrIds)); s->nbrLen = s->track(dev_upload(hs.nbrLen));

@@ -57,19 +57,22 @@ __device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsign
 __device__ __forceinline__ float u01(unsigned x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
 
 // item -> particle id (or -1 for padding / past the end); flag: 1 owned, 2 ghost
-__device__ __forceinline__ int active_item(const ActiveItems& A, const TypesDev& types, long long item, int& flag)
+__device__ __forceinline__ int active_item(const ActiveItems A, int item, int& flag)
 {
-    const long long ownedItems = (long long)A.lists.cellPrefix[types.n] * A.maxP;
+    const TypesDev* ty = A.types;
+    const int nTypes = ty->n;
+    const int ownedItems = A.cellPrefix[nTypes] * A.maxP;
     if (item < ownedItems) {
-        const int w = (int)(item / A.maxP), k = (int)(item % A.maxP);
+        const int w = item / A.maxP, k = item - w * A.maxP;
         int t = 0;
-        while (t + 1 < types.n && w >= A.lists.cellPrefix[t + 1]) ++t;
-        if (k >= types.t[t].P) return -1;
-        const int c = A.lists.cells[A.lists.typeFirst[t] + (w - A.lists.cellPrefix[t])];
+        while (t + 1 < nTypes && w >= A.cellPrefix[t + 1]) ++t;
+        const int P = ty->t[t].P;
+        if (k >= P) return -1;
+        const int c = A.cells[ty->t[t].cStart + (w - A.cellPrefix[t])];
         flag = 1;
-        return types.t[t].pStart + (c - types.t[t].cStart) * types.t[t].P + k;
+        return ty->t[t].pStart + (c - ty->t[t].cStart) * P + k;
     }
-    const long long gi = item - ownedItems;
+    const int gi = item - ownedItems;
     if (gi < *A.ghostCount) {
         flag = 2;
         return A.ghostList[gi];

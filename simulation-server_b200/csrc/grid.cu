@@ -548,11 +548,11 @@ __device__ __forceinline__ int block_sum(int v, int* warpSum)
 
 __global__ void __launch_bounds__(256) cs_mark_kernel(const float4* __restrict__ pos, const unsigned char* __restrict__ pflag, GridDev g,
                                                       int* __restrict__ keyOf, unsigned* __restrict__ cellMask, Counters* __restrict__ counters,
-                                                      const ActiveItems act, const TypesDev types)
+                                                      const ActiveItems act)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
-    if (act.lists.cells) {
-        i = active_item(act, types, i, f);
+    if (act.cells) {
+        i = active_item(act, i, f);
         if (i < 0) return;
     } else {
         if (i >= g.n) return;
@@ -666,13 +666,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* _
 __global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ keyOf,
                                                        const unsigned* __restrict__ cellMask, const int* __restrict__ cellRank,
                                                        unsigned* __restrict__ cellCount, int* __restrict__ rankOf, int* __restrict__ placeOf,
-                                                       int* __restrict__ nActive, const ActiveItems items, const TypesDev types)
+                                                       int* __restrict__ nActive, const ActiveItems items)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool act;
-    if (items.lists.cells) {
+    if (items.cells) {
         int f;
-        i = active_item(items, types, i, f);
+        i = active_item(items, i, f);
         act = i >= 0;
     } else {
         act = i < n && (pflag ? pflag[i] != 0 : true);
@@ -692,12 +692,11 @@ __global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __re
 
 __global__ void __launch_bounds__(256) cs_scatter_kernel(const unsigned char* __restrict__ pflag, int n, const int* __restrict__ rankOf,
                                                          const int* __restrict__ placeOf, const int* __restrict__ occStart,
-                                                         int* __restrict__ tmpIds, int* __restrict__ tmpRank, const ActiveItems items,
-                                                         const TypesDev types)
+                                                         int* __restrict__ tmpIds, int* __restrict__ tmpRank, const ActiveItems items)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
-    if (items.lists.cells) {
-        i = active_item(items, types, i, f);
+    if (items.cells) {
+        i = active_item(items, i, f);
         if (i < 0) return;
     } else {
         if (i >= n) return;
@@ -868,24 +867,24 @@ static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
     const int n = g.n, blocks = (n + 255) / 256;
     // slab mode enumerates owned cells x maxP (padding included) + ghosts: launched for that capacity, CTAs past the
     // device-side item count leave at once
-    const int itemBlocks = a.items.lists.cells ? (int)(((long long)a.itemCapacity + 255) / 256) : blocks;
+    const int itemBlocks = a.items.cells ? (int)(((long long)a.itemCapacity + 255) / 256) : blocks;
     SortScratch* sc = a.scratch;
     BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
     BCS_CUDA(cudaMemsetAsync(sc->cellCount, 0, ((size_t)n + 1) * sizeof(unsigned), st));
     if (a.nDevOut) BCS_CUDA(cudaMemsetAsync(a.nDevOut, 0, sizeof(int), st));
-    BCS_LAUNCH("cell_keys", st, cs_mark_kernel<<<itemBlocks, 256, 0, st>>>(a.objPos, a.pflag, g, sc->keyOf, a.cellMask, a.counters, a.items, a.types));
+    BCS_LAUNCH("cell_keys", st, cs_mark_kernel<<<itemBlocks, 256, 0, st>>>(a.objPos, a.pflag, g, sc->keyOf, a.cellMask, a.counters, a.items));
     const int maskTiles = (a.maskWords + SCAN_TILE - 1) / SCAN_TILE;
     BCS_LAUNCH("cell_rank_totals", st, cs_tile_totals_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals));
     BCS_LAUNCH("cell_rank_scan", st,
                cs_scan_kernel<0><<<maskTiles, SCAN_THREADS, 0, st>>>(a.cellMask, a.maskWords, nullptr, sc->scanTotals, a.cellRank, a.numOcc, 0, nullptr));
     BCS_LAUNCH("cell_count", st,
                cs_count_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->keyOf, a.cellMask, a.cellRank, sc->cellCount, sc->rankOf, sc->placeOf, a.nDevOut,
-                                                       a.items, a.types));
+                                                       a.items));
     const int cntTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     BCS_LAUNCH("cell_start_totals", st, cs_tile_totals_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals));
     BCS_LAUNCH("cell_start_scan", st,
                cs_scan_kernel<1><<<cntTiles, SCAN_THREADS, 0, st>>>(sc->cellCount, n, a.numOcc, sc->scanTotals, a.occStart, nullptr, n, a.nDev));
-    BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank, a.items, a.types));
+    BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank, a.items));
     if (a.reorder)
         BCS_LAUNCH("finalize_grid", st,
                    cs_order_kernel<true><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,

@@ -42,7 +42,6 @@ struct GridBuildArgs {
     const unsigned char* pflag;  // slab mode: per-particle flags (bit 0 owned, bit 1 ghost); null otherwise
     ActiveItems items;        // slab mode: enumeration of the active particles (items.lists.cells == null otherwise)
     long long itemCapacity;   //            upper bound of the item count (launch size)
-    TypesDev types;
     const int* nDev;          // slab mode: number of active particles (device scalar read by the sort / finalize kernels)
     int* nDevOut;             //            ... written by the key kernel
     bool reorder;             // also write sorted-order copies of pos/vel

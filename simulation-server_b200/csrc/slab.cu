@@ -39,24 +39,25 @@ namespace bcs {
                                                  std::to_string(__LINE__) + ")"};                                   \
     } while (0)
 
-__device__ __forceinline__ int cell_of_particle(const TypesDev& types, int i, int* typeOut = nullptr)
+__device__ __forceinline__ int cell_of_particle(const TypesDev* __restrict__ types, int i, int* typeOut = nullptr)
 {
     int t = 0;
-    while (t + 1 < types.n && i >= types.t[t + 1].pStart) ++t;
+    const int n = types->n;
+    while (t + 1 < n && i >= types->t[t + 1].pStart) ++t;
     if (typeOut) *typeOut = t;
-    return types.t[t].cStart + (i - types.t[t].pStart) / types.t[t].P;
+    return types->t[t].cStart + (i - types->t[t].pStart) / types->t[t].P;
 }
 
 // ownership from the current positions (after the initial upload): a blood cell belongs to the slab its centre is in
-__global__ void __launch_bounds__(128) slab_init_ownership_kernel(TypesDev types, int nCells, SlabDev slab, const float4* __restrict__ pos,
+__global__ void __launch_bounds__(128) slab_init_ownership_kernel(const TypesDev* __restrict__ types, int nCells, SlabDev slab, const float4* __restrict__ pos,
                                                                  unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                                  signed char* __restrict__ moveTo)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     int t = 0;
-    while (t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
-    const TypeDev ty = types.t[t];
+    while (t + 1 < types->n && c >= types->t[t + 1].cStart) ++t;
+    const TypeDev ty = types->t[t];
     const int first = ty.pStart + (c - ty.cStart) * ty.P;
     float cy = 0.f;
     for (int k = 0; k < ty.P; ++k) cy += pos[first + k].y;
@@ -77,13 +78,13 @@ __global__ void __launch_bounds__(256) slab_init_vertices_kernel(int V, SlabDev 
 }
 
 // ---- owned-cell lists (rebuilt every step after the exchange) ---------------------------------------------------
-__global__ void __launch_bounds__(256) slab_list_cells_kernel(TypesDev types, int nCells, const unsigned char* __restrict__ ownedCell,
+__global__ void __launch_bounds__(256) slab_list_cells_kernel(const TypesDev* __restrict__ types, int nCells, const unsigned char* __restrict__ ownedCell,
                                                              int* __restrict__ cells, int* __restrict__ count)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool own = c < nCells && ownedCell[c];
     int t = 0;
-    while (own && t + 1 < types.n && c >= types.t[t + 1].cStart) ++t;
+    while (own && t + 1 < types->n && c >= types->t[t + 1].cStart) ++t;
     // warp-aggregated append: one atomic per (warp, type) instead of one per blood cell
     const unsigned active = __ballot_sync(0xffffffffu, own);
     if (own) {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) slab_list_cells_kernel(TypesDev types, in
         int base = 0;
         if (lane == leader) base = atomicAdd(&count[t], __popc(peers));
         base = __shfl_sync(peers, base, leader);
-        cells[types.t[t].cStart + base + __popc(peers & ((1u << lane) - 1u))] = c;   // type t's segment starts at cStart_t
+        cells[types->t[t].cStart + base + __popc(peers & ((1u << lane) - 1u))] = c;   // type t's segment starts at cStart_t
     }
 }
 
@@ -117,18 +118,18 @@ __device__ __forceinline__ int dest_of(const SlabDev& s, int target)
     return 2;
 }
 
-__global__ void __launch_bounds__(256) slab_pack_kernel(TypesDev types, int n, SlabDev slab, const float4* __restrict__ pos,
+__global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restrict__ types, int n, SlabDev slab, const float4* __restrict__ pos,
                                                        const float4* __restrict__ vel, const float4* __restrict__ frc,
                                                        unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                        const signed char* __restrict__ moveTo, SlabBuffers buf, int* __restrict__ ghostList,
                                                        int* __restrict__ ghostCount, int* __restrict__ errorFlag, const ActiveItems items)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (items.lists.cells) {
+    if (items.cells) {
         // enumerate the owned particles through the owned-cell lists (ghost flags were expired by slab_expire_ghosts)
-        if ((long long)i >= (long long)items.lists.cellPrefix[types.n] * items.maxP) return;
+        if (i >= items.cellPrefix[types->n] * items.maxP) return;
         int fl = 0;
-        i = active_item(items, types, i, fl);
+        i = active_item(items, i, fl);
         if (i < 0 || fl != 1) return;
     } else {
         if (i >= n) return;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(TypesDev types, int n, S
         const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth) || (d == 1 && p.y < slab.yLo + slab.haloWidth);
         pflag[i] = keep ? 2 : 0;
         if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
-        if (i == types.t[t].pStart + (c - types.t[t].cStart) * types.t[t].P) ownedCell[c] = 0;
+        if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
         return;
     }
     // stays: mirror it on the neighbours whose slab it is close to
@@ -208,7 +209,7 @@ __global__ void slab_reset_headers_kernel(SlabBuffers buf, int* ghostCount, int 
 }
 
 // ---- unpack -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) slab_unpack_kernel(TypesDev types, const SlabHeader* __restrict__ hdr, const MigRecord* __restrict__ mig,
+__global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __restrict__ types, const SlabHeader* __restrict__ hdr, const MigRecord* __restrict__ mig,
                                                          const HaloRecord* __restrict__ halo, const VertexRecord* __restrict__ verts, int nVerts,
                                                          int capMig, int capHalo, float4* __restrict__ pos, float4* __restrict__ vel,
                                                          float4* __restrict__ frc, float4* __restrict__ vpos, float4* __restrict__ vvel,
@@ -417,7 +418,7 @@ static void unpack_one(SlabState* s, const SlabCtx& ctx, char* raw, bool full)
     const MigRecord* mig = (const MigRecord*)(raw + sizeof(SlabHeader));
     const HaloRecord* halo = (const HaloRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord));
     BCS_LAUNCH("slab_unpack", ctx.stream,
-               slab_unpack_kernel<<<64, 256, 0, ctx.stream>>>(ctx.types, hdr, mig, halo, full ? vertex_region(s, raw) : nullptr,
+               slab_unpack_kernel<<<64, 256, 0, ctx.stream>>>(ctx.typesDev, hdr, mig, halo, full ? vertex_region(s, raw) : nullptr,
                                                               full ? s->capVert : 0, s->capMig, full ? s->capHalo : 0, ctx.pos, ctx.vel,
                                                               ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount));
 }
@@ -427,13 +428,14 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
     cudaStream_t st = ctx.stream;
     ActiveItems items{};
     if (s->listsValid) {
-        items.lists = slab_lists(s, ctx.types); items.ghostList = s->ghostList; items.ghostCount = s->ghostCount; items.maxP = ctx.maxP;
+        items.cells = s->listCells; items.cellPrefix = s->listCellPrefix; items.ghostList = s->ghostList; items.ghostCount = s->ghostCount;
+        items.types = ctx.typesDev; items.maxP = ctx.maxP;
         BCS_LAUNCH("slab_expire_ghosts", st, slab_expire_ghosts_kernel<<<32, 256, 0, st>>>(s->ghostList, s->ghostCount, s->pflag));
     }
     BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
     const long long packItems = s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N;
     BCS_LAUNCH("slab_pack", st,
-               slab_pack_kernel<<<(int)((packItems + 255) / 256), 256, 0, st>>>(ctx.types, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
+               slab_pack_kernel<<<(int)((packItems + 255) / 256), 256, 0, st>>>(ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
                                                                                  s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
                                                                                  s->errorFlag, items));
     for (int d = 0; d < 2; ++d)
@@ -459,7 +461,7 @@ void slab_build_lists(SlabState* s, const SlabCtx& ctx)
     cudaStream_t st = ctx.stream;
     BCS_CUDA(cudaMemsetAsync(s->listCount, 0, BCS_MAX_TYPES * sizeof(int), st));
     BCS_LAUNCH("slab_list_cells", st,
-               slab_list_cells_kernel<<<(ctx.B + 255) / 256, 256, 0, st>>>(ctx.types, ctx.B, s->ownedCell, s->listCells, s->listCount));
+               slab_list_cells_kernel<<<(ctx.B + 255) / 256, 256, 0, st>>>(ctx.typesDev, ctx.B, s->ownedCell, s->listCells, s->listCount));
     BCS_LAUNCH("slab_list_prefix", st,
                slab_list_prefix_kernel<<<1, 1, 0, st>>>(ctx.types.n, ctx.plan, s->listCount, s->listBlockStart, s->listCellPrefix));
     BCS_CUDA(cudaGetLastError());
@@ -478,7 +480,7 @@ void slab_prime(SlabState* s, const SlabCtx& ctx)
     cudaStream_t st = ctx.stream;
     s->listsValid = false;
     BCS_LAUNCH("slab_init_ownership", st,
-               slab_init_ownership_kernel<<<(ctx.B + 127) / 128, 128, 0, st>>>(ctx.types, ctx.B, s->dev, ctx.pos, s->ownedCell, s->pflag, s->moveTo));
+               slab_init_ownership_kernel<<<(ctx.B + 127) / 128, 128, 0, st>>>(ctx.typesDev, ctx.B, s->dev, ctx.pos, s->ownedCell, s->pflag, s->moveTo));
     slab_end_of_step(s, ctx);   // nothing migrates (moveTo = -1): plain halo exchange (+ owned-cell lists)
     s->primed = true;
 }

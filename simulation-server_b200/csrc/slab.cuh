@@ -34,6 +34,7 @@ struct SlabCtx {             // what the slab code needs from the simulation han
     float4 *pos, *vel, *frc, *vpos, *vvel;
     SpringPlan plan;         // cells per CTA of the cell-group kernels
     int maxP;                // largest particles-per-cell
+    const TypesDev* typesDev;   // device copy of the type table
     cudaStream_t stream;
 };
 
