@@ -10,7 +10,7 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench"; timeout 900 python bench.py --steps ${STEPS:-100} --warmup 10 2>&1 | tail -2 | tee $O/bench.json
 if [ "${NCU:-1}" = 1 ]; then
   echo "== ncu launch list"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 120 --csv --log-file $O/launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 300 --csv --log-file $O/launches.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1
   tail -2 $O/ncu_bench.log | cut -c1-300
   python - <<PY
