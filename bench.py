@@ -108,6 +108,8 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "vein_cull_cells": 12 * N,                 # R positions
         "vein_collisions": 24 * N + 120 * hits,
         "vein_ghost_splat": 0,
+        "vein_masking": 0,                         # phase B of the wall-grid path: a few thousand particles
+        "wall_rebuild": 0,                         # returns at once unless a vertex left its margin
         "finish_step": 72 * N,                     # integrate (R 36N, W 24N) + vein-end test (12N)
         "integrate_particles": 60 * N,
         "vein_integrate": 72 * V,

@@ -297,6 +297,7 @@ typedef struct bcs_stats {
     uint64_t vein_hits;
     uint64_t teleported_cells;
     uint64_t out_of_bounds;   /* positions outside the grid bounds seen by the cell-id stage */
+    uint64_t wall_rebuilds;   /* rebuilds of the lazily maintained wall grid (vein-collision culling structure) */
 } bcs_stats;
 /* Totals since creation (pair/triangle counters only advance when bcs_opts.collect_stats = 1). */
 int bcs_get_stats(bcs_sim* sim, bcs_stats* out);

@@ -95,7 +95,8 @@ class DeviceView(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("pair_tests", C.c_uint64), ("pair_hits", C.c_uint64), ("triangle_tests", C.c_uint64),
-                ("vein_hits", C.c_uint64), ("teleported_cells", C.c_uint64), ("out_of_bounds", C.c_uint64)]
+                ("vein_hits", C.c_uint64), ("teleported_cells", C.c_uint64), ("out_of_bounds", C.c_uint64),
+                ("wall_rebuilds", C.c_uint64)]
 
 
 class BcsError(RuntimeError):

@@ -131,6 +131,8 @@ struct bcs_sim {
     TypesDev* typesDev = nullptr;   // device copy of `types` for kernels that index it through a pointer
     int maxP = 1;
     bool exhaustiveVein = false;
+    WallGridDev wall{};             // lazily rebuilt wall grid (clean semantics; wall.enabled = 0 otherwise)
+    int numSMs = 148;
     unsigned* vidx = nullptr;
     int* nbrIds = nullptr;
     float* nbrLen = nullptr;
@@ -246,6 +248,100 @@ void build_triangle_grid(bcs_sim* s)
     launch_grid_build(a, s->stream);
 }
 
+// Lazily rebuilt wall grid (wall.cu): geometry from the rest positions of the vein, list capacity from a host-side
+// count of the (triangle, cell) overlaps with the same padding the device uses.
+void setup_wall(bcs_sim* s)
+{
+    const HostScene& hs = s->hs;
+    const int V = hs.V, T = hs.T;
+    WallGridDev& w = s->wall;
+    const char* em = getenv("BCS_WALL_MARGIN");
+    const char* eh = getenv("BCS_WALL_CELL");
+    w.margin = em ? (float)atof(em) : 0.25f;
+    w.h = eh ? (float)atof(eh) : 4.0f;
+    BCS_REQUIRE(w.margin > 0.f && w.h >= 1.f, BCS_ERR_INVALID, "bad BCS_WALL_MARGIN / BCS_WALL_CELL");
+    w.h = std::max(w.h, 0.51f * s->phys.impactNear + 0.01f);   // phase A relies on reach <= 2 cells
+    w.invh = 1.0f / w.h;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int v = 0; v < V; ++v) {
+        const float p[3] = {hs.vx[v], hs.vy[v], hs.vz[v]};
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
+    }
+    const float slack = 2.0f + w.margin;   // beyond it cells are clamped (still conservative, only slower)
+    int dims[3];
+    for (int k = 0; k < 3; ++k) {
+        lo[k] -= slack; hi[k] += slack;
+        dims[k] = std::max(1, (int)std::ceil((hi[k] - lo[k]) * w.invh));
+    }
+    w.ox = lo[0]; w.oy = lo[1]; w.oz = lo[2];
+    w.nx = dims[0]; w.ny = dims[1]; w.nz = dims[2];
+    const long long cells = (long long)dims[0] * dims[1] * dims[2];
+    BCS_REQUIRE(cells < (1ll << 30), BCS_ERR_UNSUPPORTED, "wall grid too large (raise BCS_WALL_CELL)");
+    w.cells = (int)cells;
+    // capacity: exact overlap count at rest x 1.5 (+ header words)
+    const float pad = 0.05f + w.margin;
+    auto axis = [&](float p, int k) { float q = std::floor((p - lo[k]) * w.invh); return (int)std::min(std::max(q, 0.f), (float)(dims[k] - 1)); };
+    long long entries = 0;
+    std::vector<unsigned char> seen((size_t)cells, 0);
+    long long nonEmpty = 0;
+    for (int t = 0; t < T; ++t) {
+        int c0[3], c1[3];
+        for (int k = 0; k < 3; ++k) {
+            const std::vector<float>& a = k == 0 ? hs.vx : k == 1 ? hs.vy : hs.vz;
+            const float p0 = a[hs.vidx[3 * t]], p1 = a[hs.vidx[3 * t + 1]], p2 = a[hs.vidx[3 * t + 2]];
+            c0[k] = axis(std::min(p0, std::min(p1, p2)) - pad, k);
+            c1[k] = axis(std::max(p0, std::max(p1, p2)) + pad, k);
+        }
+        for (int z = c0[2]; z <= c1[2]; ++z)
+            for (int y = c0[1]; y <= c1[1]; ++y)
+                for (int x = c0[0]; x <= c1[0]; ++x) {
+                    ++entries;
+                    unsigned char& f = seen[((size_t)z * dims[1] + y) * dims[0] + x];
+                    if (!f) { f = 1; ++nonEmpty; }
+                }
+    }
+    const long long cap = entries * 3 / 2 + 4096;
+    (void)nonEmpty;
+    BCS_REQUIRE(cap < (1ll << 31), BCS_ERR_UNSUPPORTED, "wall grid lists too large (raise BCS_WALL_CELL)");
+    w.cap = (int)cap;
+    w.start = s->track(dev_alloc<int>((size_t)w.cells + 1));
+    w.cursor = s->track(dev_alloc<int>((size_t)w.cells));
+    w.rec = s->track(dev_alloc<int4>(2 * (size_t)w.cells));
+    w.near = s->track(dev_alloc<unsigned char>((size_t)w.cells));
+    w.nearTmp = s->track(dev_alloc<unsigned char>(2 * (size_t)w.cells));
+    BCS_CUDA(cudaMemset(w.near, 0, (size_t)w.cells));
+    w.list = s->track(dev_alloc<int>((size_t)w.cap));
+    w.vposBuilt = s->track(dev_alloc<float4>(V));
+    int4* info = s->track(dev_alloc<int4>(T));
+    int4* verts = s->track(dev_alloc<int4>(T));
+    w.slotInfo = info;
+    w.slotVerts = verts;
+    std::vector<Aabb> inv((size_t)std::max((T + 7) / 8, s->tg.cells), Aabb{3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f});
+    w.groupBox = s->track(dev_alloc<Aabb>((T + 7) / 8));
+    w.cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
+    BCS_CUDA(cudaMemcpy(w.groupBox, inv.data(), (size_t)((T + 7) / 8) * sizeof(Aabb), cudaMemcpyHostToDevice));
+    BCS_CUDA(cudaMemcpy(w.cellBox, inv.data(), (size_t)s->tg.cells * sizeof(Aabb), cudaMemcpyHostToDevice));
+    w.dirty = s->track(dev_alloc<int>(1));
+    w.overflow = s->track(dev_alloc<int>(1));
+    w.barrier = s->track(dev_alloc<unsigned>(2));
+    w.builds = s->track(dev_alloc<unsigned long long>(1));
+    w.queueCount = s->track(dev_alloc<int>(1));
+    cudaDeviceProp prop{};
+    BCS_CUDA(cudaGetDeviceProperties(&prop, s->device));
+    s->numSMs = prop.multiProcessorCount;
+    w.blockSums = s->track(dev_alloc<int>(s->numSMs));
+    w.queue = s->track(dev_alloc<int>(hs.N));
+    w.queueBest = s->track(dev_alloc<unsigned long long>(hs.N));
+    BCS_CUDA(cudaMemset(w.start, 0, ((size_t)w.cells + 1) * sizeof(int)));
+    BCS_CUDA(cudaMemset(w.overflow, 0, sizeof(int)));
+    BCS_CUDA(cudaMemset(w.barrier, 0, 2 * sizeof(unsigned)));
+    BCS_CUDA(cudaMemset(w.builds, 0, sizeof(unsigned long long)));
+    BCS_CUDA(cudaMemset(w.dirty, 1, sizeof(int)));
+    launch_wall_slot_info(s->tkeys[1], s->tids[1], s->vidx, T, s->tg, info, verts, s->stream);
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    w.enabled = 1;
+}
+
 VeinArgs vein_args(bcs_sim* s)
 {
     VeinArgs a{};
@@ -253,6 +349,7 @@ VeinArgs vein_args(bcs_sim* s)
     a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc;
     a.nbrIds = s->nbrIds; a.nbrLen = s->nbrLen; a.vidx = s->vidx;
     a.vOwned = s->slab ? s->slab->vOwned : nullptr;
+    if (s->wall.enabled) { a.vposBuilt = s->wall.vposBuilt; a.wallMargin = s->wall.margin; a.wallDirty = s->wall.dirty; }
     return a;
 }
 
@@ -268,7 +365,10 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.nCells = s->hs.B; a.maxP = s->maxP; a.cullList = s->cullList; a.cullCount = s->cullCount;
     a.collR = s->collR; a.counters = s->counters;
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
+    a.wall = s->wall;
+    if (s->exhaustiveVein) a.wall.enabled = 0;
     if (s->slab) {
+        a.pflag = s->slab->pflag;
         a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.lists = slab_lists(s->slab, s->types);
         a.ghostList = s->slab->ghostList; a.ghostCount = s->slab->ghostCount;
     }
@@ -325,8 +425,13 @@ void stage(bcs_sim* s, int st)
         break;
     case BCS_STAGE_VEIN_COLLISIONS: {
         VeinCollideArgs a = vein_collide_args(s);
-        launch_tri_refit(a, s->stream);
-        launch_vein_collisions(a, s->stream);
+        if (a.wall.enabled) {
+            launch_wall_rebuild(a, s->hs.V, s->numSMs, s->stream);
+            launch_wall_collisions(a, s->stream);
+        } else {
+            launch_tri_refit(a, s->stream);
+            launch_vein_collisions(a, s->stream);
+        }
         break;
     }
     case BCS_STAGE_INTEGRATE_PARTICLES: launch_integrate_particles(integrate_args(s), s->stream); break;
@@ -344,6 +449,7 @@ SlabCtx slab_ctx(bcs_sim* s)
     c.plan = s->plan;
     c.maxP = s->maxP;
     c.typesDev = s->typesDev;
+    if (s->wall.enabled) { c.wallBuilt = s->wall.vposBuilt; c.wallMargin = s->wall.margin; c.wallDirty = s->wall.dirty; }
     c.stream = s->stream;
     return c;
 }
@@ -508,6 +614,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             build_triangle_grid(s);
             BCS_CUDA(cudaStreamSynchronize(s->stream));
         }
+        if (s->semantics == BCS_SEM_CLEAN && !getenv("BCS_NO_WALL_GRID")) setup_wall(s);
         if (slabOpts) {
             BCS_REQUIRE(slabOpts->struct_size == sizeof(bcs_slab_opts), BCS_ERR_INVALID, "bcs_slab_opts.struct_size mismatch");
             BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN, BCS_ERR_UNSUPPORTED, "slab decomposition needs clean semantics");
@@ -665,6 +772,7 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, a.ptr, n, s->types, s->collR, a.isParticlePos ? 1 : 0);
     BCS_CUDA(cudaGetLastError());
     if (s->slab && which == BCS_PARTICLE_POS) s->slab->primed = false;   // ownership is re-derived from the new positions
+    if (s->wall.enabled && which == BCS_VEIN_POS) BCS_CUDA(cudaMemsetAsync(s->wall.dirty, 1, sizeof(int), s->stream));   // wall grid: rebuild
     BCS_API_END
 }
 
@@ -869,6 +977,15 @@ int bcs_get_stats(bcs_sim* s, bcs_stats* o)
     BCS_CUDA(cudaStreamSynchronize(s->stream));
     o->pair_tests = c.pairTests; o->pair_hits = c.pairHits; o->triangle_tests = c.triTests;
     o->vein_hits = c.veinHits; o->teleported_cells = c.teleported; o->out_of_bounds = c.oob;
+    o->wall_rebuilds = 0;
+    if (s->wall.enabled) {
+        unsigned long long builds = 0;
+        int overflow = 0;
+        BCS_CUDA(cudaMemcpy(&builds, s->wall.builds, sizeof builds, cudaMemcpyDeviceToHost));
+        BCS_CUDA(cudaMemcpy(&overflow, s->wall.overflow, sizeof overflow, cudaMemcpyDeviceToHost));
+        o->wall_rebuilds = builds;
+        BCS_REQUIRE(!overflow, BCS_ERR_STATE, "the wall grid outgrew its list capacity (vein deformed far beyond its rest shape)");
+    }
     BCS_API_END
 }
 

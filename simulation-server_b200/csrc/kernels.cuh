@@ -106,6 +106,39 @@ struct CollideArgs {
 };
 void launch_particle_collisions(const CollideArgs& a, cudaStream_t st);
 
+// ---- wall.cu: lazily rebuilt wall grid (production path of the vein-collision stage, clean semantics) ----
+// A uniform grid of `h`-unit cells over the vein's bounding box.  Every cell lists the sorted triangle slots whose
+// AABB (padded by BOX_PAD + margin) overlaps it, preceded by a 5-word header: the slab {n, dmin, dmax} along the
+// mean normal of those triangles (padded likewise).  The structure stays valid while no vertex has moved more than
+// `margin` from its position at build time (vein_integrate / the vertex-halo unpack raise `dirty` otherwise), so a
+// step normally rebuilds nothing: the rebuild kernel returns at once.
+struct WallGridDev {
+    int enabled;
+    float ox, oy, oz, h, invh;
+    int nx, ny, nz, cells;
+    int* start;               // [cells + 1] offsets into list
+    int4* rec;                // [2 * cells] 32-byte record per cell: {list start, entries, n.x, n.y | n.z, dmin, dmax, -}
+    unsigned char* near;      // [cells] 1 = a non-empty cell lies within +-2 cells (a particle here can reach the wall)
+    unsigned char* nearTmp;   // [2 * cells] scratch of the separable dilation
+    int* cursor;              // [cells]     counts during a rebuild, then fill cursors
+    int* list;                // [cap]
+    int cap;
+    float4* vposBuilt;        // [V] vertex positions the structure was built from
+    const int4* slotInfo;     // [T] static: triangle id and triangle-grid cell (x,y,z) of every sorted slot
+    const int4* slotVerts;    // [T] static: the three vertex ids (and the triangle id) of every sorted slot
+    Aabb* groupBox;           // [(T+7)/8] AABB of 8 consecutive sorted slots, padded by BOX_PAD + margin
+    Aabb* cellBox;            // [triangle-grid cells] union of the group boxes a cell's slot range touches
+    int* dirty;               // device flag: a vertex left its margin -> rebuild at the start of the next step
+    int* overflow;            // sticky: list capacity exceeded
+    unsigned* barrier;        // [2] grid barrier of the rebuild kernel
+    int* blockSums;           // [rebuild grid]
+    unsigned long long* builds;   // number of rebuilds so far
+    float margin;
+    int* queue;               // [N] particles with a near hit (phase B work list) ...
+    unsigned long long* queueBest;   // ... and their (traversal key << 32 | slot)
+    int* queueCount;
+};
+
 // ---- vein.cu -------------------------------------------------------------------------------------------
 struct VeinArgs {
     int V, T;
@@ -117,6 +150,9 @@ struct VeinArgs {
     const float* nbrLen;
     const unsigned* vidx;       // [3T]
     const unsigned char* vOwned;   // slab mode: [V] 1 = vertex integrated by this rank; null = all
+    const float4* vposBuilt;       // wall grid: positions at build time, margin and the flag to raise (null: no tracking)
+    float wallMargin;
+    int* wallDirty;
 };
 void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st);
 void launch_vein_gather(const VeinArgs& a, cudaStream_t st);
@@ -148,6 +184,9 @@ struct VeinCollideArgs {
     const int* ghostList;               // slab mode: ghost particle ids (splat-only pass) and their count
     const int* ghostCount;
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
+    int liveTris;               // 1: triangles are gathered from the live vertices (tris is not refreshed per step)
+    WallGridDev wall;           // wall.enabled: production path (clean semantics)
+    const unsigned char* pflag; // slab mode: per-particle flags (bit 0 owned, bit 1 ghost); null otherwise
     int nCells;                 // blood cells
     int maxP;                   // largest particles-per-cell over the types
     CullEntry* cullList;        // [nCells] blood cells that may touch the wall this step
@@ -161,6 +200,11 @@ struct VeinCollideArgs {
 };
 void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st);
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st);
+// wall.cu
+void launch_wall_rebuild(const VeinCollideArgs& a, int V, int numSMs, cudaStream_t st);   // returns at once unless wall.dirty
+void launch_wall_collisions(const VeinCollideArgs& a, cudaStream_t st);
+void launch_wall_slot_info(const int* sortedTriKeys, const int* triIds, const unsigned* vidx, int T, GridDev tgrid, int4* slotInfo, int4* slotVerts,
+                           cudaStream_t st);
 
 // ---- integrate.cu --------------------------------------------------------------------------------------
 struct IntegrateArgs {

@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __rest
                                                          int capMig, int capHalo, float4* __restrict__ pos, float4* __restrict__ vel,
                                                          float4* __restrict__ frc, float4* __restrict__ vpos, float4* __restrict__ vvel,
                                                          unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
-                                                         int* __restrict__ ghostList, int* __restrict__ ghostCount)
+                                                         int* __restrict__ ghostList, int* __restrict__ ghostCount,
+                                                         const float4* __restrict__ wallBuilt, float wallMargin, int* __restrict__ wallDirty)
 {
     const int nMig = min(hdr->nMig, capMig), nHalo = min(hdr->nHalo, capHalo);
     nVerts = min(nVerts, hdr->nVerts);
@@ -237,6 +238,12 @@ __global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __rest
             const VertexRecord r = verts[k - nMig - nHalo];
             vpos[r.id] = make_float4(r.px, r.py, r.pz, 0.f);
             vvel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
+            if (wallBuilt) {
+                // wall grid (wall.cu): a halo vertex that left its margin invalidates the padded structure
+                const float4 b = wallBuilt[r.id];
+                const float dx = r.px - b.x, dy = r.py - b.y, dz = r.pz - b.z;
+                if (dx * dx + dy * dy + dz * dz > wallMargin * wallMargin) *wallDirty = 1;
+            }
         }
     }
 }
@@ -420,7 +427,8 @@ static void unpack_one(SlabState* s, const SlabCtx& ctx, char* raw, bool full)
     BCS_LAUNCH("slab_unpack", ctx.stream,
                slab_unpack_kernel<<<64, 256, 0, ctx.stream>>>(ctx.typesDev, hdr, mig, halo, full ? vertex_region(s, raw) : nullptr,
                                                               full ? s->capVert : 0, s->capMig, full ? s->capHalo : 0, ctx.pos, ctx.vel,
-                                                              ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount));
+                                                              ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount,
+                                                              ctx.wallBuilt, ctx.wallMargin, ctx.wallDirty));
 }
 
 void slab_end_of_step(SlabState* s, const SlabCtx& ctx)

@@ -35,6 +35,9 @@ struct SlabCtx {             // what the slab code needs from the simulation han
     SpringPlan plan;         // cells per CTA of the cell-group kernels
     int maxP;                // largest particles-per-cell
     const TypesDev* typesDev;   // device copy of the type table
+    const float4* wallBuilt;    // wall grid (wall.cu): vertex positions at build time, margin, flag to raise; null = none
+    float wallMargin;
+    int* wallDirty;
     cudaStream_t stream;
 };
 

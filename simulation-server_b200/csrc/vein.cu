@@ -10,6 +10,7 @@
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include "vein_device.cuh"
 
 #include <cstdlib>
 
@@ -84,6 +85,12 @@ __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
     a.vvel[id] = v;
     a.vpos[id] = x;
     a.vfrc[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.vposBuilt) {
+        // wall grid (wall.cu): a vertex that left its margin invalidates the padded structure
+        const float4 b = a.vposBuilt[id];
+        const float dx = x.x - b.x, dy = x.y - b.y, dz = x.z - b.z;
+        if (dx * dx + dy * dy + dz * dz > a.wallMargin * a.wallMargin) *a.wallDirty = 1;
+    }
 }
 
 void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)
@@ -97,7 +104,6 @@ void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)
 // The Moeller-Trumbore test only ever uses these three vectors, so the per-test gathers of the reference
 // (3 index loads + 9 coordinate loads through two indirections) become three aligned float4 loads.
 // The same pass refits the culling hierarchy: one AABB per group of 8 consecutive sorted slots.
-constexpr float BOX_PAD = 0.05f;   // covers float error of a Moeller-Trumbore "hit" that lies marginally outside its triangle
 
 __global__ void __launch_bounds__(256) tri_refit_kernel(const float4* __restrict__ vpos, const unsigned* __restrict__ vidx,
                                                         const int* __restrict__ triIds, int T, TriPacked* __restrict__ out,
@@ -222,258 +228,6 @@ void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st)
     BCS_CUDA(cudaGetLastError());
 }
 
-struct RayHit {
-    float t;
-    float3 normal;
-    float3 refl;
-    int tri;
-};
-
-// realCollisionDetection (vein_collisions.cu:11-45) on a packed triangle
-__device__ __forceinline__ bool ray_triangle(const float3 origin, const float3 dir, const TriPacked& tp, RayHit& h)
-{
-    constexpr float EPS = 0.000001f;
-    const float3 v0 = f3(tp.a.x, tp.a.y, tp.a.z);
-    const float3 edge1 = f3(tp.a.w, tp.b.x, tp.b.y);
-    const float3 edge2 = f3(tp.b.z, tp.b.w, tp.c.x);
-    const float3 hh = cross(dir, edge2);
-    const float a = dot(edge1, hh);
-    if (a > -EPS && a < EPS) return false;
-    const float f = 1 / a;
-    const float3 s = origin - v0;
-    const float u = f * dot(s, hh);
-    if (u < 0 || u > 1) return false;
-    const float3 q = cross(s, edge1);
-    const float v = f * dot(dir, q);
-    if (v < 0 || u + v > 1) return false;
-    const float t = f * dot(edge2, q);
-    if (t > EPS) {
-        h.t = t;
-        h.normal = normalize(cross(edge2, edge1));
-        h.refl = dir - (2 * dot(dir, h.normal)) * h.normal;
-        h.tri = __float_as_int(tp.c.y);
-        return true;
-    }
-    return false;
-}
-
-// calculateBaricentric (vein_collisions.cu:47-61); note e1 = v2 - v1 there
-__device__ __forceinline__ float3 barycentric(float3 point, float3 v0, float3 v1, float3 v2)
-{
-    const float3 e0 = v1 - v0, e1 = v2 - v1, e2 = point - v0;
-    const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(e2, e0), d21 = dot(e2, e1);
-    const float denom = d00 * d11 - d01 * d01;
-    float3 b;
-    b.x = (d11 * d20 - d01 * d21) / denom;
-    b.y = (d00 * d21 - d01 * d20) / denom;
-    b.z = 1.0f - b.x - b.y;
-    return b;
-}
-
-__device__ __forceinline__ void tri_stencil_range(unsigned id, int count, int& lo, int& hi)
-{
-    // vein_collisions.cu:82-230: ids are unsigned, `id > count - 2` is an unsigned comparison
-    if (id < 1u) { lo = 0; hi = 1; }
-    else if (id > (unsigned)(count - 2)) { lo = -1; hi = 0; }
-    else { lo = -1; hi = 1; }
-}
-
-__device__ __forceinline__ TriPacked load_tri(const TriPacked* __restrict__ tris, int i)
-{
-    TriPacked tp;
-    tp.a = tris[i].a; tp.b = tris[i].b; tp.c = tris[i].c;
-    return tp;
-}
-
-// does the box [lo,hi] overlap the box q?
-__device__ __forceinline__ bool box_overlap(const Aabb& q, float lox, float loy, float loz, float hix, float hiy, float hiz)
-{
-    return q.lox <= hix && q.hix >= lox && q.loy <= hiy && q.hiy >= loy && q.loz <= hiz && q.hiz >= loz;
-}
-
-// does the half-line o + t*d, t >= 0, touch the (already padded) box?  Conservative slab test.
-__device__ __forceinline__ bool ray_box(const Aabb& q, const float3 o, const float3 d)
-{
-    float tn = 0.f, tf = 3e38f;
-    const float lo[3] = {q.lox, q.loy, q.loz}, hi[3] = {q.hix, q.hiy, q.hiz};
-    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (fabsf(dd[k]) < 1e-12f) {
-            if (oo[k] < lo[k] || oo[k] > hi[k]) return false;
-        } else {
-            const float inv = 1.0f / dd[k];
-            const float t1 = (lo[k] - oo[k]) * inv, t2 = (hi[k] - oo[k]) * inv;
-            tn = fmaxf(tn, fminf(t1, t2));
-            tf = fminf(tf, fmaxf(t1, t2));
-        }
-    }
-    return tn <= tf * 1.00001f + 1e-4f;
-}
-
-// ---- first hit in the reference's traversal order -------------------------------------------------------
-// Straight traversal: x outer, y, z inner, sorted triangles inside a cell; the FIRST accepted triangle
-// wins, however far away it is (vein_collisions.cuh:66-91).
-template <bool STATS>
-__device__ bool first_hit_naive(const VeinCollideArgs& a, const float3 pos, const float3 dir, int cell, int x0, int x1, int y0, int y1,
-                                int z0, int z1, RayHit& h, unsigned long long& tests)
-{
-    const GridDev& g = a.tgrid;
-    const int plane = g.nx * g.ny;
-    for (int x = x0; x <= x1; ++x)
-        for (int y = y0; y <= y1; ++y)
-            for (int z = z0; z <= z1; ++z) {
-                const int c = cell + z * plane + y * g.nx + x;
-                if (c < 0 || c >= g.cells) continue;
-                const int s = a.cellStart[c], e = a.cellEnd[c];
-                for (int i = s; i <= e; ++i) {
-                    if (STATS) ++tests;
-                    if (ray_triangle(pos, dir, load_tri(a.tris, i), h)) return true;
-                }
-            }
-    return false;
-}
-
-// Same RESULT for everything the stage can observe, without testing ~800 triangles per particle.
-// The stage only acts when the first hit in traversal order lies within veinImpactDistance (d^2 <= 36,
-// vein_collisions.cu:237); a far first hit does nothing, exactly like no hit.  So:
-//   phase A  find the first triangle in traversal order that the ray hits with t <= 6 (+margin): only
-//            cells / slot groups whose box overlaps the box of that short segment are touched; for a
-//            particle in the bulk of the vein that is 27 box tests and nothing else;
-//   phase B  (rare: only particles about to touch the wall) make sure no EARLIER triangle in traversal
-//            order is hit further away - such a far hit would have been returned first by the reference
-//            and would mask the near one.  Uses half-line vs box culling.
-// Returns true iff the reference's traversal ends on a triangle within reach; h = that hit.
-template <bool STATS>
-__device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const float3 dir, int cell, int x0, int x1, int y0, int y1,
-                               int z0, int z1, RayHit& h, unsigned long long& tests)
-{
-    const GridDev& g = a.tgrid;
-    const int plane = g.nx * g.ny;
-    const float reach = a.phys.impactNear;
-    const float3 tip = pos + reach * dir;
-    const float slx = fminf(pos.x, tip.x), shx = fmaxf(pos.x, tip.x);
-    const float sly = fminf(pos.y, tip.y), shy = fmaxf(pos.y, tip.y);
-    const float slz = fminf(pos.z, tip.z), shz = fmaxf(pos.z, tip.z);
-    // ---- phase A
-    int hitOrder = -1, hitSlot = -1;   // position of the near hit in traversal order: (cell ordinal, slot)
-    int ord = 0;
-    for (int x = x0; x <= x1 && hitOrder < 0; ++x)
-        for (int y = y0; y <= y1 && hitOrder < 0; ++y)
-            for (int z = z0; z <= z1 && hitOrder < 0; ++z, ++ord) {
-                const int c = cell + z * plane + y * g.nx + x;
-                if (c < 0 || c >= g.cells) continue;
-                if (!box_overlap(a.cellBox[c], slx, sly, slz, shx, shy, shz)) continue;
-                const int s = a.cellStart[c], e = a.cellEnd[c];
-                for (int gi = s >> 3; gi <= (e >> 3) && hitOrder < 0; ++gi) {
-                    if (!box_overlap(a.groupBox[gi], slx, sly, slz, shx, shy, shz)) continue;
-                    const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
-                    for (int i = i0; i <= i1; ++i) {
-                        if (STATS) ++tests;
-                        RayHit cand;
-                        if (ray_triangle(pos, dir, load_tri(a.tris, i), cand) && cand.t <= reach) {
-                            h = cand; hitOrder = ord; hitSlot = i;
-                            break;
-                        }
-                    }
-                }
-            }
-    if (hitOrder < 0) return false;
-    // ---- phase B: any hit (necessarily beyond reach) earlier in traversal order?
-    ord = 0;
-    for (int x = x0; x <= x1; ++x)
-        for (int y = y0; y <= y1; ++y)
-            for (int z = z0; z <= z1; ++z, ++ord) {
-                if (ord > hitOrder) return true;
-                const int c = cell + z * plane + y * g.nx + x;
-                if (c < 0 || c >= g.cells) continue;
-                if (!ray_box(a.cellBox[c], pos, dir)) continue;
-                const int s = a.cellStart[c];
-                const int e = (ord == hitOrder) ? hitSlot - 1 : a.cellEnd[c];
-                for (int gi = s >> 3; gi <= (e >> 3); ++gi) {
-                    if (e < s) break;
-                    if (!ray_box(a.groupBox[gi], pos, dir)) continue;
-                    const int i0 = max(s, gi << 3), i1 = min(e, (gi << 3) + 7);
-                    for (int i = i0; i <= i1; ++i) {
-                        if (STATS) ++tests;
-                        RayHit far;
-                        if (ray_triangle(pos, dir, load_tri(a.tris, i), far)) return false;   // masked by an earlier (far) triangle
-                    }
-                }
-            }
-    return true;
-}
-
-// what the stage does once the traversal has ended on triangle h (vein_collisions.cu:234-276)
-__device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid, const float4 p4, const float4 v4, const float3 dir,
-                                               const RayHit& h, bool splatOnly = false)
-{
-    const PhysDev& ph = a.phys;
-    const float3 pos = xyz(p4), velocity = xyz(v4);
-    const bool hit = true;
-    // relativePosition = pos - (pos + t*dir), evaluated literally (vein_collisions.cu:234)
-    const float3 rel = pos - (pos + h.t * dir);
-    const float d2 = length_squared(rel);
-    if (a.apply && hit && d2 <= ph.impact2) {
-        if (!splatOnly && d2 > ph.minForce2) {
-            const float4 F4 = a.frc[pid];
-            const float3 F = xyz(F4);
-            float3 add;
-            if (ph.reactionForce) {
-                add = ((-1.0f * dot(F, h.normal)) * h.normal) / dot(h.normal, h.normal);
-            } else {
-                int t = 0;
-                while (t + 1 < a.types.n && pid >= a.types.t[t + 1].pStart) ++t;
-                const float radius = __ldg(a.collR + a.types.t[t].mStart + (pid - a.types.t[t].pStart) % a.types.t[t].P);
-                // physics::addResilientForceOnCollision(relativePosition, velocity, d2, radius, id, 0.5f, forces)
-                const float3 rdir = normalize(rel);
-                const float3 tang = velocity - dot(velocity, rdir) * rdir;
-                const float3 spring = (-ph.coll_spring * (radius * 2 - sqrtf(d2))) * rdir;
-                add = 0.5f * (spring + ph.coll_damping * velocity + ph.coll_shear * tang);
-            }
-            a.frc[pid] = make_float4(F.x + add.x, F.y + add.y, F.z + add.z, F4.w);
-        }
-        if (!splatOnly) {
-            const float speed = length(velocity);
-            const float3 dv = 1.0f * ((ph.velocity_collision_damping * speed) * h.refl - velocity);   // gpuCount = 1
-            a.vel[pid] = make_float4(velocity.x + dv.x, velocity.y + dv.y, velocity.z + dv.z, v4.w);
-        }
-        const float3 ds = ph.vein_collision_force_intensity * velocity;
-        const unsigned i0 = a.vidx[3 * h.tri], i1 = a.vidx[3 * h.tri + 1], i2 = a.vidx[3 * h.tri + 2];
-        const float3 b = barycentric(pos + h.t * dir, xyz(a.vpos[i0]), xyz(a.vpos[i1]), xyz(a.vpos[i2]));
-        // the reference uses plain += here and loses updates when two particles share a vertex
-        atomicAdd(&a.vfrc[i0].x, b.x * ds.x); atomicAdd(&a.vfrc[i0].y, b.x * ds.y); atomicAdd(&a.vfrc[i0].z, b.x * ds.z);
-        atomicAdd(&a.vfrc[i1].x, b.y * ds.x); atomicAdd(&a.vfrc[i1].y, b.y * ds.y); atomicAdd(&a.vfrc[i1].z, b.y * ds.z);
-        atomicAdd(&a.vfrc[i2].x, b.z * ds.x); atomicAdd(&a.vfrc[i2].y, b.z * ds.y); atomicAdd(&a.vfrc[i2].z, b.z * ds.z);
-        if (!splatOnly) atomicAdd(&a.counters->veinHits, 1ull);
-    }
-}
-
-// one particle of the vein-collision stage (vein_collisions.cu:63-277)
-template <bool FAST, bool STATS>
-__device__ __forceinline__ void vein_collide_particle(const VeinCollideArgs& a, int pid, unsigned long long& myTests, bool splatOnly = false)
-{
-    const GridDev& g = a.tgrid;
-    const PhysDev& ph = a.phys;
-    const float4 p4 = a.pos[pid], v4 = a.vel[pid];
-    const float3 pos = xyz(p4), velocity = xyz(v4);
-    const float3 dir = normalize(velocity);
-    const int cell = axis_cell(pos.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(pos.y, g.miny, g.leny, g.csy) * g.nx +
-                     axis_cell(pos.x, g.minx, g.lenx, g.csx);
-    int x0, x1, y0, y1, z0, z1;
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
-    tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
-    RayHit h;
-    h.t = 1e10f; h.normal = f3(0.f, 0.f, 0.f); h.refl = f3(0.f, 0.f, 0.f); h.tri = 0;
-    const bool hit = FAST ? first_hit_fast<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests)
-                          : first_hit_naive<STATS>(a, pos, dir, cell, x0, x1, y0, y1, z0, z1, h, myTests);
-    if (a.dbgTri) {
-        a.dbgTri[pid] = hit ? h.tri : -1;
-        a.dbgT[pid] = hit ? h.t : 1e10f;
-    }
-    if (hit) vein_apply_hit(a, pid, p4, v4, dir, h, splatOnly);
-}
 
 // every particle (exhaustive cross-check mode and the debug view)
 template <bool FAST, bool STATS>
@@ -488,20 +242,6 @@ __global__ void __launch_bounds__(128) vein_collisions_kernel(const VeinCollideA
     }
 }
 
-// point (or ball) vs slab widened by `reach`
-__device__ __forceinline__ bool slab_near(const CellSlab& sl, float3 p, float reach)
-{
-    const float d = sl.nx * p.x + sl.ny * p.y + sl.nz * p.z;
-    return d + reach >= sl.dmin && d - reach <= sl.dmax;
-}
-
-// segment p .. p + reach*dir vs slab
-__device__ __forceinline__ bool slab_segment(const CellSlab& sl, float3 p, float3 dir, float reach)
-{
-    const float d0 = sl.nx * p.x + sl.ny * p.y + sl.nz * p.z;
-    const float d1 = d0 + reach * (sl.nx * dir.x + sl.ny * dir.y + sl.nz * dir.z);
-    return fmaxf(d0, d1) + 1e-3f >= sl.dmin && fminf(d0, d1) - 1e-3f <= sl.dmax;
-}
 
 // Production path, step 1: one thread per BLOOD CELL.  The stage can only act on a particle that has a wall
 // triangle within veinImpactDistance along its ray, so a blood cell is skipped as a whole unless its bounding
@@ -632,7 +372,7 @@ __device__ bool first_hit_marked(const VeinCollideArgs& a, const CullEntry& ent,
             for (int i = i0; i <= i1; ++i) {
                 if (STATS) ++tests;
                 RayHit cand;
-                if (ray_triangle(pos, dir, load_tri(a.tris, i), cand) && cand.t <= reach) {
+                if (ray_triangle(pos, dir, load_tri(a, i), cand) && cand.t <= reach) {
                     h = cand; bestKey = key; bestSlot = i; found = true;
                     break;
                 }
@@ -660,7 +400,7 @@ __device__ bool first_hit_marked(const VeinCollideArgs& a, const CullEntry& ent,
                     for (int i = i0; i <= i1; ++i) {
                         if (STATS) ++tests;
                         RayHit far;
-                        if (ray_triangle(pos, dir, load_tri(a.tris, i), far)) return false;   // masked by an earlier (far) triangle
+                        if (ray_triangle(pos, dir, load_tri(a, i), far)) return false;   // masked by an earlier (far) triangle
                     }
                 }
             }
@@ -867,7 +607,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
             const int pl = q.x & 255, key = q.x >> 8;
             if (STATS) ++myTests;
             RayHit cand;
-            if (ray_triangle(xyz(sPos[pl]), xyz(sDir[pl]), load_tri(a.tris, slot), cand) && cand.t <= reach)
+            if (ray_triangle(xyz(sPos[pl]), xyz(sDir[pl]), load_tri(a, slot), cand) && cand.t <= reach)
                 atomicMin(&sBest[pl], ((unsigned long long)key << 32) | (unsigned)slot);
         }
         __syncthreads();
@@ -922,7 +662,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
                             if (slot >= s && slot <= e) {
                                 if (STATS) ++myTests;
                                 RayHit far;
-                                hitFar = ray_triangle(pos, dir, load_tri(a.tris, slot), far);
+                                hitFar = ray_triangle(pos, dir, load_tri(a, slot), far);
                             }
                         }
                         masked = __any_sync(0xffffffffu, hitFar);
@@ -931,7 +671,7 @@ __global__ void __launch_bounds__(COOP_THREADS) vein_collisions_coop_kernel(cons
             }
             if (!masked && lane == 0) {
                 RayHit h;
-                ray_triangle(pos, dir, load_tri(a.tris, bestSlot), h);
+                ray_triangle(pos, dir, load_tri(a, bestSlot), h);
                 const int pid = sPid[pl];
                 vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], dir, h, sSplatOnly[pl] != 0);
             }

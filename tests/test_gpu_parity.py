@@ -112,12 +112,16 @@ def test_vs_oracle_cylinder_scene(bcs_lib, oracle_lib):
         _compare_step(sim, orc, 8, "cylinder")
 
 
-@pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
+@pytest.mark.parametrize("semantics,wall_margin", [(capi.SEM_CLEAN, None), (capi.SEM_CLEAN, "0.0002"), (capi.SEM_REFERENCE, None)])
 @pytest.mark.parametrize("which", ["cfg1_wide", "cylinder"])
-def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantics):
-    """The production vein-collision kernel (segment / half-line culling over a refitted box hierarchy) must
-    act on exactly the particles, with exactly the triangle, the reference's exhaustive in-order traversal
-    ends on - including far triangles that mask a near hit.  Bitwise equal particle outputs."""
+def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantics, wall_margin, monkeypatch):
+    """The production vein-collision kernels (clean semantics: lazily rebuilt wall grid, wall.cu; reference
+    semantics: segment / half-line culling over the per-step refitted box hierarchy, vein.cu) must act on exactly
+    the particles, with exactly the triangle, the reference's exhaustive in-order traversal ends on - including
+    far triangles that mask a near hit.  Bitwise equal particle outputs.  A tiny wall margin forces
+    the wall grid through its rebuild path every few steps."""
+    if wall_margin:
+        monkeypatch.setenv("BCS_WALL_MARGIN", wall_margin)
     if which == "cfg1_wide":
         sc = golden_scene("cfg1")
         st, _ = seeded_state("cfg1", "wide")
@@ -140,6 +144,9 @@ def test_culled_vein_search_equals_exhaustive_traversal(bcs_lib, which, semantic
             refcheck.assert_close(refcheck.down(fast, capi.VEIN_FRC), refcheck.down(slow, capi.VEIN_FRC), "vein force splats", rtol=1e-5,
                                   scale=1.0)
             fast.step(1)
+        if semantics == capi.SEM_CLEAN:
+            builds = fast.stats()["wall_rebuilds"]
+            assert builds >= 1 and (not wall_margin or builds > 3), builds
     assert total_hits > 100
 
 
