@@ -106,7 +106,8 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "tri_refit": 96 * T,                       # R 3 idx + 3 vertices (48), W packed triangle (48)
         "cell_box": 48 * T,                        # R packed triangles
         "vein_cull_cells": 12 * N,                 # R positions
-        "vein_collisions": 24 * N + 120 * hits,
+        "vein_filter": 24 * N,                     # wall-grid path: R pos+vel of every particle
+        "vein_collisions": 24 * N + 120 * hits,    # (wall-grid path: the triangle tests of the few candidates; same contract figure)
         "vein_ghost_splat": 0,
         "vein_masking": 0,                         # phase B of the wall-grid path: a few thousand particles
         "wall_rebuild": 0,                         # returns at once unless a vertex left its margin

@@ -308,6 +308,8 @@ void setup_wall(bcs_sim* s)
     w.cursor = s->track(dev_alloc<int>((size_t)w.cells));
     w.rec = s->track(dev_alloc<int4>(2 * (size_t)w.cells));
     w.near = s->track(dev_alloc<unsigned char>((size_t)w.cells));
+    w.occ = s->track(dev_alloc<unsigned char>((size_t)w.cells));
+    w.occ3 = s->track(dev_alloc<unsigned char>((size_t)w.cells));
     w.nearTmp = s->track(dev_alloc<unsigned char>(2 * (size_t)w.cells));
     BCS_CUDA(cudaMemset(w.near, 0, (size_t)w.cells));
     w.list = s->track(dev_alloc<int>((size_t)w.cap));
@@ -325,13 +327,17 @@ void setup_wall(bcs_sim* s)
     w.overflow = s->track(dev_alloc<int>(1));
     w.barrier = s->track(dev_alloc<unsigned>(2));
     w.builds = s->track(dev_alloc<unsigned long long>(1));
-    w.queueCount = s->track(dev_alloc<int>(1));
+    w.queueCount = s->track(dev_alloc<int>(2));
+    w.entryCount = w.queueCount + 1;
     cudaDeviceProp prop{};
     BCS_CUDA(cudaGetDeviceProperties(&prop, s->device));
     s->numSMs = prop.multiProcessorCount;
     w.blockSums = s->track(dev_alloc<int>(s->numSMs));
     w.queue = s->track(dev_alloc<int>(hs.N));
-    w.queueBest = s->track(dev_alloc<unsigned long long>(hs.N));
+    w.best = s->track(dev_alloc<unsigned long long>(hs.N));
+    w.ghostFlag = s->track(dev_alloc<unsigned char>(hs.N));
+    w.entryCap = 4 * hs.N + 1024;
+    w.entries = s->track(dev_alloc<int2>((size_t)w.entryCap));
     BCS_CUDA(cudaMemset(w.start, 0, ((size_t)w.cells + 1) * sizeof(int)));
     BCS_CUDA(cudaMemset(w.overflow, 0, sizeof(int)));
     BCS_CUDA(cudaMemset(w.barrier, 0, 2 * sizeof(unsigned)));

@@ -118,6 +118,8 @@ struct WallGridDev {
     int nx, ny, nz, cells;
     int* start;               // [cells + 1] offsets into list
     int4* rec;                // [2 * cells] 32-byte record per cell: {list start, entries, n.x, n.y | n.z, dmin, dmax, -}
+    unsigned char* occ;       // [cells] 1 = the cell lists at least one triangle
+    unsigned char* occ3;      // [cells] bits 0..2 = occ of the cell and its two +x neighbours
     unsigned char* near;      // [cells] 1 = a non-empty cell lies within +-2 cells (a particle here can reach the wall)
     unsigned char* nearTmp;   // [2 * cells] scratch of the separable dilation
     int* cursor;              // [cells]     counts during a rebuild, then fill cursors
@@ -134,9 +136,13 @@ struct WallGridDev {
     int* blockSums;           // [rebuild grid]
     unsigned long long* builds;   // number of rebuilds so far
     float margin;
-    int* queue;               // [N] particles with a near hit (phase B work list) ...
-    unsigned long long* queueBest;   // ... and their (traversal key << 32 | slot)
-    int* queueCount;
+    int* queue;               // [N] particles with a near hit (phase B work list)
+    unsigned char* ghostFlag; // [N] slab mode: 1 = ghost (splat only); valid for candidates
+    int* queueCount;          // [2] {phase-B particles, entries}: adjacent, cleared together
+    int* entryCount;          // = queueCount + 1
+    int2* entries;            // [entryCap] (particle, wall-grid cell) pairs whose triangles are to be tested
+    int entryCap;
+    unsigned long long* best; // [N] (traversal key << 32 | slot) of the first near hit; valid for candidates only
 };
 
 // ---- vein.cu -------------------------------------------------------------------------------------------

@@ -197,7 +197,7 @@ wall_rebuild_kernel(const WallGridDev w, const GridDev tg, int V, int T, const f
     for (int c = gwarp; c < w.cells; c += nWarps) {
         const int s = w.start[c], e = min(w.start[c + 1], w.cap);
         if (e <= s) {
-            if (lane == 0) { w.rec[2 * c] = make_int4(s, 0, 0, 0); w.near[c] = 0; }
+            if (lane == 0) { w.rec[2 * c] = make_int4(s, 0, 0, 0); w.occ[c] = 0; }
             continue;
         }
         float3 nsum = f3(0.f, 0.f, 0.f);
@@ -229,7 +229,7 @@ wall_rebuild_kernel(const WallGridDev w, const GridDev tg, int V, int T, const f
         if (lane == 0) {
             w.rec[2 * c] = make_int4(s, e - s, __float_as_int(n.x), __float_as_int(n.y));
             w.rec[2 * c + 1] = make_int4(__float_as_int(n.z), __float_as_int(dmin - pad), __float_as_int(dmax + pad), 0);
-            w.near[c] = 1;
+            w.occ[c] = 1;
         }
     }
     // ---- P5b: boxes of the triangle-grid cells (phase B): union of the group boxes the cell's slot range touches
@@ -261,8 +261,10 @@ wall_rebuild_kernel(const WallGridDev w, const GridDev tg, int V, int T, const f
         const int x = c % w.nx;
         unsigned char v = 0;
         for (int d = -2; d <= 2; ++d)
-            if (x + d >= 0 && x + d < w.nx) v |= w.near[c + d];
+            if (x + d >= 0 && x + d < w.nx) v |= w.occ[c + d];
         t0[c] = v;
+        // occupancy of the three x-adjacent cells starting here, one byte: a (y,z) row of a segment's box is ONE load
+        w.occ3[c] = (unsigned char)(w.occ[c] | (x + 1 < w.nx ? w.occ[c + 1] << 1 : 0) | (x + 2 < w.nx ? w.occ[c + 2] << 2 : 0));
     }
     grid_barrier(w.barrier, target, nb);
     for (int c = gtid; c < w.cells; c += gsize) {
@@ -307,41 +309,47 @@ __global__ void __launch_bounds__(256) wall_slot_info_kernel(const int* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// phase A.  A CTA takes 256 particles and works in three uniformly executed passes (a thread-per-particle search
-// ran with 5 of 32 lanes active: every particle meets a different number of cells and triangles):
-//   1  thread per particle: near-mask byte, occupancy of the <= 3x3x3 wall-grid cells under the segment's box
-//      (branch-free: all loads in flight together), slab test per occupied cell -> shared queue of (particle, cell)
-//   2  8 lanes per queue entry, one lane per listed triangle: stencil membership from the static slot table,
-//      Moeller-Trumbore on the live vertices; near hits race with a 64-bit atomicMin on (traversal key, slot)
-//   3  particles with a near hit go to the global phase-B queue
-// Queue overflow (pathological clustering) and particles outside the triangle grid take the sequential search
+// Phase A in two kernels, so that every pass runs with full warps and nothing waits at a CTA barrier:
+//   A1  thread per particle (streaming, light): near-mask byte; occupancy of the <= 3x3x3 wall-grid cells under the
+//       segment's box (branch-free: all loads in flight together); slab test per occupied cell.  Survivors are
+//       appended to a global queue of (particle, cell) entries - one atomicAdd per WARP - and the particle to the
+//       candidate list, its best[] word reset.
+//   A2  8 lanes per queue entry, entries spread evenly over a persistent grid: one lane per listed triangle,
+//       stencil membership from the static slot table, Moeller-Trumbore on the live vertices; near hits race with a
+//       64-bit atomicMin on best[particle] = (traversal key, slot).
+// Particles outside the triangle grid and queue overflow (pathological clustering) take the sequential search
 // (vein_device.cuh) in phase B.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PHASE_A_THREADS = 256;
-constexpr int Q1_CAP = 2048;
 constexpr unsigned long long NO_HIT = ~0ull, SEQUENTIAL = ~0ull - 1ull;
 
-template <bool STATS, bool SLAB>
-__global__ void __launch_bounds__(PHASE_A_THREADS) wall_phase_a_kernel(const VeinCollideArgs a)
-{
-    __shared__ float4 sPos[PHASE_A_THREADS], sDir[PHASE_A_THREADS];
-    __shared__ int4 sInfo[PHASE_A_THREADS];                    // pcx, pcy, pcz, packed stencil ranges
-    __shared__ unsigned long long sBest[PHASE_A_THREADS];
-    __shared__ int2 q1[Q1_CAP];                                // (particle slot in the CTA, wall-grid cell)
-    __shared__ int q1n;
+struct ParticleFrame {     // what the triangle tests need to know about a particle; recomputed identically in A2 and B
+    float3 pos, dir;
+    int pcx, pcy, pcz;     // its triangle-grid cell
+    int x0, x1, y0, y1, z0, z1;   // trimmed stencil (vein_collisions.cu:76-230)
+};
 
+__device__ __forceinline__ ParticleFrame particle_frame(const VeinCollideArgs& a, int pid)
+{
+    const GridDev& g = a.tgrid;
+    ParticleFrame f;
+    f.pos = xyz(a.pos[pid]);
+    f.dir = normalize(xyz(a.vel[pid]));
+    f.pcx = axis_cell(f.pos.x, g.minx, g.lenx, g.csx); f.pcy = axis_cell(f.pos.y, g.miny, g.leny, g.csy);
+    f.pcz = axis_cell(f.pos.z, g.minz, g.lenz, g.csz);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(f.pos.x - g.minx, (float)g.csx)), g.nx, f.x0, f.x1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(f.pos.y - g.miny, (float)g.csy)), g.ny, f.y0, f.y1);
+    tri_stencil_range(__float2uint_rz(__fdiv_rn(f.pos.z - g.minz, (float)g.csz)), g.nz, f.z0, f.z1);
+    return f;
+}
+
+template <bool SLAB>
+__global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs a)
+{
     const WallGridDev& w = a.wall;
     const GridDev& g = a.tgrid;
     const float reach = a.phys.impactNear;
-    unsigned long long myTests = 0;
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * PHASE_A_THREADS + tid;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     if (i == 0) *w.dirty = 0;   // consumed by this step's rebuild; the vertex integrator raises it again if needed
-    if (tid == 0) q1n = 0;
-    sBest[tid] = NO_HIT;
-    __syncthreads();
-
-    // ---- pass 1
     int pid = -1, ghost = 0;
     if (SLAB) {
         if (i < a.n) {
@@ -351,6 +359,9 @@ __global__ void __launch_bounds__(PHASE_A_THREADS) wall_phase_a_kernel(const Vei
     } else if (i < a.n) {
         pid = i;
     }
+    unsigned pass = 0;          // bit b: cell (b%3, (b/3)%3, b/9) of the segment's box passed the slab test
+    int wx0 = 0, wy0 = 0, wz0 = 0;
+    bool sequential = false;
     if (pid >= 0) {
         const float4 p4 = a.pos[pid], v4 = a.vel[pid];
         const float3 pos = xyz(p4);
@@ -360,86 +371,98 @@ __global__ void __launch_bounds__(PHASE_A_THREADS) wall_phase_a_kernel(const Vei
             const float3 dir = normalize(xyz(v4));
             const float3 tip = pos + reach * dir;
             constexpr float EPSB = 1e-3f;
-            const int wx0 = wall_axis(fminf(pos.x, tip.x) - EPSB, w.ox, w.invh, w.nx), wx1 = wall_axis(fmaxf(pos.x, tip.x) + EPSB, w.ox, w.invh, w.nx);
-            const int wy0 = wall_axis(fminf(pos.y, tip.y) - EPSB, w.oy, w.invh, w.ny), wy1 = wall_axis(fmaxf(pos.y, tip.y) + EPSB, w.oy, w.invh, w.ny);
-            const int wz0 = wall_axis(fminf(pos.z, tip.z) - EPSB, w.oz, w.invh, w.nz), wz1 = wall_axis(fmaxf(pos.z, tip.z) + EPSB, w.oz, w.invh, w.nz);
-            // reach <= 2 cells: the box spans at most 3 cells per axis.  Occupancy of all of them, branch-free.
+            wx0 = wall_axis(fminf(pos.x, tip.x) - EPSB, w.ox, w.invh, w.nx);
+            wy0 = wall_axis(fminf(pos.y, tip.y) - EPSB, w.oy, w.invh, w.ny);
+            wz0 = wall_axis(fminf(pos.z, tip.z) - EPSB, w.oz, w.invh, w.nz);
+            const int wx1 = wall_axis(fmaxf(pos.x, tip.x) + EPSB, w.ox, w.invh, w.nx);
+            const int wy1 = wall_axis(fmaxf(pos.y, tip.y) + EPSB, w.oy, w.invh, w.ny);
+            const int wz1 = wall_axis(fmaxf(pos.z, tip.z) + EPSB, w.oz, w.invh, w.nz);
+            // reach <= 2 cells: the box spans at most 3 cells per axis.  Occupancy of all of them, branch-free: one byte
+            // per (y,z) row holds the bits of its three x-adjacent cells.
             unsigned occ = 0;
+            const unsigned xmask = (1u << (wx1 - wx0 + 1)) - 1u;
 #pragma unroll
-            for (int b = 0; b < 27; ++b) {
-                const int x = wx0 + b % 3, y = wy0 + (b / 3) % 3, z = wz0 + b / 9;
-                const bool in = x <= wx1 && y <= wy1 && z <= wz1;
-                const int c = in ? (z * w.ny + y) * w.nx + x : 0;
-                const int cnt = __ldg(&w.rec[2 * c].y);
-                occ |= (in && cnt > 0) ? 1u << b : 0u;
+            for (int r = 0; r < 9; ++r) {
+                const int y = wy0 + r % 3, z = wz0 + r / 3;
+                const bool in = y <= wy1 && z <= wz1;
+                const unsigned bits = __ldg(w.occ3 + (in ? (z * w.ny + y) * w.nx + wx0 : 0));
+                occ |= in ? (bits & xmask) << (3 * r) : 0u;
             }
-            if (occ) {
+            while (occ) {
+                const int b = __ffs(occ) - 1;
+                occ &= occ - 1;
+                const int c = ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3;
+                const int4 r0 = __ldg(w.rec + 2 * c), r1 = __ldg(w.rec + 2 * c + 1);
+                const CellSlab sl{__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y), __int_as_float(r1.z)};
+                if (slab_segment(sl, pos, dir, reach)) pass |= 1u << b;
+            }
+            if (pass) {
                 const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
                           pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
-                bool sequential = pcx >= g.nx || pcy >= g.ny || pcz >= g.nz;   // outside the triangle grid
-                bool any = false;
-                while (occ) {
-                    const int b = __ffs(occ) - 1;
-                    occ &= occ - 1;
-                    const int c = ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3;
-                    const int4 r0 = __ldg(w.rec + 2 * c), r1 = __ldg(w.rec + 2 * c + 1);
-                    const CellSlab sl{__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y), __int_as_float(r1.z)};
-                    if (!slab_segment(sl, pos, dir, reach)) continue;
-                    any = true;
-                    if (sequential) break;
-                    const int idx = atomicAdd(&q1n, 1);
-                    if (idx < Q1_CAP) q1[idx] = make_int2(tid, c);
-                    else sequential = true;
-                }
-                if (any) {
-                    if (sequential) {
-                        sBest[tid] = SEQUENTIAL;
-                    } else {
-                        int x0, x1, y0, y1, z0, z1;
-                        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
-                        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
-                        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
-                        sPos[tid] = make_float4(pos.x, pos.y, pos.z, 0.f);
-                        sDir[tid] = make_float4(dir.x, dir.y, dir.z, 0.f);
-                        sInfo[tid] = make_int4(pcx, pcy, pcz, (x0 + 1) | ((x1 + 1) << 2) | ((y0 + 1) << 4) | ((y1 + 1) << 6) | ((z0 + 1) << 8) | ((z1 + 1) << 10));
-                    }
-                }
+                sequential = pcx >= g.nx || pcy >= g.ny || pcz >= g.nz;   // outside the triangle grid
             }
         }
     }
-    __syncthreads();
+    // warp-aggregated append: entries, then candidates
+    const int mine = sequential ? 0 : __popc(pass);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned candMask = __ballot_sync(0xffffffffu, pass != 0);
+    if (candMask == 0) return;
+    int ebase = 0;
+    if (lane == 0 && total) ebase = atomicAdd(w.entryCount, total);
+    ebase = __shfl_sync(0xffffffffu, ebase, 0);
+    if (pass) {
+        int at = ebase + incl - mine;
+        if (!sequential && at + mine > w.entryCap) sequential = true;   // queue full: this particle searches sequentially
+        if (!sequential) {
+            unsigned m = pass;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                w.entries[at++] = make_int2(pid, ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3);
+            }
+        }
+        w.best[pid] = sequential ? SEQUENTIAL : NO_HIT;
+        w.ghostFlag[pid] = (unsigned char)ghost;
+        if (sequential) w.queue[atomicAdd(w.queueCount, 1)] = pid;   // rare: straight to phase B
+    }
+}
 
-    // ---- pass 2: 8 lanes per (particle, cell) entry, one lane per listed triangle
-    const int n1 = min(q1n, Q1_CAP);
-    const int sub = tid & 7;
-    for (int e = tid >> 3; e < n1; e += PHASE_A_THREADS / 8) {
-        const int2 it = q1[e];
-        const int pl = it.x;
-        if (sBest[pl] == SEQUENTIAL) continue;
+template <bool STATS>
+__global__ void __launch_bounds__(256) wall_triangles_kernel(const VeinCollideArgs a)
+{
+    const WallGridDev& w = a.wall;
+    const float reach = a.phys.impactNear;
+    const int n = min(*w.entryCount, w.entryCap);
+    const int sub = threadIdx.x & 7;
+    const int groups = (gridDim.x * blockDim.x) >> 3;
+    unsigned long long myTests = 0;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; e < n; e += groups) {
+        const int2 it = w.entries[e];
+        const int pid = it.x;
+        if (w.best[pid] == SEQUENTIAL) continue;
         const int4 r0 = __ldg(w.rec + 2 * it.y);
-        const int4 info = sInfo[pl];
-        const int x0 = (info.w & 3) - 1, x1 = ((info.w >> 2) & 3) - 1, y0 = ((info.w >> 4) & 3) - 1, y1 = ((info.w >> 6) & 3) - 1,
-                  z0 = ((info.w >> 8) & 3) - 1, z1 = ((info.w >> 10) & 3) - 1;
-        const float3 pos = xyz(sPos[pl]), dir = xyz(sDir[pl]);
+        const ParticleFrame f = particle_frame(a, pid);
         for (int k = sub; k < r0.y; k += 8) {
             const int slot = __ldg(w.list + r0.x + k);
             const int4 si = __ldg(w.slotInfo + slot);
-            const int dx = si.y - info.x, dy = si.z - info.y, dz = si.w - info.z;
-            if (dx < x0 || dx > x1 || dy < y0 || dy > y1 || dz < z0 || dz > z1) continue;   // outside this particle's stencil
+            const int dx = si.y - f.pcx, dy = si.z - f.pcy, dz = si.w - f.pcz;
+            if (dx < f.x0 || dx > f.x1 || dy < f.y0 || dy > f.y1 || dz < f.z0 || dz > f.z1) continue;   // outside this particle's stencil
             const unsigned long long cand = ((unsigned long long)(((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1)) << 32) | (unsigned)slot;
-            if (cand >= sBest[pl]) continue;   // a filter only (racy read): the atomicMin decides
+            if (cand >= w.best[pid]) continue;   // a filter only (racy read): the atomicMin decides
             if (STATS) ++myTests;
             RayHit h;
-            if (ray_triangle(pos, dir, load_tri(a, slot), h) && h.t <= reach) atomicMin(&sBest[pl], cand);
+            if (ray_triangle(f.pos, f.dir, load_tri(a, slot), h) && h.t <= reach) {
+                // whoever replaces NO_HIT is the particle's first near hit to land: it enters the phase-B list exactly once
+                if (atomicMin(w.best + pid, cand) == NO_HIT) w.queue[atomicAdd(w.queueCount, 1)] = pid;
+            }
         }
-    }
-    __syncthreads();
-
-    // ---- pass 3
-    if (sBest[tid] != NO_HIT) {
-        const int q = atomicAdd(w.queueCount, 1);
-        w.queue[q] = ghost ? -(pid + 1) : pid;
-        w.queueBest[q] = sBest[tid];
     }
     if (STATS) {
         for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
@@ -448,10 +471,12 @@ __global__ void __launch_bounds__(PHASE_A_THREADS) wall_phase_a_kernel(const Vei
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// phase B: warp per particle with a near hit - is it masked by an earlier (far) hit?  Then apply.
+// phase B: a warp per particle with a near hit (listed by A2 when its first near hit landed) - is it masked by an earlier (far) hit?  Then apply.
+// The (stencil cell, slot group) pairs up to the near hit are flattened over the lanes, so the box tests and the
+// triangle tests run 32 wide instead of cell after cell (the search is a chain of dependent L2 reads).
 // ------------------------------------------------------------------------------------------------------------
 template <bool STATS>
-__global__ void __launch_bounds__(128) wall_phase_b_kernel(const VeinCollideArgs a)
+__global__ void __launch_bounds__(128) wall_masking_kernel(const VeinCollideArgs a)
 {
     const WallGridDev& w = a.wall;
     const GridDev& g = a.tgrid;
@@ -461,68 +486,75 @@ __global__ void __launch_bounds__(128) wall_phase_b_kernel(const VeinCollideArgs
     const int n = *w.queueCount;
     unsigned long long myTests = 0;
     for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += nWarps) {
-        const int tag = w.queue[q];
-        const bool splatOnly = tag < 0;
-        const int pid = splatOnly ? -tag - 1 : tag;
-        const unsigned long long best = w.queueBest[q];
-        if (best == SEQUENTIAL) {
-            if (lane == 0) vein_collide_particle<true, STATS>(a, pid, myTests, splatOnly);
-            continue;
-        }
-        const float4 p4 = a.pos[pid], v4 = a.vel[pid];
-        const float3 pos = xyz(p4), dir = normalize(xyz(v4));
-        const int bestKey = (int)(best >> 32), bestSlot = (int)(best & 0xffffffffu);
-        const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
-                  pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
-        int x0, x1, y0, y1, z0, z1;
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.x - g.minx, (float)g.csx)), g.nx, x0, x1);
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.y - g.miny, (float)g.csy)), g.ny, y0, y1);
-        tri_stencil_range(__float2uint_rz(__fdiv_rn(pos.z - g.minz, (float)g.csz)), g.nz, z0, z1);
-        const int cell = (pcz * g.ny + pcy) * g.nx + pcx;
-        // lane == traversal key of one stencil cell (x outer, y, z inner)
-        const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
-        const int c = cell + dz * plane + dy * g.nx + dx;
-        bool visit = lane < 27 && lane <= bestKey && dx >= x0 && dx <= x1 && dy >= y0 && dy <= y1 && dz >= z0 && dz <= z1 && c >= 0 && c < g.cells;
-        if (visit) visit = a.cellEnd[c] >= a.cellStart[c] && ray_box(w.cellBox[c], pos, dir);
-        unsigned cm = __ballot_sync(0xffffffffu, visit);
-        bool masked = false;
-        while (cm && !masked) {
-            const int key = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const int cc = cell + (key % 3 - 1) * plane + ((key / 3) % 3 - 1) * g.nx + (key / 9 - 1);
-            const int s = a.cellStart[cc];
-            const int e = (key == bestKey) ? bestSlot - 1 : a.cellEnd[cc];
-            if (e < s) continue;
-            for (int g0 = s >> 3; g0 <= (e >> 3) && !masked; g0 += 32) {
-                const int gi = g0 + lane;
-                const bool ok = gi <= (e >> 3) && ray_box(w.groupBox[gi], pos, dir);
+        {
+            const int pid = w.queue[q];
+            const unsigned long long best = w.best[pid];
+            const bool splatOnly = w.ghostFlag[pid] != 0;
+            if (best == SEQUENTIAL) {
+                if (lane == 0) vein_collide_particle<true, STATS>(a, pid, myTests, splatOnly);
+                continue;
+            }
+            const ParticleFrame f = particle_frame(a, pid);
+            const int bestKey = (int)(best >> 32), bestSlot = (int)(best & 0xffffffffu);
+            const int cell = (f.pcz * g.ny + f.pcy) * g.nx + f.pcx;
+            // lane == traversal key of one stencil cell (x outer, y, z inner): its slot-group range up to the near hit
+            const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
+            const int c = cell + dz * plane + dy * g.nx + dx;
+            int s = 0, e = -1;
+            if (lane < 27 && lane <= bestKey && dx >= f.x0 && dx <= f.x1 && dy >= f.y0 && dy <= f.y1 && dz >= f.z0 && dz <= f.z1 && c >= 0 && c < g.cells) {
+                s = a.cellStart[c];
+                e = (lane == bestKey) ? bestSlot - 1 : a.cellEnd[c];
+                if (e >= s && !ray_box(w.cellBox[c], f.pos, f.dir)) e = s - 1;
+            }
+            const int g0 = s >> 3, ng = e >= s ? (e >> 3) - g0 + 1 : 0;
+            int incl = ng;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int G = __shfl_sync(0xffffffffu, incl, 31);
+            bool masked = false;
+            for (int fb = 0; fb < G && !masked; fb += 32) {
+                // flattened group index -> owning stencil cell (lane L with incl[L-1] <= fi < incl[L])
+                const int fi = fb + lane;
+                int L = 0;
+#pragma unroll
+                for (int l = 0; l < 27; ++l) L += __shfl_sync(0xffffffffu, incl, l) <= fi;
+                const int Ls = min(L, 26);
+                const int os = __shfl_sync(0xffffffffu, s, Ls), oe = __shfl_sync(0xffffffffu, e, Ls);
+                const int og0 = __shfl_sync(0xffffffffu, g0, Ls), oincl = __shfl_sync(0xffffffffu, incl, Ls), ong = __shfl_sync(0xffffffffu, ng, Ls);
+                const int gi = og0 + (fi - (oincl - ong));
+                const bool ok = fi < G && ray_box(w.groupBox[gi], f.pos, f.dir);
                 unsigned gm = __ballot_sync(0xffffffffu, ok);
                 while (gm && !masked) {
                     // four slot groups (32 triangles) per round
-                    int mine = -1;
+                    int from = -1;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int gsel = gm ? g0 + __ffs(gm) - 1 : -1;
+                        const int sel = gm ? __ffs(gm) - 1 : -1;
                         gm &= gm - 1;
-                        if ((lane >> 3) == r) mine = gsel;
+                        if ((lane >> 3) == r) from = sel;
                     }
+                    const int fromS = max(from, 0);
+                    const int mg = __shfl_sync(0xffffffffu, gi, fromS), ms = __shfl_sync(0xffffffffu, os, fromS), me = __shfl_sync(0xffffffffu, oe, fromS);
                     bool hitFar = false;
-                    if (mine >= 0) {
-                        const int slot = (mine << 3) + (lane & 7);
-                        if (slot >= s && slot <= e) {
+                    if (from >= 0) {
+                        const int slot = (mg << 3) + (lane & 7);
+                        if (slot >= ms && slot <= me) {
                             if (STATS) ++myTests;
                             RayHit far;
-                            hitFar = ray_triangle(pos, dir, load_tri(a, slot), far);
+                            hitFar = ray_triangle(f.pos, f.dir, load_tri(a, slot), far);
                         }
                     }
                     masked = __any_sync(0xffffffffu, hitFar);
                 }
             }
-        }
-        if (!masked && lane == 0) {
-            RayHit h;
-            ray_triangle(pos, dir, load_tri(a, bestSlot), h);
-            vein_apply_hit(a, pid, p4, v4, dir, h, splatOnly);
+            if (!masked && lane == 0) {
+                RayHit h;
+                ray_triangle(f.pos, f.dir, load_tri(a, bestSlot), h);
+                vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], f.dir, h, splatOnly);
+            }
         }
     }
     if (STATS) {
@@ -554,17 +586,14 @@ void launch_wall_collisions(const VeinCollideArgs& a0, cudaStream_t st)
     a.liveTris = 1;                 // nothing is repacked per step on this path
     a.cellBox = a.wall.cellBox;     // the sequential fallback (particles outside the triangle grid) culls with the lazy boxes
     a.groupBox = a.wall.groupBox;
-    BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, sizeof(int), st));
-    const int blocks = (a.n + PHASE_A_THREADS - 1) / PHASE_A_THREADS;
-    if (a.pflag) {
-        if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_phase_a_kernel<true, true><<<blocks, PHASE_A_THREADS, 0, st>>>(a));
-        else BCS_LAUNCH("vein_collisions", st, wall_phase_a_kernel<false, true><<<blocks, PHASE_A_THREADS, 0, st>>>(a));
-    } else {
-        if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_phase_a_kernel<true, false><<<blocks, PHASE_A_THREADS, 0, st>>>(a));
-        else BCS_LAUNCH("vein_collisions", st, wall_phase_a_kernel<false, false><<<blocks, PHASE_A_THREADS, 0, st>>>(a));
-    }
-    if (a.stats) BCS_LAUNCH("vein_masking", st, wall_phase_b_kernel<true><<<148 * 16, 128, 0, st>>>(a));
-    else BCS_LAUNCH("vein_masking", st, wall_phase_b_kernel<false><<<148 * 16, 128, 0, st>>>(a));
+    BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 2 * sizeof(int), st));   // queueCount, entryCount (adjacent)
+    const int blocks = (a.n + 255) / 256;
+    if (a.pflag) BCS_LAUNCH("vein_filter", st, wall_filter_kernel<true><<<blocks, 256, 0, st>>>(a));
+    else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<blocks, 256, 0, st>>>(a));
+    if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<true><<<148 * 8, 256, 0, st>>>(a));
+    else BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<false><<<148 * 8, 256, 0, st>>>(a));
+    if (a.stats) BCS_LAUNCH("vein_masking", st, wall_masking_kernel<true><<<148 * 8, 128, 0, st>>>(a));
+    else BCS_LAUNCH("vein_masking", st, wall_masking_kernel<false><<<148 * 8, 128, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
