@@ -418,7 +418,7 @@ void stage(bcs_sim* s, int st)
     case BCS_STAGE_VEIN_GATHER: launch_vein_gather(vein_args(s), s->stream); break;
     case BCS_STAGE_SPRINGS: {
         SpringArgs a{};
-        a.types = s->types; a.plan = s->plan; a.phys = s->phys;
+        a.types = s->types; a.typesDev = s->typesDev; a.plan = s->plan; a.phys = s->phys;
         a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
         a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
         if (s->slab) a.lists = slab_lists(s->slab, s->types);

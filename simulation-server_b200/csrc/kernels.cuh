@@ -59,10 +59,13 @@ struct SpringPlan {
     bool pairwise[BCS_MAX_TYPES];        // springs evaluated once per undirected spring (shared-memory exchange)
     int totalBlocks;
     int sharedBytes;                     // dynamic shared memory of the spring kernel
+    int sfCap;                           // entries of the parked spring-force array
+    int tableInts;                       // words of the per-type table area
 };
 SpringPlan make_spring_plan(const TypesDev& types);
 struct SpringArgs {
     TypesDev types;
+    const TypesDev* typesDev;   // device copy of `types`
     SpringPlan plan;
     PhysDev phys;
     const float4* pos;
