@@ -132,6 +132,10 @@ struct bcs_sim {
     int maxP = 1;
     bool exhaustiveVein = false;
     WallGridDev wall{};             // lazily rebuilt wall grid (clean semantics; wall.enabled = 0 otherwise)
+    // independent stages of a step run on forked streams (graph branches when captured): springs | wall search | vein gather
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evSprings = nullptr, evWall = nullptr, evGather = nullptr, evMasked = nullptr, evVein = nullptr;
+    bool overlap = true;
     int numSMs = 148;
     unsigned* vidx = nullptr;
     int* nbrIds = nullptr;
@@ -406,6 +410,8 @@ IntegrateArgs integrate_args(bcs_sim* s)
     return a;
 }
 
+SpringArgs spring_args(bcs_sim* s);
+
 void stage(bcs_sim* s, int st)
 {
     switch (st) {
@@ -417,12 +423,7 @@ void stage(bcs_sim* s, int st)
         break;   // static: built at creation from the initial centres
     case BCS_STAGE_VEIN_GATHER: launch_vein_gather(vein_args(s), s->stream); break;
     case BCS_STAGE_SPRINGS: {
-        SpringArgs a{};
-        a.types = s->types; a.typesDev = s->typesDev; a.plan = s->plan; a.phys = s->phys;
-        a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
-        a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
-        if (s->slab) a.lists = slab_lists(s->slab, s->types);
-        launch_springs(a, s->stream);
+        launch_springs(spring_args(s), s->stream);
         break;
     }
     case BCS_STAGE_PARTICLE_COLLISIONS:
@@ -460,14 +461,67 @@ SlabCtx slab_ctx(bcs_sim* s)
     return c;
 }
 
+SpringArgs spring_args(bcs_sim* s)
+{
+    SpringArgs a{};
+    a.types = s->types; a.typesDev = s->typesDev; a.plan = s->plan; a.phys = s->phys;
+    a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
+    a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
+    if (s->slab) a.lists = slab_lists(s->slab, s->types);
+    return a;
+}
+
 void enqueue_step(bcs_sim* s)
 {
     if (s->slab && !s->slab->primed) slab_prime(s->slab, slab_ctx(s));
-    // same stage order as the staged entry points; the tail (integrate particles, vein end, step counter) is one
-    // fused kernel, and the vein integrator - independent of it - follows
-    for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
-    launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, s->stream);
-    stage(s, BCS_STAGE_INTEGRATE_VEIN);
+    cudaStream_t m = s->stream;
+    const bool fork = s->overlap && !s->ctx.timing && s->side[0];
+    if (!fork) {
+        // same stage order as the staged entry points; the tail (integrate particles, vein end, step counter) is one
+        // fused kernel, and the vein integrator - independent of it - follows
+        for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
+        launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, m);
+        stage(s, BCS_STAGE_INTEGRATE_VEIN);
+    } else {
+        // Data flow of a step (reference order main.cu:175-208 + simulation_controller.cu:246-331, which serialises every
+        // stage with a device-wide sync):
+        //   grid build         reads pos, vel                    -> sorted copies, cell index
+        //   springs            reads pos, vel, frc               -> frc, centres                (independent of the grid)
+        //   vein gather        reads vpos, vvel                  -> vfrc                         (independent of particles)
+        //   wall search        reads pos, vel, vpos, wall grid   -> near-hit list               (independent of frc)
+        //   particle collisions need grid + springs; wall apply needs collisions + search + gather; the particle tail and
+        //   the vein integrator both need wall apply and are independent of each other.
+        VeinCollideArgs va = vein_collide_args(s);
+        const bool wall = va.wall.enabled != 0;
+        BCS_CUDA(cudaEventRecord(s->evFork, m));
+        for (int k = 0; k < 3; ++k) BCS_CUDA(cudaStreamWaitEvent(s->side[k], s->evFork, 0));
+        launch_springs(spring_args(s), s->side[0]);
+        BCS_CUDA(cudaEventRecord(s->evSprings, s->side[0]));
+        if (wall) {
+            launch_wall_rebuild(va, s->hs.V, s->numSMs, s->side[1]);
+            launch_wall_search(va, s->side[1]);
+        }
+        BCS_CUDA(cudaEventRecord(s->evWall, s->side[1]));
+        launch_vein_gather(vein_args(s), s->side[2]);
+        BCS_CUDA(cudaEventRecord(s->evGather, s->side[2]));
+        stage(s, BCS_STAGE_GRID_PARTICLES);
+        BCS_CUDA(cudaStreamWaitEvent(m, s->evSprings, 0));
+        stage(s, BCS_STAGE_PARTICLE_COLLISIONS);
+        BCS_CUDA(cudaStreamWaitEvent(m, s->evWall, 0));
+        BCS_CUDA(cudaStreamWaitEvent(m, s->evGather, 0));
+        if (wall) {
+            launch_wall_apply(va, m);
+        } else {
+            launch_tri_refit(va, m);
+            launch_vein_collisions(va, m);
+        }
+        BCS_CUDA(cudaEventRecord(s->evMasked, m));
+        BCS_CUDA(cudaStreamWaitEvent(s->side[2], s->evMasked, 0));
+        launch_vein_integrate(vein_args(s), s->side[2]);
+        BCS_CUDA(cudaEventRecord(s->evVein, s->side[2]));
+        launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, m);
+        BCS_CUDA(cudaStreamWaitEvent(m, s->evVein, 0));
+    }
     if (s->slab) slab_end_of_step(s->slab, slab_ctx(s));   // migration + halo exchange for the next step
 }
 
@@ -500,6 +554,8 @@ void destroy(bcs_sim* s)
     for (void* p : s->owned) cudaFree(p);
     s->sortP.release();
     s->sortT.release();
+    for (cudaStream_t q : s->side) if (q) cudaStreamDestroy(q);
+    for (cudaEvent_t e : {s->evFork, s->evSprings, s->evWall, s->evGather, s->evMasked, s->evVein}) if (e) cudaEventDestroy(e);
     if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -621,6 +677,12 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             BCS_CUDA(cudaStreamSynchronize(s->stream));
         }
         if (s->semantics == BCS_SEM_CLEAN && !getenv("BCS_NO_WALL_GRID")) setup_wall(s);
+        s->overlap = !getenv("BCS_NO_OVERLAP");
+        if (s->overlap) {
+            for (cudaStream_t& q : s->side) BCS_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            for (cudaEvent_t* e : {&s->evFork, &s->evSprings, &s->evWall, &s->evGather, &s->evMasked, &s->evVein})
+                BCS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
         if (slabOpts) {
             BCS_REQUIRE(slabOpts->struct_size == sizeof(bcs_slab_opts), BCS_ERR_INVALID, "bcs_slab_opts.struct_size mismatch");
             BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN, BCS_ERR_UNSUPPORTED, "slab decomposition needs clean semantics");

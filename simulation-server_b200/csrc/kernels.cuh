@@ -211,7 +211,9 @@ void launch_tri_refit(const VeinCollideArgs& a, cudaStream_t st);
 void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st);
 // wall.cu
 void launch_wall_rebuild(const VeinCollideArgs& a, int V, int numSMs, cudaStream_t st);   // returns at once unless wall.dirty
-void launch_wall_collisions(const VeinCollideArgs& a, cudaStream_t st);
+void launch_wall_collisions(const VeinCollideArgs& a, cudaStream_t st);   // = search + apply
+void launch_wall_search(const VeinCollideArgs& a, cudaStream_t st);
+void launch_wall_apply(const VeinCollideArgs& a, cudaStream_t st);
 void launch_wall_slot_info(const int* sortedTriKeys, const int* triIds, const unsigned* vidx, int T, GridDev tgrid, int4* slotInfo, int4* slotVerts,
                            cudaStream_t st);
 

@@ -239,14 +239,18 @@ springs_kernel(const TypesDev* __restrict__ typesDev, const SpringPlan plan, con
 
         mbar_wait(bars + s, (uint32_t)((it >> 1) & 1));
 
-        if (tid < gi.nCells) {
-            // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60)
-            float3 c = f3(0.f, 0.f, 0.f);
-            for (int k = 0; k < P; ++k) c = c + xyz(sp[tid * P + k]);
-            c = c / (float)P;
-            sc[tid] = make_float4(c.x, c.y, c.z, 0.f);
-            const int cellId = LISTS ? lists.cells[lists.typeFirst[gi.t] + gi.firstIdx + tid] : sTy.cStart + gi.firstIdx + tid;
-            centers[cellId] = make_float4(c.x, c.y, c.z, 0.f);
+        {
+            // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60): a serial sum, so the cells are dealt
+            // round-robin to the warps (lane 0 of warp 0 takes cell 0, lane 0 of warp 1 cell 1, ...)
+            const int myCell = (tid & 31) * (SPRING_THREADS / 32) + (tid >> 5);
+            if (myCell < gi.nCells) {
+                float3 c = f3(0.f, 0.f, 0.f);
+                for (int k = 0; k < P; ++k) c = c + xyz(sp[myCell * P + k]);
+                c = c / (float)P;
+                sc[myCell] = make_float4(c.x, c.y, c.z, 0.f);
+                const int cellId = LISTS ? lists.cells[lists.typeFirst[gi.t] + gi.firstIdx + myCell] : sTy.cStart + gi.firstIdx + myCell;
+                centers[cellId] = make_float4(c.x, c.y, c.z, 0.f);
+            }
         }
         if (pairwise) {
             // every undirected spring once; independent iterations, unrolled so that their latencies overlap

@@ -580,21 +580,43 @@ void launch_wall_rebuild(const VeinCollideArgs& a, int V, int numSMs, cudaStream
     BCS_CUDA(cudaGetLastError());
 }
 
-void launch_wall_collisions(const VeinCollideArgs& a0, cudaStream_t st)
+static VeinCollideArgs wall_args(const VeinCollideArgs& a0)
 {
     VeinCollideArgs a = a0;
     a.liveTris = 1;                 // nothing is repacked per step on this path
     a.cellBox = a.wall.cellBox;     // the sequential fallback (particles outside the triangle grid) culls with the lazy boxes
     a.groupBox = a.wall.groupBox;
+    return a;
+}
+
+// phase A (filter + triangle tests): reads particle positions / velocities and the wall only - may run beside the
+// spring and particle-collision kernels
+void launch_wall_search(const VeinCollideArgs& a0, cudaStream_t st)
+{
+    const VeinCollideArgs a = wall_args(a0);
     BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 2 * sizeof(int), st));   // queueCount, entryCount (adjacent)
     const int blocks = (a.n + 255) / 256;
     if (a.pflag) BCS_LAUNCH("vein_filter", st, wall_filter_kernel<true><<<blocks, 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<blocks, 256, 0, st>>>(a));
     if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<true><<<148 * 8, 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<false><<<148 * 8, 256, 0, st>>>(a));
+    BCS_CUDA(cudaGetLastError());
+}
+
+// phase B (masking check + the stage's effect on particle force / velocity and the wall-force splats): after the
+// particle collisions (it reads the accumulated force) and the vein spring gather (both add to the vertex forces)
+void launch_wall_apply(const VeinCollideArgs& a0, cudaStream_t st)
+{
+    const VeinCollideArgs a = wall_args(a0);
     if (a.stats) BCS_LAUNCH("vein_masking", st, wall_masking_kernel<true><<<148 * 8, 128, 0, st>>>(a));
     else BCS_LAUNCH("vein_masking", st, wall_masking_kernel<false><<<148 * 8, 128, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
+}
+
+void launch_wall_collisions(const VeinCollideArgs& a, cudaStream_t st)
+{
+    launch_wall_search(a, st);
+    launch_wall_apply(a, st);
 }
 
 }  // namespace bcs

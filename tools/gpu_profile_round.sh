@@ -5,7 +5,7 @@ set -uo pipefail
 TAG=${1:-r01p}
 O=gpurun_out/$TAG; mkdir -p $O
 bash tools/gpu_round.sh $TAG
-for K in springs_kernel particle_collisions_kernel vein_collisions_coop_kernel finalize_compact_kernel; do
+for K in ${KERNELS:-springs_kernel particle_collisions_kernel wall_filter_kernel}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 6 -c 1 -f -o $O/full_$K \
      python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_full_$K.log 2>&1
   tail -1 $O/ncu_full_$K.log | cut -c1-200

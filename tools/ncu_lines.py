@@ -4,7 +4,7 @@ usage: ncu_lines.py report.ncu-rep [top_n]   -> lines ranked by stall samples, w
 import csv, io, subprocess, sys
 
 rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur, hdr = None, None
@@ -25,11 +25,12 @@ for r in rows:
             pass
 tot_s = sum(i[0] for i in items); tot_i = sum(i[1] for i in items)
 print(f"total samples {tot_s}  total warp instructions {tot_i}")
+by_ins = "--by-instructions" in sys.argv
 agg = {}
 for it in items:
     for k, v in it[5].items():
         agg[k] = agg.get(k, 0) + v
 print("stalls:", ", ".join(f"{k[6:]} {v/max(tot_s,1):.1%}" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
-for s, i, f, ln, src, stall in sorted(items, reverse=True)[:top]:
+for s, i, f, ln, src, stall in sorted(items, key=(lambda x: (x[1], x[0])) if by_ins else None, reverse=True)[:top]:
     st = ",".join(f"{k[6:]}:{v}" for k, v in sorted(stall.items(), key=lambda kv: -kv[1])[:3])
     print(f"{s/max(tot_s,1):6.1%} smp {i/max(tot_i,1):6.1%} ins  {f}:{ln:>4s}  {src}   [{st}]")
