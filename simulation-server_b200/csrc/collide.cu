@@ -113,34 +113,45 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                 }
             }
         } else {
-            // pass 1 (branch-free, all lanes alike): occupancy bits of the 9 stencil rows.  A row is the <= 3
-            // x-adjacent cells [row+x0, row+x1]: adjacent cell ids, i.e. adjacent bits of the occupancy mask.
+            // The 9 stencil rows are resolved level by level, branch-free and all lanes alike, so that the dependent loads
+            // of ALL rows are in flight together (a row-after-row walk chains 3 L2 round trips per non-empty row):
+            //   level 1  occupancy bits.  A row is the <= 3 x-adjacent cells [row+x0, row+x1]: adjacent cell ids, i.e.
+            //            adjacent bits of the occupancy mask (two words, funnel-shifted)
+            //   level 2  rank of the row's first occupied cell = cellRank[word] + popc(bits below it)
+            //   level 3  occupied cells of a row have consecutive ranks and ONE contiguous slot range
+            //            [occStart[rank], occStart[rank + popc(bits)])
+            //   level 4  the candidates
             const int nb = x1 - x0 + 1;
             const unsigned nbm = (1u << nb) - 1u;
-            unsigned occ = 0;   // 3 bits per row, row r = (dz+1)*3 + (dy+1)
+            int first[9];      // first occupied cell of the row (or -1)
+            unsigned below[9]; // occupancy bits below it inside its mask word
+            int nocc[9];
 #pragma unroll
             for (int r = 0; r < 9; ++r) {
                 const int dz = r / 3 - 1, dy = r % 3 - 1;
                 const int c0 = cell + dz * plane + dy * g.nx + x0;
                 const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
-                unsigned bits = 0;
-                if (in) {
-                    const int w0 = c0 >> 5;
-                    bits = __funnelshift_r(__ldg(a.cellMask + w0), __ldg(a.cellMask + w0 + 1), c0 & 31) & nbm;
-                }
-                occ |= bits << (3 * r);
+                const int w0 = in ? c0 >> 5 : 0;
+                const unsigned lo = __ldg(a.cellMask + w0), hi = __ldg(a.cellMask + w0 + 1);
+                const unsigned bits = in ? __funnelshift_r(lo, hi, c0 & 31) & nbm : 0u;
+                const int f = c0 + __ffs(bits) - 1;
+                first[r] = bits ? f : -1;
+                nocc[r] = __popc(bits);
+                below[r] = ((f >> 5) == w0 ? lo : hi) & ((1u << (f & 31)) - 1u);
             }
-            // pass 2: only the non-empty rows.  Occupied cells of a row have consecutive ranks and ONE contiguous
-            // slot range [occStart[rank(first)], occStart[rank(first) + popc(bits)]).
-            while (occ) {
-                const int r = (__ffs(occ) - 1) / 3;
-                const unsigned bits = (occ >> (3 * r)) & 7u;
-                occ &= ~(7u << (3 * r));
-                const int first = cell + (r / 3 - 1) * plane + (r % 3 - 1) * g.nx + x0 + __ffs(bits) - 1;
-                const int fw = first >> 5;
-                const int rank = __ldg(a.cellRank + fw) + __popc(__ldg(a.cellMask + fw) & ((1u << (first & 31)) - 1u));
-                const int lo = __ldg(a.occStart + rank), hi = __ldg(a.occStart + rank + __popc(bits)) - 1;
-                for (int j = lo; j <= hi; ++j) {
+            int rank[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) rank[r] = __ldg(a.cellRank + (first[r] >= 0 ? first[r] >> 5 : 0)) + __popc(below[r]);
+            int lo[9], hi[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const int rk = first[r] >= 0 ? rank[r] : 0;
+                lo[r] = __ldg(a.occStart + rk);
+                hi[r] = first[r] >= 0 ? __ldg(a.occStart + rk + nocc[r]) : lo[r];
+            }
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                for (int j = lo[r]; j < hi[r]; ++j) {
                     if (j == slot) continue;
                     const float4 q4 = a.spos[j];
                     if (DEBUG) {
