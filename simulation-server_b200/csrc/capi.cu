@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <string>
 
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
@@ -392,6 +393,18 @@ CollideArgs collide_args(bcs_sim* s)
     a.keys = s->keys[1]; a.spos = s->spos; a.svel = s->svel;
     a.cellStart = s->cellStart; a.cellEnd = s->cellEnd; a.collR = s->collR;
     a.cellMask = s->cellMask; a.cellRank = s->cellRank; a.occStart = s->occStart;
+    // BCS_COLLIDE=tiled: shared-memory staged variant (collide.cu).  Measured slower than the index walk at the bench's
+    // ~1 particle per occupied cell (112 vs 70 us at 1 M particles), so it is opt-in.
+    {
+        const char* mode = getenv("BCS_COLLIDE");
+        a.tiled = mode && std::string(mode) == "tiled" && !s->sortP.radixForCompact;
+    }
+    {
+        int l = 0;
+        while ((1ll << l) < s->pg.nx) ++l;
+        a.nxShift = 32 + l;
+        a.nxMagic = ((1ull << a.nxShift) + (unsigned long long)s->pg.nx - 1ull) / (unsigned long long)s->pg.nx;
+    }
     a.frc = s->frc; a.counters = s->counters;
     a.reference = s->semantics == BCS_SEM_REFERENCE; a.stats = s->stats;
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;

@@ -53,6 +53,233 @@ __device__ __forceinline__ void test_pair(const PhysDev& ph, const float3 p1, co
     }
 }
 
+
+// clean-semantics walk of one sorted slot through the compact cell index (global memory); see the tiled kernel below
+// for the production path
+template <bool DEBUG, bool STATS>
+__device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, const float3 p1, const float3 v1, const float r1, int cell, int x0,
+                                                int x1, int y0, int y1, int z0, int z1, PairAccum& acc, int& cnt, unsigned long long& sum,
+                                                unsigned long long& myTests)
+{
+    const GridDev& g = a.grid;
+    const int plane = g.nx * g.ny;
+    // The 9 stencil rows are resolved level by level, branch-free and all lanes alike, so that the dependent loads
+    // of ALL rows are in flight together (a row-after-row walk chains 3 L2 round trips per non-empty row):
+    //   level 1  occupancy bits.  A row is the <= 3 x-adjacent cells [row+x0, row+x1]: adjacent cell ids, i.e.
+    //            adjacent bits of the occupancy mask (two words, funnel-shifted)
+    //   level 2  rank of the row's first occupied cell = cellRank[word] + popc(bits below it)
+    //   level 3  occupied cells of a row have consecutive ranks and ONE contiguous slot range
+    //            [occStart[rank], occStart[rank + popc(bits)])
+    //   level 4  the candidates
+    const int nb = x1 - x0 + 1;
+    const unsigned nbm = (1u << nb) - 1u;
+    int first[9];      // first occupied cell of the row (or -1)
+    unsigned below[9]; // occupancy bits below it inside its mask word
+    int nocc[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int dz = r / 3 - 1, dy = r % 3 - 1;
+        const int c0 = cell + dz * plane + dy * g.nx + x0;
+        const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
+        const int w0 = in ? c0 >> 5 : 0;
+        const unsigned lo = __ldg(a.cellMask + w0), hi = __ldg(a.cellMask + w0 + 1);
+        const unsigned bits = in ? __funnelshift_r(lo, hi, c0 & 31) & nbm : 0u;
+        const int f = c0 + __ffs(bits) - 1;
+        first[r] = bits ? f : -1;
+        nocc[r] = __popc(bits);
+        below[r] = ((f >> 5) == w0 ? lo : hi) & ((1u << (f & 31)) - 1u);
+    }
+    int rank[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) rank[r] = __ldg(a.cellRank + (first[r] >= 0 ? first[r] >> 5 : 0)) + __popc(below[r]);
+    int lo[9], hi[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const int rk = first[r] >= 0 ? rank[r] : 0;
+        lo[r] = __ldg(a.occStart + rk);
+        hi[r] = first[r] >= 0 ? __ldg(a.occStart + rk + nocc[r]) : lo[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        for (int j = lo[r]; j < hi[r]; ++j) {
+            if (j == slot) continue;
+            const float4 q4 = a.spos[j];
+            if (DEBUG) {
+                const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
+                ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
+            }
+            test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);
+            if (STATS) ++myTests;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Clean semantics, production path: the neighbour runs are STAGED IN SHARED MEMORY per tile of sorted slots.
+//
+// Cell ids are z-major (uniform_grid.cu:33-35), so a tile of 256 consecutive sorted slots covers a run of x-rows
+// (y,z) of one z-layer, and everything its particles can collide with lies in THREE contiguous slot windows - the
+// rows [first-1, last+1] of the layers z-1, z, z+1.  The CTA finds the six window bounds through the compact cell
+// index (six lookups instead of ~36 per particle), copies the three windows (positions + keys, coalesced) into
+// shared memory and builds a row-start table there.  After that a particle resolves its 9 stencil rows with two
+// shared-memory reads each and scans only shared memory: all lanes run the same short loops, where the per-thread
+// walk through the global index ran with 13 of 32 lanes active and ~4 dependent L2 round trips per row.
+// Candidate sets (checked in debug mode against the reference's), hits and forces are identical to the cell-index
+// walk; a tile whose windows or row span exceed the shared-memory capacity (layer ends, pathological clustering)
+// takes that walk instead.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TILE = 256;        // sorted slots per CTA
+constexpr int WCAP = 512;        // window capacity (slots)
+constexpr int RCAP = 256;        // window capacity (x-rows)
+
+__device__ __forceinline__ int fast_div(unsigned n, unsigned long long magic, int shift)
+{
+    return (int)(((unsigned long long)n * magic) >> shift);   // exact for n < 2^31 (magic = ceil(2^shift / d), shift = 32 + ceil(log2 d))
+}
+
+// first sorted slot whose key is >= K, through the compact cell index (cellRank is a full exclusive prefix in the
+// counting-sort grid build)
+__device__ __forceinline__ int first_slot_at_or_after(const CollideArgs& a, int K, int n)
+{
+    if (K >= a.grid.cells) return n;
+    if (K < 0) K = 0;
+    const int w = K >> 5;
+    const int rank = __ldg(a.cellRank + w) + __popc(__ldg(a.cellMask + w) & ((1u << (K & 31)) - 1u));
+    return __ldg(a.occStart + rank);
+}
+
+template <bool DEBUG, bool STATS>
+__global__ void __launch_bounds__(TILE) particle_collisions_tiled_kernel(const CollideArgs a)
+{
+    __shared__ float4 wpos[3][WCAP];
+    __shared__ int wkey[3][WCAP];
+    __shared__ unsigned short wrow[3][RCAP + 2];
+    __shared__ int wlo[3], wcnt[3], wrowBase[3], wrows[3];
+    __shared__ int sFallback;
+
+    const GridDev& g = a.grid;
+    const int tid = threadIdx.x;
+    const int n = a.nDev ? *a.nDev : a.n;
+    const int tileFirst = blockIdx.x * TILE;
+    if (tileFirst >= n) return;
+    const int tileLast = min(n, tileFirst + TILE) - 1;
+    const int nRows = g.ny * g.nz;
+
+    if (tid == 0) sFallback = 0;
+    if (tid < 3) {
+        const int dz = tid - 1;
+        const int rowF = fast_div((unsigned)a.keys[tileFirst], a.nxMagic, a.nxShift), rowL = fast_div((unsigned)a.keys[tileLast], a.nxMagic, a.nxShift);
+        const int rLo = max(0, min(nRows - 1, rowF + dz * g.ny - 1)), rHi = max(0, min(nRows - 1, rowL + dz * g.ny + 1));
+        const int lo = first_slot_at_or_after(a, rLo * g.nx, n);
+        const int hi = rHi + 1 >= nRows ? n : first_slot_at_or_after(a, (rHi + 1) * g.nx, n);
+        wlo[tid] = lo; wcnt[tid] = max(0, hi - lo); wrowBase[tid] = rLo; wrows[tid] = rHi - rLo + 1;
+    }
+    __syncthreads();
+    if (tid < 3 && (wcnt[tid] > WCAP || wrows[tid] > RCAP)) sFallback = 1;
+    __syncthreads();
+    const bool fallback = sFallback != 0;
+
+    if (!fallback) {
+        // stage the three windows and clear their row tables
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int lo = wlo[w], cnt = wcnt[w];
+            for (int j = tid; j < cnt; j += TILE) {
+                wpos[w][j] = a.spos[lo + j];
+                wkey[w][j] = a.keys[lo + j];
+            }
+        }
+        __syncthreads();
+        // row-start table: window slot j opens every row in (row(j-1), row(j)]; the tail rows end at cnt
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int cnt = wcnt[w], base = wrowBase[w], rows = wrows[w];
+            for (int j = tid; j <= cnt; j += TILE) {
+                const int rPrev = j == 0 ? -1 : fast_div((unsigned)wkey[w][j - 1], a.nxMagic, a.nxShift) - base;
+                const int rThis = j == cnt ? rows : fast_div((unsigned)wkey[w][j], a.nxMagic, a.nxShift) - base;
+                for (int q = rPrev + 1; q <= min(rThis, rows); ++q) wrow[w][q] = (unsigned short)j;
+            }
+        }
+        __syncthreads();
+    }
+
+    const int slot = tileFirst + tid;
+    unsigned long long myTests = 0;
+    int myHits = 0;
+    if (slot < n && __float_as_int(a.svel[slot].w) >= 0) {
+        const float4 p4 = a.spos[slot];
+        const float4 v4 = a.svel[slot];
+        const int pid = __float_as_int(v4.w) & 0x7fffffff;
+        const float3 p1 = xyz(p4), v1 = xyz(v4);
+        const float r1 = p4.w;
+        const int cell = a.keys[slot];
+        int x0, x1, y0, y1, z0, z1;
+        stencil_range(axis_cell_raw(p1.x, g.minx, g.csx), g.nx, x0, x1);
+        stencil_range(axis_cell_raw(p1.y, g.miny, g.csy), g.ny, y0, y1);
+        stencil_range(axis_cell_raw(p1.z, g.minz, g.csz), g.nz, z0, z1);
+        PairAccum acc{f3(0.f, 0.f, 0.f), 0};
+        int cnt = 0;
+        unsigned long long sum = 0;
+        if (fallback) {
+            clean_slot_walk<DEBUG, STATS>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests);
+        } else {
+            const int row0 = fast_div((unsigned)cell, a.nxMagic, a.nxShift);
+            const int own = slot - wlo[1];
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int dz = w - 1;
+                if (dz < z0 || dz > z1) continue;
+                const int base = wrowBase[w], rows = wrows[w], glo = wlo[w];
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    if (dy < y0 || dy > y1) continue;
+                    const int row = row0 + dz * g.ny + dy, r = row - base;
+                    if (r < 0 || r >= rows) continue;   // beyond the grid: no such cells
+                    const int e = wrow[w][r + 1];
+                    const int kLo = cell + (dz * g.ny + dy) * g.nx + x0, kHi = kLo + (x1 - x0);
+                    // first slot of the row inside the x window (a row holds up to a chord of cells: binary search)
+                    int s = wrow[w][r], hi = e;
+                    while (s < hi) {
+                        const int mid = (s + hi) >> 1;
+                        if (wkey[w][mid] < kLo) s = mid + 1; else hi = mid;
+                    }
+                    for (int j = s; j < e; ++j) {
+                        if (wkey[w][j] > kHi) break;
+                        if (w == 1 && j == own) continue;
+                        const float4 q4 = wpos[w][j];
+                        if (DEBUG) {
+                            const int qid = __float_as_int(a.svel[glo + j].w) & 0x7fffffff;
+                            ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
+                        }
+                        test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, glo + j, acc);
+                        if (STATS) ++myTests;
+                    }
+                }
+            }
+        }
+        if (DEBUG) {
+            a.dbgCount[pid] = cnt;
+            a.dbgSum[pid] = sum;
+            a.dbgHits[pid] = acc.hits;
+        } else if (acc.hits) {
+            float4 f = a.frc[pid];
+            f.x += acc.F.x; f.y += acc.F.y; f.z += acc.F.z;
+            a.frc[pid] = f;
+        }
+        myHits = acc.hits;
+    }
+    if (STATS && !DEBUG) {
+        for (int o = 16; o; o >>= 1) {
+            myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
+            myHits += __shfl_xor_sync(0xffffffffu, myHits, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&a.counters->pairTests, myTests);
+            atomicAdd(&a.counters->pairHits, (unsigned long long)myHits);
+        }
+    }
+}
+
 template <bool REFERENCE, bool DEBUG, bool STATS>
 __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideArgs a)
 {
@@ -113,55 +340,7 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                 }
             }
         } else {
-            // The 9 stencil rows are resolved level by level, branch-free and all lanes alike, so that the dependent loads
-            // of ALL rows are in flight together (a row-after-row walk chains 3 L2 round trips per non-empty row):
-            //   level 1  occupancy bits.  A row is the <= 3 x-adjacent cells [row+x0, row+x1]: adjacent cell ids, i.e.
-            //            adjacent bits of the occupancy mask (two words, funnel-shifted)
-            //   level 2  rank of the row's first occupied cell = cellRank[word] + popc(bits below it)
-            //   level 3  occupied cells of a row have consecutive ranks and ONE contiguous slot range
-            //            [occStart[rank], occStart[rank + popc(bits)])
-            //   level 4  the candidates
-            const int nb = x1 - x0 + 1;
-            const unsigned nbm = (1u << nb) - 1u;
-            int first[9];      // first occupied cell of the row (or -1)
-            unsigned below[9]; // occupancy bits below it inside its mask word
-            int nocc[9];
-#pragma unroll
-            for (int r = 0; r < 9; ++r) {
-                const int dz = r / 3 - 1, dy = r % 3 - 1;
-                const int c0 = cell + dz * plane + dy * g.nx + x0;
-                const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
-                const int w0 = in ? c0 >> 5 : 0;
-                const unsigned lo = __ldg(a.cellMask + w0), hi = __ldg(a.cellMask + w0 + 1);
-                const unsigned bits = in ? __funnelshift_r(lo, hi, c0 & 31) & nbm : 0u;
-                const int f = c0 + __ffs(bits) - 1;
-                first[r] = bits ? f : -1;
-                nocc[r] = __popc(bits);
-                below[r] = ((f >> 5) == w0 ? lo : hi) & ((1u << (f & 31)) - 1u);
-            }
-            int rank[9];
-#pragma unroll
-            for (int r = 0; r < 9; ++r) rank[r] = __ldg(a.cellRank + (first[r] >= 0 ? first[r] >> 5 : 0)) + __popc(below[r]);
-            int lo[9], hi[9];
-#pragma unroll
-            for (int r = 0; r < 9; ++r) {
-                const int rk = first[r] >= 0 ? rank[r] : 0;
-                lo[r] = __ldg(a.occStart + rk);
-                hi[r] = first[r] >= 0 ? __ldg(a.occStart + rk + nocc[r]) : lo[r];
-            }
-#pragma unroll
-            for (int r = 0; r < 9; ++r) {
-                for (int j = lo[r]; j < hi[r]; ++j) {
-                    if (j == slot) continue;
-                    const float4 q4 = a.spos[j];
-                    if (DEBUG) {
-                        const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
-                        ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
-                    }
-                    test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);
-                    if (STATS) ++myTests;
-                }
-            }
+            clean_slot_walk<DEBUG, STATS>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests);
         }
         if (DEBUG) {
             a.dbgCount[pid] = cnt;
@@ -191,7 +370,12 @@ void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
 {
     const int threads = 128, blocks = (a.n + threads - 1) / threads;
     const bool dbg = a.dbgCount != nullptr;
-    if (a.reference) {
+    if (!a.reference && a.tiled) {
+        const int tiles = (a.n + TILE - 1) / TILE;
+        if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_tiled_kernel<true, false><<<tiles, TILE, 0, st>>>(a));
+        else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_tiled_kernel<false, true><<<tiles, TILE, 0, st>>>(a));
+        else BCS_LAUNCH("particle_collisions", st, particle_collisions_tiled_kernel<false, false><<<tiles, TILE, 0, st>>>(a));
+    } else if (a.reference) {
         if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, true, false><<<blocks, threads, 0, st>>>(a));
         else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, true><<<blocks, threads, 0, st>>>(a));
         else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, false><<<blocks, threads, 0, st>>>(a));

@@ -97,6 +97,9 @@ struct CollideArgs {
     const unsigned* cellMask;   // compact cell index (clean semantics), see grid.cu
     const int* cellRank;
     const int* occStart;
+    bool tiled;                 // shared-memory tiled kernel (needs the counting-sort grid: cellRank is a full prefix there)
+    unsigned long long nxMagic; // exact division by grid.nx: q = (n * nxMagic) >> nxShift
+    int nxShift;
     const float* collR;         // [nModel] (reference-mode lookup)
     float4* frc;
     Counters* counters;
