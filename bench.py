@@ -120,6 +120,16 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
     return table.get(kernel, 0)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels captured with `ncu --set full`
+    on this workload; profiles/traffic.json is written by tools/ncu_traffic.py from the committed captures."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -201,9 +211,11 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sc, st, info = workloads.long_vein(args.particles)
+    # slab decomposition along the vein axis.  Default: STRONG scaling, the same 1 M-particle scene split over the ranks
+    # (BASELINE.json's metric); --scaling weak keeps 1 M particles PER RANK (a vein N times as long, same density)
+    n_particles = args.particles * (world if args.scaling == "weak" else 1)
+    sc, st, info = workloads.long_vein(n_particles)
     if world > 1:
-        # slab decomposition along the vein axis: STRONG scaling, the same 1 M-particle scene split over the ranks
         planes = dd.slab_boundaries(sc, st, world)
         sim = dd.create_slab_sim(sc, st, rank, world, local_rank, dd.broadcast_unique_id(rank), planes)
     else:
@@ -252,13 +264,16 @@ def run_product(args):
                for k, v in prof.items()}
     dominant = max(prof, key=lambda k: prof[k][0])
     peak, peak_src = measured_peaks()
+    traffic = ncu_traffic()
 
     def roof(name):
         per_launch_ms = prof[name][0] / prof[name][1]
         b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits)
         gbs = b / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        t = traffic.get(name) if world == 1 else None   # captured at N=1 on this workload
         return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms, "peak_source": peak_src}
+                "traffic": t["bytes"] if t else None, "traffic_source": t["source"] if t else None,
+                "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms, "peak_source": peak_src}
 
     roofline = roof(dominant)
     roofline["contract_kernels"] = {k: roof(k) for k in ("springs", "particle_collisions") if k in prof}
@@ -305,12 +320,12 @@ def run_product(args):
     if world > 1:
         config["parallelism"] = f"y-slab decomposition over {world} ranks, NCCL halo exchange + blood-cell migration (one grouped send/recv per neighbour and step)"
         config["rank0_slab"] = slab_info
-    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step" if world == 1 else "plain launches + NCCL p2p per step",
+    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step (springs / wall search / vein gather on forked branches)" if world == 1 else "CUDA graph replay, 1 graph per step, NCCL send/recv captured in the graph",
                    "l2": f"no flush: per-step working set ~{ws_mb:.0f} MB exceeds the 126 MB L2 (inputs larger than L2)",
                    "occupied_grid_cells": c_occ, "grid_cells": int(sim.layout.grid_cells)})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
     }
@@ -331,6 +346,8 @@ def main():
     ap.add_argument("--impl", default="bcs", choices=["bcs", "reference"])
     ap.add_argument("--reference-sample", type=int, default=100_000, help="particles in the CPU-timed sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the --particles scene split over the ranks (default, BASELINE metric); weak = --particles per rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -257,6 +257,11 @@ int bcs_step(bcs_sim* sim, int32_t nsteps);
 int bcs_synchronize(bcs_sim* sim);
 /* number of completed steps (drives the respawn RNG counter) */
 int bcs_get_step_count(const bcs_sim* sim, int64_t* out);
+/* Checkpoint / restart (the reference has none): the complete dynamic state of a simulation is the six
+ * state arrays (bcs_download / bcs_upload) plus the step count - the respawn RNG is counter based, keyed by
+ * (seed, blood cell, step), so restoring the count restores the random stream.  In slab mode upload the merged global
+ * state on every rank: ownership is re-derived from the positions. */
+int bcs_set_step_count(bcs_sim* sim, int64_t steps);
 
 /* Single stages, in the reference's order, for stage-by-stage parity tests. */
 typedef enum bcs_stage {

@@ -900,6 +900,7 @@ int orc_step(orc_sim* s, int32_t nsteps)
 }
 int orc_synchronize(orc_sim*) { return BCS_OK; }
 int orc_get_step_count(const orc_sim* s, int64_t* out) { *out = s->stepCount; return BCS_OK; }
+int orc_set_step_count(orc_sim* s, int64_t steps) { s->stepCount = steps; return BCS_OK; }
 
 int orc_download_grid(orc_sim* s, int which, int32_t* keys, int32_t* ids, int32_t n)
 {

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, Optional, Tuple
+from typing import Mapping, Dict, Optional, Tuple
 
 import numpy as np
 
@@ -290,6 +290,28 @@ class Sim:
         v = C.c_int64()
         self._call("get_step_count", self._h, C.byref(v))
         return v.value
+
+    def set_step_count(self, steps: int):
+        self._call("set_step_count", self._h, C.c_int64(steps))
+
+    # -- checkpoint / restart: the six state arrays + the step count are the whole dynamic state
+    _CHECKPOINT_ARRAYS = (("pos", PARTICLE_POS), ("vel", PARTICLE_VEL), ("frc", PARTICLE_FRC),
+                          ("vein_pos", VEIN_POS), ("vein_vel", VEIN_VEL), ("vein_frc", VEIN_FRC))
+
+    def checkpoint(self) -> Dict[str, np.ndarray]:
+        """Snapshot of the dynamic state as a dict of float32 arrays (+ 'step'); write it with bcsd.write()."""
+        out: Dict[str, np.ndarray] = {}
+        for name, which in self._CHECKPOINT_ARRAYS:
+            x, y, z = self.download(which)
+            out[name + "_x"], out[name + "_y"], out[name + "_z"] = x, y, z
+        out["step"] = np.array([self.step_count()], dtype=np.int64)
+        return out
+
+    def restore(self, ck: Mapping[str, np.ndarray]):
+        """Inverse of checkpoint(): the run continues bit-identically (the respawn RNG is keyed by the step count)."""
+        for name, which in self._CHECKPOINT_ARRAYS:
+            self.upload(which, ck[name + "_x"], ck[name + "_y"], ck[name + "_z"])
+        self.set_step_count(int(np.asarray(ck["step"]).ravel()[0]))
 
     # -- inspection
     def table(self, which: int) -> np.ndarray:

@@ -1048,6 +1048,17 @@ int bcs_get_step_count(const bcs_sim* s, int64_t* out)
     BCS_API_END
 }
 
+int bcs_set_step_count(bcs_sim* s, int64_t steps)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s && steps >= 0, BCS_ERR_INVALID, "bad argument");
+    BCS_CUDA(cudaSetDevice(s->device));
+    const unsigned long long v = (unsigned long long)steps;
+    BCS_CUDA(cudaMemcpyAsync(&s->counters->step, &v, sizeof v, cudaMemcpyHostToDevice, s->stream));
+    BCS_CUDA(cudaStreamSynchronize(s->stream));
+    BCS_API_END
+}
+
 int bcs_get_stats(bcs_sim* s, bcs_stats* o)
 {
     BCS_API_BEGIN
