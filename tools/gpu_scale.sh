@@ -10,3 +10,8 @@ fi
 timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+20)) bench.py --gpus $N --steps 100 --warmup 10 > $O/bench_g$N.log 2>&1
 grep "^{" $O/bench_g$N.log > $O/bench_g$N.json; grep -i "error\|Traceback" $O/bench_g$N.log | head -5
 python tools/show_bench.py $O/bench_g$N.json | head -30
+if [ "${WEAK:-0}" = 1 ]; then
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((PORT+40)) bench.py --gpus $N --steps 100 --warmup 10 --scaling weak > $O/bench_weak_g$N.log 2>&1
+grep "^{" $O/bench_weak_g$N.log > $O/bench_weak_g$N.json; grep -i "error\|Traceback" $O/bench_weak_g$N.log | head -5
+python tools/show_bench.py $O/bench_weak_g$N.json 2>/dev/null | head -30
+fi
