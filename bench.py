@@ -50,9 +50,15 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi needs a moment to start (longer on an 8-GPU box): wait for its first line, so that the samples
+            # that follow fall into the warm-up / timed region
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 4.0:
+                time.sleep(0.02)
+            self.first = len(self.rows)
         except OSError:
             self.proc = None
         return self
@@ -63,12 +69,14 @@ class ClockSampler:
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.03)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            if len(self.rows) > getattr(self, "first", 0):
+                self.rows = self.rows[self.first:]   # drop the idle sample(s) taken before the region started
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -226,11 +234,11 @@ def run_product(args):
     stream = torch.cuda.ExternalStream(view.stream, device=local_rank)
 
     # ---- device-resident throughput: W warm-up steps, then exactly K steps between two events (max over ranks)
-    sim.step(args.warmup)
-    sim.synchronize()
-    launches0 = sim.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:   # samples from the warm-up on: clocks under load around the timed region
+        sim.step(args.warmup)
+        sim.synchronize()
+        launches0 = sim.launch_count()
         barrier()
         torch.cuda.synchronize()
         start.record(stream)

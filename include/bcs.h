@@ -238,6 +238,16 @@ typedef struct bcs_device_view {
 int bcs_device_ptrs(bcs_sim* sim, bcs_device_view* out);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers without a CUDA runtime binding. */
+/* Headless frame export into the interleaved layouts the reference's renderer fills from the physics
+ * state (graphics/glcontroller.cu:23-50: calculatePositionsKernel, calculateTriangleVerticesKernel): DEVICE pointers,
+ * e.g. mapped GL buffers; any of them may be null.
+ *   cell_vertices6  [6 * n_particles] xyz of particle i at [6 i .. 6 i + 2] (floats 3..5 - the normals - are left alone);
+ *                   a per-type VBO of the reference is this buffer offset by 6 * particle_start of the type
+ *   offsets3        [3 * n_particles] xyz of particle i at [3 i ..]
+ *   vein_vertices6  [6 * n_vertices]  xyz of vein vertex v at [6 v .. 6 v + 2]
+ * Asynchronous on the simulation's stream (bcs_device_ptrs().stream). */
+int bcs_export_frame(bcs_sim* sim, float* cell_vertices6, float* offsets3, float* vein_vertices6);
+
 int bcs_host_alloc(void** out, size_t bytes);
 int bcs_host_free(void* p);
 

@@ -294,6 +294,10 @@ class Sim:
     def set_step_count(self, steps: int):
         self._call("set_step_count", self._h, C.c_int64(steps))
 
+    def export_frame(self, cell_vertices6: int = 0, offsets3: int = 0, vein_vertices6: int = 0):
+        """Device pointers (ints, e.g. torch tensor .data_ptr() or mapped GL buffers) of the renderer's interleaved buffers."""
+        self._call("export_frame", self._h, C.c_void_p(cell_vertices6 or None), C.c_void_p(offsets3 or None), C.c_void_p(vein_vertices6 or None))
+
     # -- checkpoint / restart (SURVEY.md 8(f).2): the six state arrays + the step count are the whole dynamic state
     _CHECKPOINT_ARRAYS = (("pos", PARTICLE_POS), ("vel", PARTICLE_VEL), ("frc", PARTICLE_FRC),
                           ("vein_pos", VEIN_POS), ("vein_vel", VEIN_VEL), ("vein_frc", VEIN_FRC))

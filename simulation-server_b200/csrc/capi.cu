@@ -89,6 +89,16 @@ __global__ void __launch_bounds__(256) unpack_kernel(const float4* __restrict__ 
     const float4 v = in[i];
     x[i] = v.x; y[i] = v.y; z[i] = v.z;
 }
+// graphics/glcontroller.cu:23-50 equivalents: xyz into a strided float buffer (stride 6: interleaved with normals; 3: offsets)
+__global__ void __launch_bounds__(256) export_xyz_kernel(const float4* __restrict__ in, int n, float* __restrict__ out6, float* __restrict__ out3)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    if (out6) { out6[6 * i] = p.x; out6[6 * i + 1] = p.y; out6[6 * i + 2] = p.z; }
+    if (out3) { out3[3 * i] = p.x; out3[3 * i + 1] = p.y; out3[3 * i + 2] = p.z; }
+}
+
 __global__ void fill_int_kernel(int* p, int v, int n)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
@@ -708,7 +718,10 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             const float extentY = hs.gsize[1] > 1.f ? hs.gsize[1] : 1.f;
             const int perHalo = (int)(4.0 * N * in.haloWidth / extentY) + 4096;
             in.capHalo = slabOpts->halo_capacity > 0 ? slabOpts->halo_capacity : std::min(N, perHalo);
-            in.capMig = slabOpts->migration_capacity > 0 ? slabOpts->migration_capacity : std::min(N, N / 50 + 2048);
+            // migration: blood cells crossing one slab face (or teleporting to the spawn rank) in ONE step - a few cells;
+            // default 2 % of a rank's share of the particles (+ slack).  Messages are sent at full capacity, so this is
+            // also the per-step NVLink volume; overflow raises a sticky error
+            in.capMig = slabOpts->migration_capacity > 0 ? slabOpts->migration_capacity : std::min(N, N / (50 * std::max(1, slabOpts->world)) + 2048);
             in.ncclId = slabOpts->nccl_unique_id;
             s->slab = slab_create(in, hs, s->tg, s->tids[1], s->tcellStart, s->tcellEnd, slab_ctx(s));
         }
@@ -882,6 +895,18 @@ int bcs_device_ptrs(bcs_sim* s, bcs_device_view* o)
     o->particle_pos4 = s->pos; o->particle_vel4 = s->vel; o->particle_frc4 = s->frc;
     o->vein_pos4 = s->vpos; o->vein_vel4 = s->vvel; o->vein_frc4 = s->vfrc;
     o->stream = (void*)s->stream;
+    BCS_API_END
+}
+
+int bcs_export_frame(bcs_sim* s, float* cellVertices6, float* offsets3, float* veinVertices6)
+{
+    BCS_API_BEGIN
+    BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
+    BCS_CUDA(cudaSetDevice(s->device));
+    const int N = s->hs.N, V = s->hs.V;
+    if (cellVertices6 || offsets3) export_xyz_kernel<<<(N + 255) / 256, 256, 0, s->stream>>>(s->pos, N, cellVertices6, offsets3);
+    if (veinVertices6) export_xyz_kernel<<<(V + 255) / 256, 256, 0, s->stream>>>(s->vpos, V, veinVertices6, nullptr);
+    BCS_CUDA(cudaGetLastError());
     BCS_API_END
 }
 

@@ -244,3 +244,26 @@ def test_tiled_collision_kernel_equals_index_walk(bcs_lib, monkeypatch):
     for x, y in zip(out[0][1], out[1][1]):
         assert np.array_equal(x, y)
     assert out[0][1][2].sum() > 0   # some pairs actually collide
+
+
+def test_frame_export_layouts(bcs_lib):
+    """bcs_export_frame fills the renderer's interleaved buffers (glcontroller.cu:23-50): stride 6 with the normal slots
+    untouched, stride 3 offsets, stride 6 vein vertices."""
+    import torch
+    sc = golden_scene("mini3")
+    st, _ = seeded_state("mini3", "wide")
+    with make_bcs(sc) as sim:
+        sim.upload_state(st)
+        sim.step(3)
+        n, v = sim.n_particles, sim.n_vertices
+        dev = torch.device("cuda", 0)
+        a = torch.full((6 * n,), -7.0, device=dev)
+        b = torch.full((3 * n,), -7.0, device=dev)
+        c = torch.full((6 * v,), -7.0, device=dev)
+        sim.export_frame(a.data_ptr(), b.data_ptr(), c.data_ptr())
+        sim.synchronize()
+        pos, vpos = refcheck.down(sim, capi.PARTICLE_POS), refcheck.down(sim, capi.VEIN_POS)
+        a, b, c = a.cpu().numpy().reshape(n, 6), b.cpu().numpy().reshape(n, 3), c.cpu().numpy().reshape(v, 6)
+        assert np.array_equal(a[:, :3], pos) and np.all(a[:, 3:] == -7.0)
+        assert np.array_equal(b, pos)
+        assert np.array_equal(c[:, :3], vpos) and np.all(c[:, 3:] == -7.0)
