@@ -179,20 +179,31 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) slab_expire_ghosts_kernel(const int* __restrict__ ghostList, const int* __restrict__ ghostCount,
-                                                               unsigned char* __restrict__ pflag)
+// last step's ghosts lose their flag, then (same single CTA, after a barrier) the send headers and the ghost count are
+// reset for this step's pack - one launch instead of two on the per-step chain
+__global__ void __launch_bounds__(1024) slab_expire_reset_kernel(const int* __restrict__ ghostList, int* __restrict__ ghostCount,
+                                                                unsigned char* __restrict__ pflag, SlabBuffers buf, int nv0, int nv1)
 {
     const int n = *ghostCount;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
         const int pid = ghostList[k];
         if (!(pflag[pid] & 1)) pflag[pid] = 0;
     }
+    __syncthreads();
+    if (threadIdx.x < 3) { buf.send[threadIdx.x]->nMig = 0; buf.send[threadIdx.x]->nHalo = 0; buf.send[threadIdx.x]->nVerts = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) { *ghostCount = 0; buf.send[0]->nVerts = nv0; buf.send[1]->nVerts = nv1; }
 }
 
 // vein vertices of the static halo lists (owned vertices near a face)
-__global__ void __launch_bounds__(256) slab_pack_vertices_kernel(const int* __restrict__ list, int count, const float4* __restrict__ vpos,
-                                                                const float4* __restrict__ vvel, VertexRecord* __restrict__ out)
+__global__ void __launch_bounds__(256) slab_pack_vertices_kernel(const int* __restrict__ list0, int count0, VertexRecord* __restrict__ out0,
+                                                                const int* __restrict__ list1, int count1, VertexRecord* __restrict__ out1,
+                                                                const float4* __restrict__ vpos, const float4* __restrict__ vvel)
 {
+    // blockIdx.y = direction (up / down neighbour)
+    const int* list = blockIdx.y ? list1 : list0;
+    const int count = blockIdx.y ? count1 : count0;
+    VertexRecord* out = blockIdx.y ? out1 : out0;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const int v = list[k];
@@ -209,16 +220,30 @@ __global__ void slab_reset_headers_kernel(SlabBuffers buf, int* ghostCount, int 
 }
 
 // ---- unpack -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __restrict__ types, const SlabHeader* __restrict__ hdr, const MigRecord* __restrict__ mig,
-                                                         const HaloRecord* __restrict__ halo, const VertexRecord* __restrict__ verts, int nVerts,
-                                                         int capMig, int capHalo, float4* __restrict__ pos, float4* __restrict__ vel,
+constexpr int MAX_UNPACK_SOURCES = 16;
+struct UnpackSources {        // every message received this step: blockIdx.y selects one
+    const char* raw[MAX_UNPACK_SOURCES];
+    unsigned char full[MAX_UNPACK_SOURCES];   // 1: neighbour message (migration + halo + vertices), 0: spawn message (migration only)
+    int n;
+    size_t haloOffset, vertOffset;            // byte offsets of the halo / vertex regions inside a message
+};
+
+__global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __restrict__ types, const UnpackSources src, int capVert,
+                                                         int capMig, int capHaloFull, float4* __restrict__ pos, float4* __restrict__ vel,
                                                          float4* __restrict__ frc, float4* __restrict__ vpos, float4* __restrict__ vvel,
                                                          unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                          int* __restrict__ ghostList, int* __restrict__ ghostCount,
                                                          const float4* __restrict__ wallBuilt, float wallMargin, int* __restrict__ wallDirty)
 {
+    const char* raw = src.raw[blockIdx.y];
+    const bool full = src.full[blockIdx.y] != 0;
+    const SlabHeader* hdr = (const SlabHeader*)raw;
+    const MigRecord* mig = (const MigRecord*)(raw + sizeof(SlabHeader));
+    const HaloRecord* halo = (const HaloRecord*)(raw + src.haloOffset);
+    const VertexRecord* verts = (const VertexRecord*)(raw + src.vertOffset);
+    const int capHalo = full ? capHaloFull : 0;
     const int nMig = min(hdr->nMig, capMig), nHalo = min(hdr->nHalo, capHalo);
-    nVerts = min(nVerts, hdr->nVerts);
+    const int nVerts = full ? min(capVert, hdr->nVerts) : 0;
     const int total = nMig + nHalo + nVerts;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         if (k < nMig) {
@@ -419,16 +444,13 @@ static VertexRecord* vertex_region(const SlabState* s, char* raw)
     return (VertexRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord) + (size_t)s->capHalo * sizeof(HaloRecord));
 }
 
-static void unpack_one(SlabState* s, const SlabCtx& ctx, char* raw, bool full)
+static void unpack_all(SlabState* s, const SlabCtx& ctx, const UnpackSources& src)
 {
-    const SlabHeader* hdr = (const SlabHeader*)raw;
-    const MigRecord* mig = (const MigRecord*)(raw + sizeof(SlabHeader));
-    const HaloRecord* halo = (const HaloRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord));
+    if (!src.n) return;
     BCS_LAUNCH("slab_unpack", ctx.stream,
-               slab_unpack_kernel<<<64, 256, 0, ctx.stream>>>(ctx.typesDev, hdr, mig, halo, full ? vertex_region(s, raw) : nullptr,
-                                                              full ? s->capVert : 0, s->capMig, full ? s->capHalo : 0, ctx.pos, ctx.vel,
-                                                              ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount,
-                                                              ctx.wallBuilt, ctx.wallMargin, ctx.wallDirty));
+               slab_unpack_kernel<<<dim3(32, src.n), 256, 0, ctx.stream>>>(ctx.typesDev, src, s->capVert, s->capMig, s->capHalo, ctx.pos, ctx.vel,
+                                                                          ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount,
+                                                                          ctx.wallBuilt, ctx.wallMargin, ctx.wallDirty));
 }
 
 void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
@@ -438,26 +460,38 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
     if (s->listsValid) {
         items.cells = s->listCells; items.cellPrefix = s->listCellPrefix; items.ghostList = s->ghostList; items.ghostCount = s->ghostCount;
         items.types = ctx.typesDev; items.maxP = ctx.maxP;
-        BCS_LAUNCH("slab_expire_ghosts", st, slab_expire_ghosts_kernel<<<32, 256, 0, st>>>(s->ghostList, s->ghostCount, s->pflag));
+        BCS_LAUNCH("slab_expire_reset", st,
+                   slab_expire_reset_kernel<<<1, 1024, 0, st>>>(s->ghostList, s->ghostCount, s->pflag, s->buf, s->vertCount[0], s->vertCount[1]));
+    } else {
+        BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
     }
-    BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
     const long long packItems = s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N;
     BCS_LAUNCH("slab_pack", st,
                slab_pack_kernel<<<(int)((packItems + 255) / 256), 256, 0, st>>>(ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
                                                                                  s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
                                                                                  s->errorFlag, items));
-    for (int d = 0; d < 2; ++d)
-        if (s->vertCount[d])
-            BCS_LAUNCH("slab_pack_vertices", st,
-                       slab_pack_vertices_kernel<<<(s->vertCount[d] + 255) / 256, 256, 0, st>>>(s->vertList[d], s->vertCount[d], ctx.vpos,
-                                                                                              ctx.vvel, vertex_region(s, s->sendRaw[d])));
+    if (s->vertCount[0] || s->vertCount[1]) {
+        const int most = max(s->vertCount[0], s->vertCount[1]);
+        BCS_LAUNCH("slab_pack_vertices", st,
+                   slab_pack_vertices_kernel<<<dim3((most + 255) / 256, 2), 256, 0, st>>>(s->vertList[0], s->vertCount[0], vertex_region(s, s->sendRaw[0]),
+                                                                                        s->vertList[1], s->vertCount[1], vertex_region(s, s->sendRaw[1]),
+                                                                                        ctx.vpos, ctx.vvel));
+    }
     BCS_CUDA(cudaGetLastError());
     if (s->dev.world > 1 && s->comm) {
         s->exchange(st);
-        if (s->dev.rank > 0) unpack_one(s, ctx, s->recvRaw[0], true);
-        if (s->dev.rank < s->dev.world - 1) unpack_one(s, ctx, s->recvRaw[1], true);
+        UnpackSources src{};
+        src.haloOffset = sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord);
+        src.vertOffset = src.haloOffset + (size_t)s->capHalo * sizeof(HaloRecord);
+        auto add = [&](const char* raw, bool full) {
+            BCS_REQUIRE(src.n < MAX_UNPACK_SOURCES, BCS_ERR_UNSUPPORTED, "too many ranks for one unpack launch");
+            src.raw[src.n] = raw; src.full[src.n] = full ? 1 : 0; ++src.n;
+        };
+        if (s->dev.rank > 0) add(s->recvRaw[0], true);
+        if (s->dev.rank < s->dev.world - 1) add(s->recvRaw[1], true);
         for (char* raw : s->spawnRecvRaw)
-            if (raw) unpack_one(s, ctx, raw, false);
+            if (raw) add(raw, false);
+        unpack_all(s, ctx, src);
     }
     slab_build_lists(s, ctx);
     s->listsValid = true;
