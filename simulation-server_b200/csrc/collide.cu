@@ -34,25 +34,71 @@ struct PairAccum {
     int hits;
 };
 
-// detectCollision + addResilientForceOnCollision with intensityCoefficient 0.5
-__device__ __forceinline__ void test_pair(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,
-                                          const float r2, const float4* __restrict__ svel, int j, PairAccum& acc)
+// detectCollision (particle_collisions.cuh:26-38): the distance test
+__device__ __forceinline__ bool pair_touches(const float3 p1, const float r1, const float4 q4, const float r2)
 {
     const float3 rel = p1 - xyz(q4);
     const float d2 = length_squared(rel);
     const float minD = r1 + r2;
-    if (d2 <= minD * minD && d2 >= 0.0001f) {
-        const float3 rv = v1 - xyz(svel[j]);
-        const float3 dir = normalize(rel);
-        const float3 tang = rv - dot(rv, dir) * dir;
-        const float3 spring = (-ph.coll_spring * (r1 * 2 - sqrtf(d2))) * dir;
-        const float3 damp = ph.coll_damping * rv;
-        const float3 shear = ph.coll_shear * tang;
-        acc.F = acc.F + 0.5f * (spring + damp + shear);
-        ++acc.hits;
-    }
+    return d2 <= minD * minD && d2 >= 0.0001f;
 }
 
+// addResilientForceOnCollision with intensityCoefficient 0.5 (physics.cuh:133-145) for a pair that touches
+__device__ __forceinline__ void pair_force(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,
+                                           const float4* __restrict__ svel, int j, PairAccum& acc)
+{
+    const float3 rel = p1 - xyz(q4);
+    const float d2 = length_squared(rel);
+    const float3 rv = v1 - xyz(svel[j]);
+    const float3 dir = normalize(rel);
+    const float3 tang = rv - dot(rv, dir) * dir;
+    const float3 spring = (-ph.coll_spring * (r1 * 2 - sqrtf(d2))) * dir;
+    const float3 damp = ph.coll_damping * rv;
+    const float3 shear = ph.coll_shear * tang;
+    acc.F = acc.F + 0.5f * (spring + damp + shear);
+    ++acc.hits;
+}
+
+// detectCollision + addResilientForceOnCollision with intensityCoefficient 0.5
+__device__ __forceinline__ void test_pair(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,
+                                          const float r2, const float4* __restrict__ svel, int j, PairAccum& acc)
+{
+    if (pair_touches(p1, r1, q4, r2)) pair_force(ph, p1, v1, r1, q4, svel, j, acc);
+}
+
+// Hits are rare (~7 % of the particles per step) and land in different loop iterations of different lanes: evaluated on
+// the spot, each costs the whole warp a ~120-instruction pass with one lane active.  The walk therefore only RECORDS the
+// touching candidates (up to DEFER per particle, in encounter order); afterwards all lanes evaluate their first hit in
+// one common pass, then their second ...  Same forces, same summation order per particle.
+constexpr int DEFER = 3;
+struct Deferred {
+    int j[DEFER];
+    int n;
+};
+__device__ __forceinline__ void defer_or_evaluate(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,
+                                                  const float4* __restrict__ svel, int j, PairAccum& acc, Deferred& df,
+                                                  const float4* __restrict__ spos)
+{
+    if (df.n < DEFER) {
+#pragma unroll
+        for (int k = 0; k < DEFER; ++k)
+            if (k == df.n) df.j[k] = j;
+        ++df.n;
+    } else {
+        // more touching candidates than slots (dense clusters): flush in order, keep the order
+#pragma unroll
+        for (int k = 0; k < DEFER; ++k) pair_force(ph, p1, v1, r1, spos[df.j[k]], svel, df.j[k], acc);
+        df.n = 1;
+        df.j[0] = j;
+    }
+}
+__device__ __forceinline__ void evaluate_deferred(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, PairAccum& acc,
+                                                  const Deferred& df, const float4* __restrict__ spos, const float4* __restrict__ svel)
+{
+#pragma unroll
+    for (int k = 0; k < DEFER; ++k)
+        if (k < df.n) pair_force(ph, p1, v1, r1, spos[df.j[k]], svel, df.j[k], acc);
+}
 
 // clean-semantics walk of one sorted slot through the compact cell index (global memory); see the tiled kernel below
 // for the production path
@@ -99,6 +145,8 @@ __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, 
         lo[r] = __ldg(a.occStart + rk);
         hi[r] = first[r] >= 0 ? __ldg(a.occStart + rk + nocc[r]) : lo[r];
     }
+    Deferred df;
+    df.n = 0;
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
         for (int j = lo[r]; j < hi[r]; ++j) {
@@ -108,10 +156,11 @@ __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, 
                 const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
                 ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
             }
-            test_pair(a.phys, p1, v1, r1, q4, q4.w, a.svel, j, acc);
+            if (pair_touches(p1, r1, q4, q4.w)) defer_or_evaluate(a.phys, p1, v1, r1, q4, a.svel, j, acc, df, a.spos);
             if (STATS) ++myTests;
         }
     }
+    evaluate_deferred(a.phys, p1, v1, r1, acc, df, a.spos, a.svel);
 }
 
 // ------------------------------------------------------------------------------------------------------------

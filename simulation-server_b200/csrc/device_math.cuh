@@ -28,9 +28,16 @@ __device__ __forceinline__ float3 normalize(float3 v)
 // calculateIdForCell (grids/uniform_grid.cu:24-36) with the `max`/`min` macros of :20-21 written out:
 //   max(0, q)    -> (0 > q ? 0 : q)        min(len, m) -> (len > m ? m : len)
 // The division must stay a true IEEE division (cell sizes such as 25 are not powers of two).
+// exact quotient (p - mn) / cs: a power-of-two cell size (the reference's 2-unit particle grid) divides exactly as a
+// product with its reciprocal, anything else (e.g. the 25-unit triangle grid) needs the IEEE division
+__device__ __forceinline__ float cell_quotient(float d, int cs)
+{
+    return (cs & (cs - 1)) == 0 ? d * (1.0f / (float)cs) : __fdiv_rn(d, (float)cs);
+}
+
 __device__ __forceinline__ int axis_cell(float p, float mn, float len, int cs)
 {
-    float q = __fdiv_rn(p - mn, (float)cs);
+    float q = cell_quotient(p - mn, cs);
     float m = (0.f > q) ? 0.f : q;
     float r = (len > m) ? m : len;
     return (int)r;
@@ -38,7 +45,7 @@ __device__ __forceinline__ int axis_cell(float p, float mn, float len, int cs)
 
 // the unclamped per-axis index the collision kernels use to trim the 27-cell stencil
 // (particle_collisions.cuh:117-119)
-__device__ __forceinline__ int axis_cell_raw(float p, float mn, int cs) { return (int)__fdiv_rn(p - mn, (float)cs); }
+__device__ __forceinline__ int axis_cell_raw(float p, float mn, int cs) { return (int)cell_quotient(p - mn, cs); }
 
 // Philox4x32-10 (counter-based respawn RNG; replaces the cuRAND XORWOW states the reference shares
 // between the threads of a cell, vein_end.cu:103-105)
