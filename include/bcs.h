@@ -232,7 +232,8 @@ typedef struct bcs_device_view {
     void* particle_frc4;
     void* vein_pos4;       /* float4[n_vertices] */
     void* vein_vel4;
-    void* vein_frc4;
+    void* vein_frc4;       /* between the vein-collision stage and the vein integrator of a step the wall splats are parked in
+                            * fixed point and NOT yet part of this array (bcs_download folds them in); whole steps: complete */
     void* stream;          /* cudaStream_t all work of this handle is ordered on */
 } bcs_device_view;
 int bcs_device_ptrs(bcs_sim* sim, bcs_device_view* out);

@@ -516,7 +516,10 @@ void stageParticleCollisions(orc_sim& s, bool apply)     // calculateParticleCol
                         sum += (uint64_t)(q + 1) * 0x9E3779B97F4A7C15ull;
                         // detectCollision, particle_collisions.cuh:26-38
                         f3 rel = p1 - s.pos.get(q);
-                        float d2 = length_squared(rel);
+                        // length_squared as nvcc compiles it in the reference (-fmad=true): z*z + (y*y + (x*x)) as an FMA
+                        // chain.  The touch decision is a threshold on this value, so the rounding sequence is part of
+                        // the contract; the CUDA path pins the same chain.
+                        float d2 = std::fmaf(rel.z, rel.z, std::fmaf(rel.y, rel.y, rel.x * rel.x));
                         float minD = r1 + radiusOf(q);
                         if (d2 <= minD * minD && d2 >= 0.0001f) {
                             ++nh;

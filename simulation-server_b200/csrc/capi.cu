@@ -132,6 +132,7 @@ struct bcs_sim {
     int maskWords = 0;
     // vein
     float4 *vpos = nullptr, *vvel = nullptr, *vfrc = nullptr, *tcent = nullptr;
+    long long* vsplat = nullptr;   // [3V] fixed-point wall-splat accumulators (vein_device.cuh: splat_add)
     int *tkeys[2] = {nullptr, nullptr}, *tids[2] = {nullptr, nullptr}, *tcellStart = nullptr, *tcellEnd = nullptr;
     TriPacked* tris = nullptr;
     Aabb *groupBox = nullptr, *cellBox = nullptr;
@@ -367,7 +368,7 @@ VeinArgs vein_args(bcs_sim* s)
 {
     VeinArgs a{};
     a.V = s->hs.V; a.T = s->hs.T; a.phys = s->phys;
-    a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc;
+    a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc; a.vsplat = s->vsplat;
     a.nbrIds = s->nbrIds; a.nbrLen = s->nbrLen; a.vidx = s->vidx;
     a.vOwned = s->slab ? s->slab->vOwned : nullptr;
     if (s->wall.enabled) { a.vposBuilt = s->wall.vposBuilt; a.wallMargin = s->wall.margin; a.wallDirty = s->wall.dirty; }
@@ -380,7 +381,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.tgrid = s->tg; a.types = s->types; a.phys = s->phys;
     a.n = s->hs.N; a.T = s->hs.T;
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc;
-    a.vpos = s->vpos; a.vfrc = s->vfrc; a.vidx = s->vidx;
+    a.vpos = s->vpos; a.vfrc = s->vfrc; a.vsplat = s->vsplat; a.vidx = s->vidx;
     a.triIds = s->tids[1]; a.cellStart = s->tcellStart; a.cellEnd = s->tcellEnd;
     a.tris = s->tris; a.groupBox = s->groupBox; a.cellBox = s->cellBox; a.cellSlab = s->cellSlab; a.groupSlab = s->groupSlab; a.fast = !s->exhaustiveVein;
     a.nCells = s->hs.B; a.maxP = s->maxP; a.cullList = s->cullList; a.cullCount = s->cullCount;
@@ -663,6 +664,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             s->cellStart = s->track(dev_alloc<int>(s->pg.cells)); s->cellEnd = s->track(dev_alloc<int>(s->pg.cells));
         }
         s->vpos = s->track(dev_alloc<float4>(V)); s->vvel = s->track(dev_alloc<float4>(V)); s->vfrc = s->track(dev_alloc<float4>(V));
+        s->vsplat = s->track(dev_alloc<long long>(3 * (size_t)V));
         s->tcent = s->track(dev_alloc<float4>(T));
         s->tris = s->track(dev_alloc<TriPacked>(T));
         s->groupBox = s->track(dev_alloc<Aabb>((T + 7) / 8));
@@ -867,6 +869,7 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     BCS_CUDA(cudaGetLastError());
     if (s->slab && which == BCS_PARTICLE_POS) s->slab->primed = false;   // ownership is re-derived from the new positions
     if (s->wall.enabled && which == BCS_VEIN_POS) BCS_CUDA(cudaMemsetAsync(s->wall.dirty, 1, sizeof(int), s->stream));   // wall grid: rebuild
+    if (which == BCS_VEIN_FRC) BCS_CUDA(cudaMemsetAsync(s->vsplat, 0, 3 * (size_t)s->hs.V * sizeof(long long), s->stream));   // the upload replaces parked splats too
     BCS_API_END
 }
 
@@ -879,6 +882,7 @@ int bcs_download(bcs_sim* s, int which, float* x, float* y, float* z, int32_t n)
     Array a = array_of(s, which);
     BCS_REQUIRE(n == a.n, BCS_ERR_INVALID, "array length mismatch");
     float* sx = s->staging; float* sy = sx + s->stagingLen; float* sz = sy + s->stagingLen;
+    if (which == BCS_VEIN_FRC) launch_vein_fold_splats(vein_args(s), s->stream);   // wall splats of a half-finished step are parked in fixed point
     unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(a.ptr, sx, sy, sz, n);
     BCS_CUDA(cudaGetLastError());
     BCS_CUDA(cudaMemcpyAsync(x, sx, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));

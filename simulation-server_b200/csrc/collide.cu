@@ -37,10 +37,13 @@ struct PairAccum {
 // detectCollision (particle_collisions.cuh:26-38): the distance test
 __device__ __forceinline__ bool pair_touches(const float3 p1, const float r1, const float4 q4, const float r2)
 {
+    // The touch decision is a threshold on d2, so its rounding sequence is pinned (the compiler is otherwise free to
+    // contract x*x + y*y + z*z in either association): the FMA chain nvcc emits for the reference's length_squared.
+    // The oracle evaluates the same chain (std::fmaf), which makes hit sets bit-identical, not just the candidate sets.
     const float3 rel = p1 - xyz(q4);
-    const float d2 = length_squared(rel);
+    const float d2 = __fmaf_rn(rel.z, rel.z, __fmaf_rn(rel.y, rel.y, __fmul_rn(rel.x, rel.x)));
     const float minD = r1 + r2;
-    return d2 <= minD * minD && d2 >= 0.0001f;
+    return d2 <= __fmul_rn(minD, minD) && d2 >= 0.0001f;
 }
 
 // addResilientForceOnCollision with intensityCoefficient 0.5 (physics.cuh:133-145) for a pair that touches

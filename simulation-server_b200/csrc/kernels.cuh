@@ -157,7 +157,8 @@ struct VeinArgs {
     PhysDev phys;
     float4* vpos;
     float4* vvel;
-    float4* vfrc;
+    float4* vfrc;               // .w != 0: wall splats are parked in vsplat (see vein_device.cuh: splat_add)
+    long long* vsplat;          // [3V] fixed-point (2^-40) sums of this step's wall-collision splats
     const int* nbrIds;          // [9][V]
     const float* nbrLen;
     const unsigned* vidx;       // [3T]
@@ -169,6 +170,7 @@ struct VeinArgs {
 void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st);
 void launch_vein_gather(const VeinArgs& a, cudaStream_t st);
 void launch_vein_integrate(const VeinArgs& a, cudaStream_t st);
+void launch_vein_fold_splats(const VeinArgs& a, cudaStream_t st);   // vfrc += parked splats (before vfrc is read back)
 
 struct VeinCollideArgs {
     GridDev tgrid;
@@ -181,6 +183,7 @@ struct VeinCollideArgs {
     float4* frc;
     const float4* vpos;
     float4* vfrc;
+    long long* vsplat;          // [3V] fixed-point splat accumulators (order-independent sums)
     const unsigned* vidx;
     const int* triIds;          // sorted triangle ids
     const int* cellStart;

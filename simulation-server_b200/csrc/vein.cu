@@ -74,11 +74,18 @@ __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
     if (id >= a.V) return;
     if (a.vOwned && !a.vOwned[id]) {
         // slab mode: not ours - state arrives with the vertex halo; forget the partial splats we accumulated on it
-        a.vfrc[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.vfrc[id].w != 0.f) {
+            splat_take(a.vsplat, id);
+            a.vfrc[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         return;
     }
     float4 x = a.vpos[id], v = a.vvel[id];
-    const float4 F = a.vfrc[id];
+    float4 F = a.vfrc[id];
+    if (F.w != 0.f) {
+        const float3 sp = splat_take(a.vsplat, id);
+        F.x += sp.x; F.y += sp.y; F.z += sp.z;
+    }
     const float dt = a.phys.dt;
     v.x += dt * F.x; v.y += dt * F.y; v.z += dt * F.z;
     x.x += dt * v.x; x.y += dt * v.y; x.z += dt * v.z;
@@ -91,6 +98,23 @@ __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
         const float dx = x.x - b.x, dy = x.y - b.y, dz = x.z - b.z;
         if (dx * dx + dy * dy + dz * dz > a.wallMargin * a.wallMargin) *a.wallDirty = 1;
     }
+}
+
+// vfrc += parked wall splats (idempotent): run before vfrc is read back between the collision stage and the integrator
+__global__ void __launch_bounds__(256) vein_fold_splats_kernel(const VeinArgs a)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= a.V) return;
+    float4 F = a.vfrc[id];
+    if (F.w == 0.f) return;
+    const float3 sp = splat_take(a.vsplat, id);
+    a.vfrc[id] = make_float4(F.x + sp.x, F.y + sp.y, F.z + sp.z, 0.f);
+}
+
+void launch_vein_fold_splats(const VeinArgs& a, cudaStream_t st)
+{
+    BCS_LAUNCH("vein_fold_splats", st, vein_fold_splats_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a));
+    BCS_CUDA(cudaGetLastError());
 }
 
 void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)

@@ -204,6 +204,30 @@ __device__ bool first_hit_fast(const VeinCollideArgs& a, const float3 pos, const
     return true;
 }
 
+// Wall splats are summed ORDER-INDEPENDENTLY: a float atomicAdd makes the vertex force depend on which particle's add
+// lands first (two splats on top of the spring force already differ in the last bit), which breaks bit-identical
+// restarts and the N-rank == 1-rank equality.  Each contribution is therefore added as a 64-bit fixed-point integer
+// (unit 2^-40: exact for every float of magnitude >= 2^-16, range +-8.3e6) and folded into the float force once, by
+// the vertex integrator (or vein_fold_splats before a read-back).  vfrc.w flags vertices with parked splats.
+constexpr float SPLAT_SCALE = 1099511627776.0f;        // 2^40
+constexpr float SPLAT_UNSCALE = 1.0f / 1099511627776.0f;
+__device__ __forceinline__ void splat_add(const VeinCollideArgs& a, unsigned v, float w, const float3 ds)
+{
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(a.vsplat) + 3 * (size_t)v;
+    atomicAdd(acc, (unsigned long long)__float2ll_rn(w * ds.x * SPLAT_SCALE));
+    atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(w * ds.y * SPLAT_SCALE));
+    atomicAdd(acc + 2, (unsigned long long)__float2ll_rn(w * ds.z * SPLAT_SCALE));
+    a.vfrc[v].w = 1.0f;
+}
+// the parked splats of vertex v as floats; clears the accumulators
+__device__ __forceinline__ float3 splat_take(long long* vsplat, int v)
+{
+    long long* acc = vsplat + 3 * (size_t)v;
+    const float3 r = make_float3(__ll2float_rn(acc[0]) * SPLAT_UNSCALE, __ll2float_rn(acc[1]) * SPLAT_UNSCALE, __ll2float_rn(acc[2]) * SPLAT_UNSCALE);
+    acc[0] = 0; acc[1] = 0; acc[2] = 0;
+    return r;
+}
+
 // what the stage does once the traversal has ended on triangle h (vein_collisions.cu:234-276)
 __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid, const float4 p4, const float4 v4, const float3 dir,
                                                const RayHit& h, bool splatOnly = false)
@@ -242,9 +266,9 @@ __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid
         const unsigned i0 = a.vidx[3 * h.tri], i1 = a.vidx[3 * h.tri + 1], i2 = a.vidx[3 * h.tri + 2];
         const float3 b = barycentric(pos + h.t * dir, xyz(a.vpos[i0]), xyz(a.vpos[i1]), xyz(a.vpos[i2]));
         // the reference uses plain += here and loses updates when two particles share a vertex
-        atomicAdd(&a.vfrc[i0].x, b.x * ds.x); atomicAdd(&a.vfrc[i0].y, b.x * ds.y); atomicAdd(&a.vfrc[i0].z, b.x * ds.z);
-        atomicAdd(&a.vfrc[i1].x, b.y * ds.x); atomicAdd(&a.vfrc[i1].y, b.y * ds.y); atomicAdd(&a.vfrc[i1].z, b.y * ds.z);
-        atomicAdd(&a.vfrc[i2].x, b.z * ds.x); atomicAdd(&a.vfrc[i2].y, b.z * ds.y); atomicAdd(&a.vfrc[i2].z, b.z * ds.z);
+        splat_add(a, i0, b.x, ds);
+        splat_add(a, i1, b.y, ds);
+        splat_add(a, i2, b.z, ds);
         if (!splatOnly) atomicAdd(&a.counters->veinHits, 1ull);
     }
 }
