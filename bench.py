@@ -118,6 +118,7 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "vein_collisions": 24 * N + 120 * hits,    # (wall-grid path: the triangle tests of the few candidates; same contract figure)
         "vein_ghost_splat": 0,
         "vein_masking": 0,                         # phase B of the wall-grid path: a few thousand particles
+        "vein_apply": 0,                           # the stage's effect for the unmasked near hits (thread per listed particle)
         "wall_rebuild": 0,                         # returns at once unless a vertex left its margin
         "finish_step": 72 * N,                     # integrate (R 36N, W 24N) + vein-end test (12N)
         "integrate_particles": 60 * N,

@@ -105,10 +105,11 @@ __device__ __forceinline__ void evaluate_deferred(const PhysDev& ph, const float
 
 // clean-semantics walk of one sorted slot through the compact cell index (global memory); see the tiled kernel below
 // for the production path
-template <bool DEBUG, bool STATS>
+constexpr int WALK_THREADS = 128;
+template <bool DEBUG, bool STATS, bool FLAT>
 __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, const float3 p1, const float3 v1, const float r1, int cell, int x0,
                                                 int x1, int y0, int y1, int z0, int z1, PairAccum& acc, int& cnt, unsigned long long& sum,
-                                                unsigned long long& myTests)
+                                                unsigned long long& myTests, int2 (*seg)[WALK_THREADS] = nullptr)
 {
     const GridDev& g = a.grid;
     const int plane = g.nx * g.ny;
@@ -150,17 +151,58 @@ __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, 
     }
     Deferred df;
     df.n = 0;
+    if (FLAT) {
+        // Level 4, flattened.  Walking row after row costs a warp sum_r max_lanes(len_r) iterations; at ~4 candidates per
+        // particle spread over 9 rows nearly every row is non-empty for SOME lane, so most iterations run a few lanes.
+        // The non-empty slot ranges are therefore parked compactly in shared memory and every lane walks its own list
+        // end to end: iteration k of the warp is candidate k of every lane (max_lanes(sum_r len_r) iterations), and the
+        // next candidate's load is issued before the current one is tested.  Same candidates, same order per particle.
+        const int tid = threadIdx.x;
+        int nseg = 0;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-        for (int j = lo[r]; j < hi[r]; ++j) {
-            if (j == slot) continue;
-            const float4 q4 = a.spos[j];
+        for (int r = 0; r < 9; ++r)
+            if (hi[r] > lo[r]) seg[nseg++][tid] = make_int2(lo[r], hi[r]);
+        int s = 0, j = 0, e = 0;
+        bool live = nseg > 0;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const int2 g0 = seg[0][tid];
+            j = g0.x; e = g0.y;
+            q = a.spos[j];
+        }
+        while (live) {
+            const int jc = j;
+            const float4 q4 = q;
+            if (++j == e) {
+                if (++s < nseg) {
+                    const int2 g1 = seg[s][tid];
+                    j = g1.x; e = g1.y;
+                } else {
+                    live = false;
+                }
+            }
+            if (live) q = a.spos[j];
+            if (jc == slot) continue;
             if (DEBUG) {
-                const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
+                const int qid = __float_as_int(a.svel[jc].w) & 0x7fffffff;
                 ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
             }
-            if (pair_touches(p1, r1, q4, q4.w)) defer_or_evaluate(a.phys, p1, v1, r1, q4, a.svel, j, acc, df, a.spos);
+            if (pair_touches(p1, r1, q4, q4.w)) defer_or_evaluate(a.phys, p1, v1, r1, q4, a.svel, jc, acc, df, a.spos);
             if (STATS) ++myTests;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            for (int j = lo[r]; j < hi[r]; ++j) {
+                if (j == slot) continue;
+                const float4 q4 = a.spos[j];
+                if (DEBUG) {
+                    const int qid = __float_as_int(a.svel[j].w) & 0x7fffffff;
+                    ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull;
+                }
+                if (pair_touches(p1, r1, q4, q4.w)) defer_or_evaluate(a.phys, p1, v1, r1, q4, a.svel, j, acc, df, a.spos);
+                if (STATS) ++myTests;
+            }
         }
     }
     evaluate_deferred(a.phys, p1, v1, r1, acc, df, a.spos, a.svel);
@@ -273,7 +315,7 @@ __global__ void __launch_bounds__(TILE) particle_collisions_tiled_kernel(const C
         int cnt = 0;
         unsigned long long sum = 0;
         if (fallback) {
-            clean_slot_walk<DEBUG, STATS>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests);
+            clean_slot_walk<DEBUG, STATS, false>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests);
         } else {
             const int row0 = fast_div((unsigned)cell, a.nxMagic, a.nxShift);
             const int own = slot - wlo[1];
@@ -332,9 +374,10 @@ __global__ void __launch_bounds__(TILE) particle_collisions_tiled_kernel(const C
     }
 }
 
-template <bool REFERENCE, bool DEBUG, bool STATS>
-__global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideArgs a)
+template <bool REFERENCE, bool DEBUG, bool STATS, bool FLAT = false, int MINB = 10>
+__global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel(const CollideArgs a)
 {
+    __shared__ int2 seg[FLAT ? 9 : 1][WALK_THREADS];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myTests = 0;
     int myHits = 0;
@@ -392,7 +435,7 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
                 }
             }
         } else {
-            clean_slot_walk<DEBUG, STATS>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests);
+            clean_slot_walk<DEBUG, STATS, FLAT>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests, seg);
         }
         if (DEBUG) {
             a.dbgCount[pid] = cnt;
@@ -420,7 +463,7 @@ __global__ void __launch_bounds__(128) particle_collisions_kernel(const CollideA
 
 void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
 {
-    const int threads = 128, blocks = (a.n + threads - 1) / threads;
+    const int threads = WALK_THREADS, blocks = (a.n + threads - 1) / threads;
     const bool dbg = a.dbgCount != nullptr;
     if (!a.reference && a.tiled) {
         const int tiles = (a.n + TILE - 1) / TILE;
@@ -431,6 +474,12 @@ void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
         if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, true, false><<<blocks, threads, 0, st>>>(a));
         else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, true><<<blocks, threads, 0, st>>>(a));
         else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<true, false, false><<<blocks, threads, 0, st>>>(a));
+    } else if (!a.rows) {
+        if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, true, false, true><<<blocks, threads, 0, st>>>(a));
+        else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, true, true><<<blocks, threads, 0, st>>>(a));
+        else if (a.occ == 12) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true, 12><<<blocks, threads, 0, st>>>(a));
+        else if (a.occ == 16) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true, 16><<<blocks, threads, 0, st>>>(a));
+        else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true><<<blocks, threads, 0, st>>>(a));
     } else {
         if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, true, false><<<blocks, threads, 0, st>>>(a));
         else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, true><<<blocks, threads, 0, st>>>(a));

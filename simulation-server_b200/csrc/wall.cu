@@ -471,9 +471,12 @@ __global__ void __launch_bounds__(256) wall_triangles_kernel(const VeinCollideAr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// phase B: a warp per particle with a near hit (listed by A2 when its first near hit landed) - is it masked by an earlier (far) hit?  Then apply.
+// phase B: a warp per particle with a near hit (listed by A2 when its first near hit landed) - is it masked by an earlier (far) hit?
 // The (stencil cell, slot group) pairs up to the near hit are flattened over the lanes, so the box tests and the
 // triangle tests run 32 wide instead of cell after cell (the search is a chain of dependent L2 reads).
+// The check reads positions, velocities and the wall only, so it belongs to the SEARCH (beside the grid build and
+// the particle collisions); a masked entry is struck from the list (queue[q] = ~pid).  What has to wait for the
+// particle collisions - the stage's effect - is wall_apply_kernel below: a thread per surviving entry.
 // ------------------------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(128) wall_masking_kernel(const VeinCollideArgs a)
@@ -489,11 +492,7 @@ __global__ void __launch_bounds__(128) wall_masking_kernel(const VeinCollideArgs
         {
             const int pid = w.queue[q];
             const unsigned long long best = w.best[pid];
-            const bool splatOnly = w.ghostFlag[pid] != 0;
-            if (best == SEQUENTIAL) {
-                if (lane == 0) vein_collide_particle<true, STATS>(a, pid, myTests, splatOnly);
-                continue;
-            }
+            if (best == SEQUENTIAL) continue;   // searched (and applied) by wall_apply_kernel
             const ParticleFrame f = particle_frame(a, pid);
             const int bestKey = (int)(best >> 32), bestSlot = (int)(best & 0xffffffffu);
             const int cell = (f.pcz * g.ny + f.pcy) * g.nx + f.pcx;
@@ -550,17 +549,40 @@ __global__ void __launch_bounds__(128) wall_masking_kernel(const VeinCollideArgs
                     masked = __any_sync(0xffffffffu, hitFar);
                 }
             }
-            if (!masked && lane == 0) {
-                RayHit h;
-                ray_triangle(f.pos, f.dir, load_tri(a, bestSlot), h);
-                vein_apply_hit(a, pid, a.pos[pid], a.vel[pid], f.dir, h, splatOnly);
-            }
+            if (masked && lane == 0) w.queue[q] = ~pid;
         }
     }
     if (STATS) {
         for (int o = 16; o; o >>= 1) myTests += __shfl_xor_sync(0xffffffffu, myTests, o);
         if (lane == 0 && myTests) atomicAdd(&a.counters->triTests, myTests);
     }
+}
+
+// the stage's effect (vein_collisions.cu:234-276) for every listed particle whose near hit was not masked: reaction
+// force, velocity reflection, wall-force splats.  Particles the grid search could not take (outside the triangle grid,
+// queue overflow) run the sequential search here.
+template <bool STATS>
+__global__ void __launch_bounds__(128) wall_apply_kernel(const VeinCollideArgs a)
+{
+    const WallGridDev& w = a.wall;
+    const int n = *w.queueCount;
+    unsigned long long myTests = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int pid = w.queue[q];
+        if (pid < 0) continue;   // masked
+        const unsigned long long best = w.best[pid];
+        const bool splatOnly = w.ghostFlag[pid] != 0;
+        if (best == SEQUENTIAL) {
+            vein_collide_particle<true, STATS>(a, pid, myTests, splatOnly);
+            continue;
+        }
+        const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+        const float3 dir = normalize(xyz(v4));
+        RayHit h;
+        ray_triangle(xyz(p4), dir, load_tri(a, (int)(best & 0xffffffffu)), h);
+        vein_apply_hit(a, pid, p4, v4, dir, h, splatOnly);
+    }
+    if (STATS && myTests) atomicAdd(&a.counters->triTests, myTests);
 }
 
 }  // namespace
@@ -600,16 +622,18 @@ void launch_wall_search(const VeinCollideArgs& a0, cudaStream_t st)
     else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<blocks, 256, 0, st>>>(a));
     if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<true><<<148 * 8, 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<false><<<148 * 8, 256, 0, st>>>(a));
+    if (a.stats) BCS_LAUNCH("vein_masking", st, wall_masking_kernel<true><<<148 * 8, 128, 0, st>>>(a));
+    else BCS_LAUNCH("vein_masking", st, wall_masking_kernel<false><<<148 * 8, 128, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
-// phase B (masking check + the stage's effect on particle force / velocity and the wall-force splats): after the
-// particle collisions (it reads the accumulated force) and the vein spring gather (both add to the vertex forces)
+// the stage's effect on particle force / velocity and the wall-force splats: after the particle collisions (it reads
+// the accumulated force) and the vein spring gather (both add to the vertex forces)
 void launch_wall_apply(const VeinCollideArgs& a0, cudaStream_t st)
 {
     const VeinCollideArgs a = wall_args(a0);
-    if (a.stats) BCS_LAUNCH("vein_masking", st, wall_masking_kernel<true><<<148 * 8, 128, 0, st>>>(a));
-    else BCS_LAUNCH("vein_masking", st, wall_masking_kernel<false><<<148 * 8, 128, 0, st>>>(a));
+    if (a.stats) BCS_LAUNCH("vein_apply", st, wall_apply_kernel<true><<<148, 128, 0, st>>>(a));
+    else BCS_LAUNCH("vein_apply", st, wall_apply_kernel<false><<<148, 128, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
