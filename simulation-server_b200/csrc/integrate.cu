@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(128) vein_end_kernel(const IntegrateArgs a)
 // A CTA owns whole blood cells (same mapping as the spring kernel), so the "any particle of the cell"
 // reduction of handleVeinEndsBlockSync/WarpSync is a shared-memory OR.
 constexpr int FINISH_THREADS = 256;
+constexpr int FINISH_MAX_ENDINGS = 16;   // vein endings staged in shared memory (more: read from global)
 
 __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const IntegrateArgs a, const SpringPlan plan, unsigned* __restrict__ doneBlocks)
 {
@@ -107,7 +108,14 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     const TypeDev ty = a.types.t[t];
     const int nPart = nCells * ty.P;
     const int tid = threadIdx.x;
-    const unsigned long long step = a.counters->step;   // read before any block can advance it (see below)
+    const unsigned long long step = *reinterpret_cast<const volatile unsigned long long*>(&a.counters->step);   // read before any block can advance it (see below)
+    // vein endings: staged once per CTA so that their loads overlap the particle loads
+    __shared__ float sEnd[4 * FINISH_MAX_ENDINGS];
+    const int nEnd = min(ph.nEndings, FINISH_MAX_ENDINGS);
+    if (ph.useBloodFlow && threadIdx.x < nEnd) {
+        sEnd[4 * threadIdx.x] = a.endC[3 * threadIdx.x]; sEnd[4 * threadIdx.x + 1] = a.endC[3 * threadIdx.x + 1];
+        sEnd[4 * threadIdx.x + 2] = a.endC[3 * threadIdx.x + 2]; sEnd[4 * threadIdx.x + 3] = a.endR[threadIdx.x];
+    }
     if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
     __syncthreads();
     const bool mine = tid < nPart;
@@ -126,11 +134,16 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
         v = make_float4(v1.x, v1.y, v1.z, v.w);
         x = make_float4(x.x + dx.x, x.y + dx.y, x.z + dx.z, x.w);
         if (ph.useBloodFlow) {
-            if (!ty.warpSync)
-                for (int e = 0; e < ph.nEndings; ++e) {
+            if (!ty.warpSync) {
+                for (int e = 0; e < nEnd; ++e) {
+                    const float r = sEnd[4 * e + 3];
+                    out = out || length_squared(f3(x.x - sEnd[4 * e], x.y - sEnd[4 * e + 1], x.z - sEnd[4 * e + 2])) <= r * r;
+                }
+                for (int e = nEnd; e < ph.nEndings; ++e) {
                     const float r = a.endR[e];
                     out = out || length_squared(f3(x.x - a.endC[3 * e], x.y - a.endC[3 * e + 1], x.z - a.endC[3 * e + 2])) <= r * r;
                 }
+            }
             out = out || x.y <= ph.lowerY || x.y >= ph.upperY || x.x <= ph.leftX || x.x >= ph.rightX || x.z <= ph.backZ || x.z >= ph.frontZ;
         }
     }
@@ -173,10 +186,11 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
             a.moveTo[sCellId[tid]] = (signed char)target;
         }
     }
-    // the last CTA to finish advances the step counter: by then every CTA has read `step`
+    // the last CTA to finish advances the step counter: by then every CTA has read `step`.  No fence: the only thing
+    // that must be ordered is this CTA's read of `step` before its own arrival, and the arrival's operand carries a
+    // (value-neutral) dependence on the value read, so the atomic cannot issue until the load has returned.
     if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(doneBlocks, 1u) == gridDim.x - 1) {
+        if (atomicAdd(doneBlocks, 1u + (unsigned)(step >> 63)) == gridDim.x - 1) {
             *doneBlocks = 0;
             a.counters->step = step + 1;
         }

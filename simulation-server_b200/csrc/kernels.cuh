@@ -14,6 +14,9 @@ struct SortScratch {
     bool radixForCompact = false;      // BCS_GRID=radix: build the compact index from a radix sort instead
     int *keyOf = nullptr, *rankOf = nullptr, *placeOf = nullptr, *tmpIds = nullptr, *tmpRank = nullptr, *scanTotals = nullptr;
     unsigned* cellCount = nullptr;
+    unsigned long long* scanStatus = nullptr;   // single-launch scans: (epoch << 32 | tile total) per tile
+    unsigned* scanCtl = nullptr;                //                      ticket, done, epoch
+    bool twoPassScan = true;                    // tile totals + scan as two launches; BCS_SCAN=fused: one ticketed launch per scan
     int* finTileCount = nullptr;       // occupied-cell starts per finalize tile (compact index build)
     unsigned* status = nullptr;        // [4][numTiles][256] look-back status words of the onesweep passes
     bool classic = false;              // BCS_SORT=classic: 3-kernel passes (histogram, scan, scatter) instead of onesweep

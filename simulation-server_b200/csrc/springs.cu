@@ -239,11 +239,12 @@ springs_kernel(const TypesDev* __restrict__ typesDev, const SpringPlan plan, con
 
         mbar_wait(bars + s, (uint32_t)((it >> 1) & 1));
 
-        {
-            // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60): a serial sum, so the cells are dealt
-            // round-robin to the warps (lane 0 of warp 0 takes cell 0, lane 0 of warp 1 cell 1, ...)
-            const int myCell = (tid & 31) * (SPRING_THREADS / 32) + (tid >> 5);
-            if (myCell < gi.nCells) {
+        if (tid < 32) {
+            // centre = (p0 + p1 + ... ) / P in index order (blood_cells.cu:54-60): a serial sum per cell.  All cells of
+            // the group are taken by the lanes of ONE warp (dealt over the warps, every warp would issue the whole
+            // P-iteration loop for one or two active lanes); the other warps are already evaluating springs, which do
+            // not need the centres.
+            for (int myCell = tid; myCell < gi.nCells; myCell += 32) {
                 float3 c = f3(0.f, 0.f, 0.f);
                 for (int k = 0; k < P; ++k) c = c + xyz(sp[myCell * P + k]);
                 c = c / (float)P;

@@ -48,11 +48,17 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
         const int nb = nbRaw < 0 ? id : nbRaw;
         const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
         const float3 q = xyz(a.vpos[nb]);
-        // one sqrt + one set of IEEE divisions: q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q)
+        // q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q).  length() and normalize() share one reciprocal
+        // square root refined to <= 1 ulp (as in the blood-cell spring kernel, springs.cu: spring_force): the IEEE sqrt +
+        // three IEEE divisions per neighbour were ~60 % of this kernel's instructions.  Deviation <= 2 ulp per component.
         const float3 d = p - q;
-        const float len = sqrtf(dot(d, d));
-        float3 n = d / len;
-        if (isnan(n.x) || isnan(n.y) || isnan(n.z)) n = f3(0.f, 0.f, 0.f);
+        const float d2 = dot(d, d);
+        float inv = rsqrtf(d2);
+        float len = d2 * inv;
+        len = fmaf(fmaf(-len, len, d2), 0.5f * inv, len);
+        inv = fmaf(fmaf(-len, inv, 1.0f), inv, inv);
+        if (!(d2 > 0.f)) { inv = 0.f; len = 0.f; }   // absent slot / coincident vertices: normalize() yields the zero vector
+        const float3 n = f3(d.x * inv, d.y * inv, d.z * inv);
         const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
         F = F + sf * f3(-n.x, -n.y, -n.z);
     }
