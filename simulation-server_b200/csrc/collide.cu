@@ -124,24 +124,26 @@ __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, 
     const int nb = x1 - x0 + 1;
     const unsigned nbm = (1u << nb) - 1u;
     int first[9];      // first occupied cell of the row (or -1)
-    unsigned below[9]; // occupancy bits below it inside its mask word
     int nocc[9];
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-        const int dz = r / 3 - 1, dy = r % 3 - 1;
-        const int c0 = cell + dz * plane + dy * g.nx + x0;
-        const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
-        const int w0 = in ? c0 >> 5 : 0;
-        const unsigned lo = __ldg(a.cellMask + w0), hi = __ldg(a.cellMask + w0 + 1);
-        const unsigned bits = in ? __funnelshift_r(lo, hi, c0 & 31) & nbm : 0u;
-        const int f = c0 + __ffs(bits) - 1;
-        first[r] = bits ? f : -1;
-        nocc[r] = __popc(bits);
-        below[r] = ((f >> 5) == w0 ? lo : hi) & ((1u << (f & 31)) - 1u);
-    }
     int rank[9];
+    {
+        unsigned below[9]; // occupancy bits below it inside its mask word
 #pragma unroll
-    for (int r = 0; r < 9; ++r) rank[r] = __ldg(a.cellRank + (first[r] >= 0 ? first[r] >> 5 : 0)) + __popc(below[r]);
+        for (int r = 0; r < 9; ++r) {
+            const int dz = r / 3 - 1, dy = r % 3 - 1;
+            const int c0 = cell + dz * plane + dy * g.nx + x0;
+            const bool in = dz >= z0 && dz <= z1 && dy >= y0 && dy <= y1 && c0 >= 0 && c0 + nb <= g.cells;
+            const int w0 = in ? c0 >> 5 : 0;
+            const unsigned lo = __ldg(a.cellMask + w0), hi = __ldg(a.cellMask + w0 + 1);
+            const unsigned bits = in ? __funnelshift_r(lo, hi, c0 & 31) & nbm : 0u;
+            const int f = c0 + __ffs(bits) - 1;
+            first[r] = bits ? f : -1;
+            nocc[r] = __popc(bits);
+            below[r] = ((f >> 5) == w0 ? lo : hi) & ((1u << (f & 31)) - 1u);
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r) rank[r] = __ldg(a.cellRank + (first[r] >= 0 ? first[r] >> 5 : 0)) + __popc(below[r]);
+    }
     int lo[9], hi[9];
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
@@ -383,14 +385,16 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
     int myHits = 0;
     // slab mode: the active count lives on the device and ghost slots (bit 31 of the id) are candidates only
     const int nActive = a.nDev ? *a.nDev : a.n;
-    if (slot < nActive && __float_as_int(a.svel[slot].w) >= 0) {
+    // the slot's own record: all three loads issued together, before the activity test (a surplus thread reads the last slot)
+    const int ownSlot = min(slot, a.n - 1);
+    const float4 v4 = a.svel[ownSlot];
+    const float4 p4 = a.spos[ownSlot];
+    const int cell = a.keys[ownSlot];
+    if (slot < nActive && __float_as_int(v4.w) >= 0) {
         const GridDev& g = a.grid;
-        const float4 p4 = a.spos[slot];
-        const float4 v4 = a.svel[slot];
         const int tag = __float_as_int(v4.w);
         const int pid = tag & 0x7fffffff;
         const float3 p1 = xyz(p4), v1 = xyz(v4);
-        const int cell = a.keys[slot];
         int x0, x1, y0, y1, z0, z1;
         stencil_range(axis_cell_raw(p1.x, g.minx, g.csx), g.nx, x0, x1);
         stencil_range(axis_cell_raw(p1.y, g.miny, g.csy), g.ny, y0, y1);
@@ -442,9 +446,10 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
             a.dbgSum[pid] = sum;
             a.dbgHits[pid] = acc.hits;
         } else if (acc.hits) {
-            float4 f = a.frc[pid];
-            f.x += acc.F.x; f.y += acc.F.y; f.z += acc.F.z;
-            a.frc[pid] = f;
+            // F[pid] += acc: only this thread updates this particle, so the three reductions (performed in L2, no value
+            // returned - the warp does not wait for a load at its very end) give the same IEEE sum as load-add-store
+            float* f = reinterpret_cast<float*>(a.frc + pid);
+            atomicAdd(f, acc.F.x); atomicAdd(f + 1, acc.F.y); atomicAdd(f + 2, acc.F.z);
         }
         myHits = acc.hits;
     }
