@@ -130,6 +130,10 @@ struct OwnedLists {
 
 // slab mode: enumeration of this rank's ACTIVE particles (owned blood cells x particles, then the ghosts) so that the
 // per-particle kernels of the grid build and of the exchange touch N_local instead of N entries
+// Slab mode: kernels over device-side counts are launched with at most this many CTAs (8 per SM of a B200) and stride
+// over the count, so a rank's step costs O(local particles) however large the global scene is.
+constexpr int BOUNDED_BLOCKS = 148 * 8;
+
 struct ActiveItems {           // small on purpose: passed by value to streaming kernels
     const int* cells;          // null: not in slab mode (kernels index all particles)
     const int* cellPrefix;     // [n_types + 1] exclusive prefix of the owned-cell counts

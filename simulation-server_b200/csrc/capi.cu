@@ -393,6 +393,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
         a.pflag = s->slab->pflag;
         a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.lists = slab_lists(s->slab, s->types);
         a.ghostList = s->slab->ghostList; a.ghostCount = s->slab->ghostCount;
+        a.items = particle_grid_args(s).items;
     }
     return a;
 }

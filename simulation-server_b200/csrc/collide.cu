@@ -19,6 +19,8 @@
 #include "device_math.cuh"
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace bcs {
 
 __device__ __forceinline__ void stencil_range(int id, int count, int& lo, int& hi)
@@ -380,17 +382,17 @@ template <bool REFERENCE, bool DEBUG, bool STATS, bool FLAT = false, int MINB = 
 __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel(const CollideArgs a)
 {
     __shared__ int2 seg[FLAT ? 9 : 1][WALK_THREADS];
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long myTests = 0;
     int myHits = 0;
-    // slab mode: the active count lives on the device and ghost slots (bit 31 of the id) are candidates only
+    // slab mode: the active count lives on the device and ghost slots (bit 31 of the id) are candidates only; the launch
+    // is a bounded grid that strides over the count (one round without slabs: the grid covers every slot)
     const int nActive = a.nDev ? *a.nDev : a.n;
-    // the slot's own record: all three loads issued together, before the activity test (a surplus thread reads the last slot)
-    const int ownSlot = min(slot, a.n - 1);
-    const float4 v4 = a.svel[ownSlot];
-    const float4 p4 = a.spos[ownSlot];
-    const int cell = a.keys[ownSlot];
-    if (slot < nActive && __float_as_int(v4.w) >= 0) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nActive; slot += gridDim.x * blockDim.x) {
+    // the slot's own record: all three loads issued together, before the activity test
+    const float4 v4 = a.svel[slot];
+    const float4 p4 = a.spos[slot];
+    const int cell = a.keys[slot];
+    if (__float_as_int(v4.w) >= 0) {
         const GridDev& g = a.grid;
         const int tag = __float_as_int(v4.w);
         const int pid = tag & 0x7fffffff;
@@ -451,7 +453,8 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
             float* f = reinterpret_cast<float*>(a.frc + pid);
             atomicAdd(f, acc.F.x); atomicAdd(f + 1, acc.F.y); atomicAdd(f + 2, acc.F.z);
         }
-        myHits = acc.hits;
+        myHits += acc.hits;
+    }
     }
     if (STATS && !DEBUG) {
         // warp-aggregated counters
@@ -468,7 +471,8 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
 
 void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
 {
-    const int threads = WALK_THREADS, blocks = (a.n + threads - 1) / threads;
+    const int threads = WALK_THREADS, allBlocks = (a.n + threads - 1) / threads;
+    const int blocks = a.nDev ? std::min(allBlocks, 2 * BOUNDED_BLOCKS) : allBlocks;
     const bool dbg = a.dbgCount != nullptr;
     if (!a.reference && a.tiled) {
         const int tiles = (a.n + TILE - 1) / TILE;

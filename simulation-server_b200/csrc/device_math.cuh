@@ -63,6 +63,9 @@ __device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsign
 // (0,1] like curand_uniform
 __device__ __forceinline__ float u01(unsigned x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
 
+// number of items of the rank's enumeration: owned blood cells x maxP (padding included) + ghosts
+__device__ __forceinline__ int item_total(const ActiveItems& A) { return A.cellPrefix[A.types->n] * A.maxP + *A.ghostCount; }
+
 // item -> particle id (or -1 for padding / past the end); flag: 1 owned, 2 ghost
 __device__ __forceinline__ int active_item(const ActiveItems A, int item, int& flag)
 {

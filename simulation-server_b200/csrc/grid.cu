@@ -550,28 +550,34 @@ __global__ void __launch_bounds__(256) cs_mark_kernel(const float4* __restrict__
                                                       int* __restrict__ keyOf, unsigned* __restrict__ cellMask, Counters* __restrict__ counters,
                                                       const ActiveItems act)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
-    if (act.cells) {
-        i = active_item(act, i, f);
-        if (i < 0) return;
-    } else {
-        if (i >= g.n) return;
-        f = pflag ? pflag[i] : 1;
-        if (!f) return;
+    // slab mode: the active particles are enumerated through the rank's lists; the launch is a bounded grid that strides
+    // over the device-side item count, so the pass costs O(local particles) whatever the global count
+    const int total = act.cells ? item_total(act) : g.n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x, f = 1;
+        if (act.cells) {
+            if (i >= total) continue;
+            i = active_item(act, i, f);
+            if (i < 0) continue;
+        } else {
+            if (i >= g.n) continue;
+            f = pflag ? pflag[i] : 1;
+            if (!f) continue;
+        }
+        const float4 p = pos[i];
+        const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
+        int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
+                  axis_cell(p.x, g.minx, g.lenx, g.csx);
+        if (oob) {
+            if (f & 1) atomicAdd(&counters->oob, 1ull);
+            key = max(0, min(key, g.cells - 1));
+        } else if (key >= g.cells) {
+            key = g.cells - 1;
+        }
+        keyOf[i] = key;
+        const unsigned bit = 1u << (key & 31);
+        if (!(cellMask[key >> 5] & bit)) atomicOr(&cellMask[key >> 5], bit);
     }
-    const float4 p = pos[i];
-    const bool oob = p.x < g.minx || p.x > g.maxx || p.y < g.miny || p.y > g.maxy || p.z < g.minz || p.z > g.maxz;
-    int key = axis_cell(p.z, g.minz, g.lenz, g.csz) * g.nx * g.ny + axis_cell(p.y, g.miny, g.leny, g.csy) * g.nx +
-              axis_cell(p.x, g.minx, g.lenx, g.csx);
-    if (oob) {
-        if (f & 1) atomicAdd(&counters->oob, 1ull);
-        key = max(0, min(key, g.cells - 1));
-    } else if (key >= g.cells) {
-        key = g.cells - 1;
-    }
-    keyOf[i] = key;
-    const unsigned bit = 1u << (key & 31);
-    if (!(cellMask[key >> 5] & bit)) atomicOr(&cellMask[key >> 5], bit);
 }
 
 // per-tile totals of popc(mask word) (MODE 0) or of the per-cell counts (MODE 1)
@@ -773,25 +779,28 @@ __global__ void __launch_bounds__(256) cs_count_kernel(const unsigned char* __re
                                                        unsigned* __restrict__ cellCount, int* __restrict__ rankOf, int* __restrict__ placeOf,
                                                        int* __restrict__ nActive, const ActiveItems items)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool act;
-    if (items.cells) {
-        int f;
-        i = active_item(items, i, f);
-        act = i >= 0;
-    } else {
-        act = i < n && (pflag ? pflag[i] != 0 : true);
-    }
-    if (act) {
-        const int key = keyOf[i];
-        const int r = cellRank[key >> 5] + __popc(cellMask[key >> 5] & ((1u << (key & 31)) - 1u));
-        rankOf[i] = r;
-        placeOf[i] = (int)atomicAdd(&cellCount[r], 1u);
-    }
-    if (nActive) {
-        // number of active particles (slab mode): one atomic per CTA
-        const int blockActive = __syncthreads_count(act);
-        if (threadIdx.x == 0 && blockActive) atomicAdd(nActive, blockActive);
+    const int total = items.cells ? item_total(items) : n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x;
+        bool act;
+        if (items.cells) {
+            int f;
+            i = i < total ? active_item(items, i, f) : -1;
+            act = i >= 0;
+        } else {
+            act = i < n && (pflag ? pflag[i] != 0 : true);
+        }
+        if (act) {
+            const int key = keyOf[i];
+            const int r = cellRank[key >> 5] + __popc(cellMask[key >> 5] & ((1u << (key & 31)) - 1u));
+            rankOf[i] = r;
+            placeOf[i] = (int)atomicAdd(&cellCount[r], 1u);
+        }
+        if (nActive) {
+            // number of active particles (slab mode): one atomic per CTA and round
+            const int blockActive = __syncthreads_count(act);
+            if (threadIdx.x == 0 && blockActive) atomicAdd(nActive, blockActive);
+        }
     }
 }
 
@@ -799,19 +808,23 @@ __global__ void __launch_bounds__(256) cs_scatter_kernel(const unsigned char* __
                                                          const int* __restrict__ placeOf, const int* __restrict__ occStart,
                                                          int* __restrict__ tmpIds, int* __restrict__ tmpRank, const ActiveItems items)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, f = 1;
-    if (items.cells) {
-        i = active_item(items, i, f);
-        if (i < 0) return;
-    } else {
-        if (i >= n) return;
-        f = pflag ? pflag[i] : 1;
-        if (!f) return;
+    const int total = items.cells ? item_total(items) : n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x, f = 1;
+        if (items.cells) {
+            if (i >= total) continue;
+            i = active_item(items, i, f);
+            if (i < 0) continue;
+        } else {
+            if (i >= n) continue;
+            f = pflag ? pflag[i] : 1;
+            if (!f) continue;
+        }
+        const int r = rankOf[i];
+        const int slot = occStart[r] + placeOf[i];
+        tmpIds[slot] = (f & 1) ? i : (i | (int)0x80000000);   // ghost tag (slab mode)
+        tmpRank[slot] = r;
     }
-    const int r = rankOf[i];
-    const int slot = occStart[r] + placeOf[i];
-    tmpIds[slot] = (f & 1) ? i : (i | (int)0x80000000);   // ghost tag (slab mode)
-    tmpRank[slot] = r;
 }
 
 template <bool REORDER>
@@ -822,22 +835,22 @@ __global__ void __launch_bounds__(256) cs_order_kernel(int nArg, const int* __re
                                                        float4* __restrict__ svel, unsigned* __restrict__ cellCount)
 {
     const int n = nDev ? *nDev : nArg;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int r = tmpRank[j];
-    const int s = occStart[r], e = occStart[r + 1];
-    const int tag = tmpIds[j], pid = tag & 0x7fffffff;
-    int before = 0;
-    for (int k = s; k < e; ++k) before += (tmpIds[k] & 0x7fffffff) < pid;
-    const int slot = s + before;
-    const int key = keyOf[pid];
-    keys[slot] = key;
-    ids[slot] = tag;
-    if (before == 0) {
-        occKey[r] = key;
-        cellCount[r] = 0u;   // consumed by the start scan; clean for the next build (no per-step memset)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int r = tmpRank[j];
+        const int s = occStart[r], e = occStart[r + 1];
+        const int tag = tmpIds[j], pid = tag & 0x7fffffff;
+        int before = 0;
+        for (int k = s; k < e; ++k) before += (tmpIds[k] & 0x7fffffff) < pid;
+        const int slot = s + before;
+        const int key = keyOf[pid];
+        keys[slot] = key;
+        ids[slot] = tag;
+        if (before == 0) {
+            occKey[r] = key;
+            cellCount[r] = 0u;   // consumed by the start scan; clean for the next build (no per-step memset)
+        }
+        if (REORDER) reorder_slot(slot, tag, false, pos, vel, spos, svel);
     }
-    if (REORDER) reorder_slot(slot, tag, false, pos, vel, spos, svel);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -986,7 +999,8 @@ static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
     const int n = g.n, blocks = (n + 255) / 256;
     // slab mode enumerates owned cells x maxP (padding included) + ghosts: launched for that capacity, CTAs past the
     // device-side item count leave at once
-    const int itemBlocks = a.items.cells ? (int)(((long long)a.itemCapacity + 255) / 256) : blocks;
+    const int itemBlocks = a.items.cells ? (int)std::min<long long>(((long long)a.itemCapacity + 255) / 256, BOUNDED_BLOCKS) : blocks;
+    const int orderBlocks = a.nDev ? std::min(blocks, BOUNDED_BLOCKS) : blocks;
     SortScratch* sc = a.scratch;
     BCS_CUDA(cudaMemsetAsync(a.cellMask, 0, (size_t)a.maskWords * sizeof(unsigned), st));
     if (a.nDevOut) BCS_CUDA(cudaMemsetAsync(a.nDevOut, 0, sizeof(int), st));
@@ -1017,11 +1031,11 @@ static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
     BCS_LAUNCH("cell_scatter", st, cs_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, sc->rankOf, sc->placeOf, a.occStart, sc->tmpIds, sc->tmpRank, a.items));
     if (a.reorder)
         BCS_LAUNCH("finalize_grid", st,
-                   cs_order_kernel<true><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
+                   cs_order_kernel<true><<<orderBlocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
                                                                  a.pos, a.vel, a.spos, a.svel, sc->cellCount));
     else
         BCS_LAUNCH("finalize_grid", st,
-                   cs_order_kernel<false><<<blocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
+                   cs_order_kernel<false><<<orderBlocks, 256, 0, st>>>(n, a.nDev, sc->tmpIds, sc->tmpRank, a.occStart, sc->keyOf, a.keys[1], a.ids[1], a.occKey,
                                                                   nullptr, nullptr, nullptr, nullptr, sc->cellCount));
     BCS_CUDA(cudaGetLastError());
 }

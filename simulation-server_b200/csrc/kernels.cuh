@@ -203,6 +203,7 @@ struct VeinCollideArgs {
     OwnedLists lists;                   // slab mode: owned blood cells (lists.cells == null otherwise)
     const int* ghostList;               // slab mode: ghost particle ids (splat-only pass) and their count
     const int* ghostCount;
+    ActiveItems items;                  // slab mode: enumeration of the rank's owned particles + ghosts (wall filter)
     bool fast;                  // culled two-phase search (default) vs exhaustive reference-order traversal
     int liveTris;               // 1: triangles are gathered from the live vertices (tris is not refreshed per step)
     WallGridDev wall;           // wall.enabled: production path (clean semantics)

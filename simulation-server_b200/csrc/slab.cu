@@ -124,19 +124,20 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
                                                        const signed char* __restrict__ moveTo, SlabBuffers buf, int* __restrict__ ghostList,
                                                        int* __restrict__ ghostCount, int* __restrict__ errorFlag, const ActiveItems items)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // bounded grid striding over the rank's owned items (or, before the lists exist, over all particles)
+    const int total = items.cells ? items.cellPrefix[types->n] * items.maxP : n;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+    int i = item;
     if (items.cells) {
         // enumerate the owned particles through the owned-cell lists (ghost flags were expired by slab_expire_ghosts)
-        if (i >= items.cellPrefix[types->n] * items.maxP) return;
         int fl = 0;
         i = active_item(items, i, fl);
-        if (i < 0 || fl != 1) return;
+        if (i < 0 || fl != 1) continue;
     } else {
-        if (i >= n) return;
         const unsigned char f = pflag[i];
         if (!(f & 1)) {
             if (f) pflag[i] = 0;   // last step's ghost expires
-            return;
+            continue;
         }
     }
     int t;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
         pflag[i] = keep ? 2 : 0;
         if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
         if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
-        return;
+        continue;
     }
     // stays: mirror it on the neighbours whose slab it is close to
 #pragma unroll
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
         } else {
             atomicExch(errorFlag, 1);
         }
+    }
     }
 }
 
@@ -467,7 +469,7 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
     }
     const long long packItems = s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N;
     BCS_LAUNCH("slab_pack", st,
-               slab_pack_kernel<<<(int)((packItems + 255) / 256), 256, 0, st>>>(ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
+               slab_pack_kernel<<<(int)std::min<long long>((packItems + 255) / 256, BOUNDED_BLOCKS), 256, 0, st>>>(ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
                                                                                  s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
                                                                                  s->errorFlag, items));
     if (s->vertCount[0] || s->vertCount[1]) {

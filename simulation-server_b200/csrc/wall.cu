@@ -27,6 +27,8 @@
 #include "kernels.cuh"
 #include "vein_device.cuh"
 
+#include <algorithm>
+
 namespace bcs {
 
 namespace {
@@ -348,13 +350,18 @@ __global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs 
     const WallGridDev& w = a.wall;
     const GridDev& g = a.tgrid;
     const float reach = a.phys.impactNear;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    if (i == 0) *w.dirty = 0;   // consumed by this step's rebuild; the vertex integrator raises it again if needed
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *w.dirty = 0;   // consumed by this step's rebuild; the vertex integrator raises it again if needed
+    // slab mode: the rank's owned particles and ghosts, enumerated through its lists by a bounded grid (O(local particles))
+    const int total = SLAB ? item_total(a.items) : a.n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
     int pid = -1, ghost = 0;
     if (SLAB) {
-        if (i < a.n) {
-            const unsigned char f = a.pflag[i];
-            if (f) { pid = i; ghost = (f & 1) == 0; }   // ghosts only deposit their wall-force splat (owner updates the particle)
+        if (i < total) {
+            int fl = 0;
+            pid = active_item(a.items, i, fl);
+            ghost = fl == 2;   // ghosts only deposit their wall-force splat (owner updates the particle)
         }
     } else if (i < a.n) {
         pid = i;
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs 
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const unsigned candMask = __ballot_sync(0xffffffffu, pass != 0);
-    if (candMask == 0) return;
+    if (candMask == 0) continue;
     int ebase = 0;
     if (lane == 0 && total) ebase = atomicAdd(w.entryCount, total);
     ebase = __shfl_sync(0xffffffffu, ebase, 0);
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs 
         w.best[pid] = sequential ? SEQUENTIAL : NO_HIT;
         w.ghostFlag[pid] = (unsigned char)ghost;
         if (sequential) w.queue[atomicAdd(w.queueCount, 1)] = pid;   // rare: straight to phase B
+    }
     }
 }
 
@@ -618,7 +626,7 @@ void launch_wall_search(const VeinCollideArgs& a0, cudaStream_t st)
     const VeinCollideArgs a = wall_args(a0);
     BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 2 * sizeof(int), st));   // queueCount, entryCount (adjacent)
     const int blocks = (a.n + 255) / 256;
-    if (a.pflag) BCS_LAUNCH("vein_filter", st, wall_filter_kernel<true><<<blocks, 256, 0, st>>>(a));
+    if (a.pflag) BCS_LAUNCH("vein_filter", st, wall_filter_kernel<true><<<std::min(blocks, BOUNDED_BLOCKS), 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<blocks, 256, 0, st>>>(a));
     if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<true><<<148 * 8, 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<false><<<148 * 8, 256, 0, st>>>(a));
