@@ -6,6 +6,8 @@
 #include "device_math.cuh"
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace bcs {
 
 // v0 = v / gpuCount (gpuCount = 1); v1 = v0 + dt*F; x += 0.5*dt*(v1 + v0); F is left untouched
@@ -88,25 +90,6 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     __shared__ int sCellId[FINISH_THREADS];
     __shared__ float sY[FINISH_THREADS];
     const OwnedLists& lists = a.lists;
-    int t = 0, firstIdx, nCells;
-    bool active = true;
-    if (lists.cells) {
-        // slab mode: groups of this rank's owned blood cells; surplus CTAs only take part in the step-counter hand-off
-        active = (int)blockIdx.x < lists.blockStart[a.types.n];
-        if (active) {
-            while (t + 1 < a.types.n && (int)blockIdx.x >= lists.blockStart[t + 1]) ++t;
-            firstIdx = ((int)blockIdx.x - lists.blockStart[t]) * plan.cellsPerBlock[t];
-            nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
-        } else {
-            firstIdx = 0; nCells = 0;
-        }
-    } else {
-        while (t + 1 < a.types.n && (int)blockIdx.x >= plan.blockStart[t + 1]) ++t;
-        firstIdx = ((int)blockIdx.x - plan.blockStart[t]) * plan.cellsPerBlock[t];
-        nCells = min(plan.cellsPerBlock[t], a.types.t[t].count - firstIdx);
-    }
-    const TypeDev ty = a.types.t[t];
-    const int nPart = nCells * ty.P;
     const int tid = threadIdx.x;
     const unsigned long long step = *reinterpret_cast<const volatile unsigned long long*>(&a.counters->step);   // read before any block can advance it (see below)
     // vein endings: staged once per CTA so that their loads overlap the particle loads
@@ -116,6 +99,23 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
         sEnd[4 * threadIdx.x] = a.endC[3 * threadIdx.x]; sEnd[4 * threadIdx.x + 1] = a.endC[3 * threadIdx.x + 1];
         sEnd[4 * threadIdx.x + 2] = a.endC[3 * threadIdx.x + 2]; sEnd[4 * threadIdx.x + 3] = a.endR[threadIdx.x];
     }
+    // slab mode: groups of this rank's owned blood cells, taken by a bounded grid striding over the device-side group
+    // count; without slabs the grid covers every group (one round)
+    const int totalGroups = lists.cells ? lists.blockStart[a.types.n] : plan.totalBlocks;
+    for (int vb = blockIdx.x; vb < totalGroups; vb += gridDim.x) {
+    int t = 0, firstIdx, nCells;
+    if (lists.cells) {
+        while (t + 1 < a.types.n && vb >= lists.blockStart[t + 1]) ++t;
+        firstIdx = (vb - lists.blockStart[t]) * plan.cellsPerBlock[t];
+        nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
+    } else {
+        while (t + 1 < a.types.n && vb >= plan.blockStart[t + 1]) ++t;
+        firstIdx = (vb - plan.blockStart[t]) * plan.cellsPerBlock[t];
+        nCells = min(plan.cellsPerBlock[t], a.types.t[t].count - firstIdx);
+    }
+    const TypeDev ty = a.types.t[t];
+    const int nPart = nCells * ty.P;
+    __syncthreads();   // shared arrays of the previous round are free (and the staged endings are visible)
     if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
     __syncthreads();
     const bool mine = tid < nPart;
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
             a.moveTo[sCellId[tid]] = (signed char)target;
         }
     }
+    }
     // the last CTA to finish advances the step counter: by then every CTA has read `step`.  No fence: the only thing
     // that must be ordered is this CTA's read of `step` before its own arrival, and the arrival's operand carries a
     // (value-neutral) dependence on the value read, so the atomic cannot issue until the load has returned.
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
 
 void launch_finish_step(const IntegrateArgs& a, const SpringPlan& plan, unsigned* doneBlocks, cudaStream_t st)
 {
-    BCS_LAUNCH("finish_step", st, finish_step_kernel<<<plan.totalBlocks, FINISH_THREADS, 0, st>>>(a, plan, doneBlocks));
+    BCS_LAUNCH("finish_step", st, finish_step_kernel<<<a.lists.cells ? std::min(plan.totalBlocks, BOUNDED_BLOCKS) : plan.totalBlocks, FINISH_THREADS, 0, st>>>(a, plan, doneBlocks));
     BCS_CUDA(cudaGetLastError());
 }
 
