@@ -219,7 +219,8 @@ typedef enum bcs_array {
     BCS_CELL_CENTERS = 6      /* download only */
 } bcs_array;
 
-/* Host SoA -> device (n = element count of that array; pinned host memory makes the copy asynchronous). */
+/* Host SoA -> device (n = element count of that array).  Pinned host memory (bcs_host_alloc) makes the copy asynchronous:
+ * the buffers must stay untouched until the stream has passed it; pageable buffers may be reused as soon as this returns. */
 int bcs_upload(bcs_sim* sim, int array, const float* x, const float* y, const float* z, int32_t n);
 /* Device -> host SoA; returns after the data has landed. */
 int bcs_download(bcs_sim* sim, int array, float* x, float* y, float* z, int32_t n);

@@ -146,6 +146,7 @@ struct bcs_sim {
     WallGridDev wall{};             // lazily rebuilt wall grid (clean semantics; wall.enabled = 0 otherwise)
     // independent stages of a step run on forked streams (graph branches when captured): springs | wall search | vein gather
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    bool nearProbe = true;      // BCS_NO_NEAR_PROBE: the wall filter streams every particle itself
     cudaEvent_t evFork = nullptr, evSprings = nullptr, evWall = nullptr, evGather = nullptr, evMasked = nullptr, evVein = nullptr;
     bool overlap = true;
     int numSMs = 148;
@@ -343,8 +344,10 @@ void setup_wall(bcs_sim* s)
     w.overflow = s->track(dev_alloc<int>(1));
     w.barrier = s->track(dev_alloc<unsigned>(2));
     w.builds = s->track(dev_alloc<unsigned long long>(1));
-    w.queueCount = s->track(dev_alloc<int>(2));
+    w.queueCount = s->track(dev_alloc<int>(3));
     w.entryCount = w.queueCount + 1;
+    w.nearCount = w.queueCount + 2;
+    w.nearList = s->track(dev_alloc<int>((size_t)s->hs.N, false));
     cudaDeviceProp prop{};
     BCS_CUDA(cudaGetDeviceProperties(&prop, s->device));
     s->numSMs = prop.multiProcessorCount;
@@ -438,7 +441,7 @@ IntegrateArgs integrate_args(bcs_sim* s)
     return a;
 }
 
-SpringArgs spring_args(bcs_sim* s);
+SpringArgs spring_args(bcs_sim* s, bool withProbe = false);
 
 void stage(bcs_sim* s, int st)
 {
@@ -489,13 +492,17 @@ SlabCtx slab_ctx(bcs_sim* s)
     return c;
 }
 
-SpringArgs spring_args(bcs_sim* s)
+SpringArgs spring_args(bcs_sim* s, bool withProbe)
 {
     SpringArgs a{};
     a.types = s->types; a.typesDev = s->typesDev; a.plan = s->plan; a.phys = s->phys;
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
     a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
     if (s->slab) a.lists = slab_lists(s->slab, s->types);
+    if (withProbe && s->wall.enabled) {
+        const WallGridDev& w = s->wall;
+        a.probe = NearProbe{w.near, w.nearList, w.nearCount, w.ox, w.oy, w.oz, w.invh, w.nx, w.ny, w.nz};
+    }
     return a;
 }
 
@@ -507,7 +514,22 @@ void enqueue_step(bcs_sim* s)
     if (!fork) {
         // same stage order as the staged entry points; the tail (integrate particles, vein end, step counter) is one
         // fused kernel, and the vein integrator - independent of it - follows
-        for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
+        VeinCollideArgs va = vein_collide_args(s);
+        if (va.wall.enabled && s->nearProbe) {
+            // wall-grid path: the spring kernel carries the near-wall probe, so the structure is brought up to date first
+            stage(s, BCS_STAGE_GRID_PARTICLES);
+            stage(s, BCS_STAGE_GRID_TRIANGLES);
+            stage(s, BCS_STAGE_VEIN_GATHER);
+            launch_wall_reset(va, m);
+            launch_wall_rebuild(va, s->hs.V, s->numSMs, m);
+            launch_springs(spring_args(s, true), m);
+            stage(s, BCS_STAGE_PARTICLE_COLLISIONS);
+            va.wall.useNearList = 1;
+            launch_wall_search(va, m);
+            launch_wall_apply(va, m);
+        } else {
+            for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
+        }
         launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, m);
         stage(s, BCS_STAGE_INTEGRATE_VEIN);
     } else {
@@ -523,13 +545,25 @@ void enqueue_step(bcs_sim* s)
         const bool wall = va.wall.enabled != 0;
         BCS_CUDA(cudaEventRecord(s->evFork, m));
         for (int k = 0; k < 3; ++k) BCS_CUDA(cudaStreamWaitEvent(s->side[k], s->evFork, 0));
-        launch_springs(spring_args(s), s->side[0]);
-        BCS_CUDA(cudaEventRecord(s->evSprings, s->side[0]));
-        if (wall) {
-            launch_wall_rebuild(va, s->hs.V, s->numSMs, s->side[1]);
-            launch_wall_search(va, s->side[1]);
+        if (wall && s->nearProbe) {
+            // the spring kernel carries the near-wall probe of the wall search (NearProbe, kernels.cuh): structure first,
+            // then springs + probe, then the filter over the short near list, triangle tests and masking check
+            launch_wall_reset(va, s->side[0]);
+            launch_wall_rebuild(va, s->hs.V, s->numSMs, s->side[0]);
+            launch_springs(spring_args(s, true), s->side[0]);
+            BCS_CUDA(cudaEventRecord(s->evSprings, s->side[0]));
+            va.wall.useNearList = 1;
+            launch_wall_search(va, s->side[0]);
+            BCS_CUDA(cudaEventRecord(s->evWall, s->side[0]));
+        } else {
+            launch_springs(spring_args(s), s->side[0]);
+            BCS_CUDA(cudaEventRecord(s->evSprings, s->side[0]));
+            if (wall) {
+                launch_wall_rebuild(va, s->hs.V, s->numSMs, s->side[1]);
+                launch_wall_search(va, s->side[1]);
+            }
+            BCS_CUDA(cudaEventRecord(s->evWall, s->side[1]));
         }
-        BCS_CUDA(cudaEventRecord(s->evWall, s->side[1]));
         launch_vein_gather(vein_args(s), s->side[2]);
         BCS_CUDA(cudaEventRecord(s->evGather, s->side[2]));
         stage(s, BCS_STAGE_GRID_PARTICLES);
@@ -707,6 +741,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         }
         if (s->semantics == BCS_SEM_CLEAN && !getenv("BCS_NO_WALL_GRID")) setup_wall(s);
         s->overlap = !getenv("BCS_NO_OVERLAP");
+        s->nearProbe = !getenv("BCS_NO_NEAR_PROBE");
         if (s->overlap) {
             for (cudaStream_t& q : s->side) BCS_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
             for (cudaEvent_t* e : {&s->evFork, &s->evSprings, &s->evWall, &s->evGather, &s->evMasked, &s->evVein})
@@ -871,6 +906,15 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     BCS_CUDA(cudaMemcpyAsync(sz, z, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, a.ptr, n, s->types, s->collR, a.isParticlePos ? 1 : 0);
     BCS_CUDA(cudaGetLastError());
+    {
+        // Pageable host memory: the caller may reuse its buffers as soon as this returns.  The runtime stages such copies
+        // on most systems, but where the GPU can read pageable memory directly (HMM / ATS) the copy is genuinely
+        // asynchronous - so the stream is drained unless the buffers are pinned (bcs_host_alloc / cudaHostAlloc).
+        cudaPointerAttributes at{};
+        const bool pinned = cudaPointerGetAttributes(&at, x) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) BCS_CUDA(cudaStreamSynchronize(s->stream));
+    }
     if (s->slab && which == BCS_PARTICLE_POS) s->slab->primed = false;   // ownership is re-derived from the new positions
     if (s->wall.enabled && which == BCS_VEIN_POS) BCS_CUDA(cudaMemsetAsync(s->wall.dirty, 1, sizeof(int), s->stream));   // wall grid: rebuild
     if (which == BCS_VEIN_FRC) BCS_CUDA(cudaMemsetAsync(s->vsplat, 0, 3 * (size_t)s->hs.V * sizeof(long long), s->stream));   // the upload replaces parked splats too

@@ -66,6 +66,16 @@ struct SpringPlan {
     int tableInts;                       // words of the per-type table area
 };
 SpringPlan make_spring_plan(const TypesDev& types);
+// Near-wall probe carried by the spring kernel (every particle's position passes through its registers anyway): one byte
+// of the wall grid's dilated occupancy answers "can this particle reach the wall at all"; the few that can are listed
+// for the wall filter, which then never streams the other ~97 % of the particles.  near == null: disabled.
+struct NearProbe {
+    const unsigned char* near;  // [wall-grid cells]
+    int* list;                  // [N] particle ids
+    int* count;
+    float ox, oy, oz, invh;
+    int nx, ny, nz;
+};
 struct SpringArgs {
     TypesDev types;
     const TypesDev* typesDev;   // device copy of `types`
@@ -82,6 +92,7 @@ struct SpringArgs {
     const float* sprL;
     const float* initR;         // [nModel]
     OwnedLists lists;           // slab mode: owned blood cells (lists.cells == null otherwise)
+    NearProbe probe;            // probe.near == null: no probe
 };
 void launch_springs(const SpringArgs& a, cudaStream_t st);
 
@@ -149,8 +160,11 @@ struct WallGridDev {
     float margin;
     int* queue;               // [N] particles with a near hit (phase B work list)
     unsigned char* ghostFlag; // [N] slab mode: 1 = ghost (splat only); valid for candidates
-    int* queueCount;          // [2] {phase-B particles, entries}: adjacent, cleared together
+    int* queueCount;          // [3] {phase-B particles, entries, near-wall particles}: adjacent, cleared together
     int* entryCount;          // = queueCount + 1
+    int* nearCount;           // = queueCount + 2
+    int* nearList;            // [N] particles the spring kernel's probe found near the wall (this step)
+    int useNearList;          // 1: the filter reads nearList (+ the ghost list in slab mode) instead of every particle
     int2* entries;            // [entryCap] (particle, wall-grid cell) pairs whose triangles are to be tested
     int entryCap;
     unsigned long long* best; // [N] (traversal key << 32 | slot) of the first near hit; valid for candidates only
@@ -224,6 +238,7 @@ void launch_vein_collisions(const VeinCollideArgs& a, cudaStream_t st);
 // wall.cu
 void launch_wall_rebuild(const VeinCollideArgs& a, int V, int numSMs, cudaStream_t st);   // returns at once unless wall.dirty
 void launch_wall_collisions(const VeinCollideArgs& a, cudaStream_t st);   // = search + apply
+void launch_wall_reset(const VeinCollideArgs& a, cudaStream_t st);   // clears the search counters (before the spring kernel's near-wall probe)
 void launch_wall_search(const VeinCollideArgs& a, cudaStream_t st);
 void launch_wall_apply(const VeinCollideArgs& a, cudaStream_t st);
 void launch_wall_slot_info(const int* sortedTriKeys, const int* triIds, const unsigned* vidx, int T, GridDev tgrid, int4* slotInfo, int4* slotVerts,

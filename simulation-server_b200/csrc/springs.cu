@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(SPRING_THREADS, 5)
 springs_kernel(const TypesDev* __restrict__ typesDev, const SpringPlan plan, const PhysDev ph, const float4* __restrict__ pos,
                const float4* __restrict__ vel, float4* __restrict__ frc, float4* __restrict__ centers, const int* __restrict__ adjJ,
                const float* __restrict__ adjL, const int* __restrict__ adjS, const int* __restrict__ sprAB, const float* __restrict__ sprL,
-               const float* __restrict__ initR, const OwnedLists lists)
+               const float* __restrict__ initR, const OwnedLists lists, const NearProbe probe)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     float4* bpos = reinterpret_cast<float4*>(smemRaw);                     // [STAGES][THREADS]
@@ -308,6 +308,23 @@ springs_kernel(const TypesDev* __restrict__ typesDev, const SpringPlan plan, con
                 gidx = sTy.pStart + gi.firstIdx * P + tid;
             }
             frc[gidx] = make_float4(out.x, out.y, out.z, 0.f);
+            if (probe.near) {
+                // near-wall probe (NearProbe, kernels.cuh): same cell arithmetic as the wall filter (wall.cu: wall_axis)
+                const int hx = (int)fminf(fmaxf(floorf((position.x - probe.ox) * probe.invh), 0.f), (float)(probe.nx - 1));
+                const int hy = (int)fminf(fmaxf(floorf((position.y - probe.oy) * probe.invh), 0.f), (float)(probe.ny - 1));
+                const int hz = (int)fminf(fmaxf(floorf((position.z - probe.oz) * probe.invh), 0.f), (float)(probe.nz - 1));
+                const bool isNear = __ldg(probe.near + (hz * probe.ny + hy) * probe.nx + hx) != 0;
+                // warp-aggregated append
+                const unsigned active = __activemask();
+                const unsigned m = __ballot_sync(active, isNear);
+                if (m) {
+                    const int leader = __ffs(m) - 1, lane = tid & 31;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(probe.count, __popc(m));
+                    base = __shfl_sync(active, base, leader);
+                    if (isNear) probe.list[base + __popc(m & ((1u << lane) - 1u))] = gidx;
+                }
+            }
         }
         __syncthreads();   // both the tiles of stage s and sF / sc are free again
     }
@@ -337,11 +354,11 @@ void launch_springs(const SpringArgs& a, cudaStream_t st)
     if (lists)
         BCS_LAUNCH("springs", st,
                    springs_kernel<true><<<grid, SPRING_THREADS, shared, st>>>(a.typesDev, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers, a.adjJ,
-                                                                             a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.lists));
+                                                                             a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.lists, a.probe));
     else
         BCS_LAUNCH("springs", st,
                    springs_kernel<false><<<grid, SPRING_THREADS, shared, st>>>(a.typesDev, a.plan, a.phys, a.pos, a.vel, a.frc, a.centers, a.adjJ,
-                                                                              a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.lists));
+                                                                              a.adjL, a.adjS, a.sprAB, a.sprL, a.initR, a.lists, a.probe));
     BCS_CUDA(cudaGetLastError());
 }
 

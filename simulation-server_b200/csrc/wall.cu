@@ -352,12 +352,18 @@ __global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs 
     const float reach = a.phys.impactNear;
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) *w.dirty = 0;   // consumed by this step's rebuild; the vertex integrator raises it again if needed
-    // slab mode: the rank's owned particles and ghosts, enumerated through its lists by a bounded grid (O(local particles))
-    const int total = SLAB ? item_total(a.items) : a.n;
+    // Which particles: (a) the near-wall list left by the spring kernel's probe (+ the ghosts in slab mode) when the step
+    // was enqueued with the probe - the filter then never streams the bulk of the lumen; (b) slab mode: the rank's owned
+    // particles and ghosts, enumerated through its lists; (c) every particle.  Bounded grid striding over the count.
+    const int nNear = w.useNearList ? *w.nearCount : 0;
+    const int total = w.useNearList ? nNear + (SLAB ? *a.ghostCount : 0) : (SLAB ? item_total(a.items) : a.n);
     for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
     const int i = base + threadIdx.x;
     int pid = -1, ghost = 0;
-    if (SLAB) {
+    if (w.useNearList) {
+        if (i < nNear) pid = w.nearList[i];
+        else if (i < total) { pid = a.ghostList[i - nNear]; ghost = 1; }
+    } else if (SLAB) {
         if (i < total) {
             int fl = 0;
             pid = active_item(a.items, i, fl);
@@ -619,15 +625,21 @@ static VeinCollideArgs wall_args(const VeinCollideArgs& a0)
     return a;
 }
 
+void launch_wall_reset(const VeinCollideArgs& a, cudaStream_t st)
+{
+    BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 3 * sizeof(int), st));
+}
+
 // phase A (filter + triangle tests): reads particle positions / velocities and the wall only - may run beside the
 // spring and particle-collision kernels
 void launch_wall_search(const VeinCollideArgs& a0, cudaStream_t st)
 {
     const VeinCollideArgs a = wall_args(a0);
-    BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 2 * sizeof(int), st));   // queueCount, entryCount (adjacent)
+    // (with the near list the three counters were cleared before the spring kernel filled the list: launch_wall_reset)
+    if (!a.wall.useNearList) BCS_CUDA(cudaMemsetAsync(a.wall.queueCount, 0, 3 * sizeof(int), st));   // queueCount, entryCount, nearCount (adjacent)
     const int blocks = (a.n + 255) / 256;
     if (a.pflag) BCS_LAUNCH("vein_filter", st, wall_filter_kernel<true><<<std::min(blocks, BOUNDED_BLOCKS), 256, 0, st>>>(a));
-    else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<blocks, 256, 0, st>>>(a));
+    else BCS_LAUNCH("vein_filter", st, wall_filter_kernel<false><<<a.wall.useNearList ? std::min(blocks, BOUNDED_BLOCKS) : blocks, 256, 0, st>>>(a));
     if (a.stats) BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<true><<<148 * 8, 256, 0, st>>>(a));
     else BCS_LAUNCH("vein_collisions", st, wall_triangles_kernel<false><<<148 * 8, 256, 0, st>>>(a));
     if (a.stats) BCS_LAUNCH("vein_masking", st, wall_masking_kernel<true><<<148 * 8, 128, 0, st>>>(a));

@@ -68,7 +68,11 @@ def _compare_step(sim, orc, nsteps, tag):
             ta, tb = sim.cell_table(which), orc.cell_table(which)
             assert all(np.array_equal(x, y) for x, y in zip(ta, tb)), f"{tag} step {step}: cell table {which}"
         ca, cb = sim.debug_candidates(), orc.debug_candidates()
-        assert all(np.array_equal(x, y) for x, y in zip(ca, cb)), f"{tag} step {step}: candidate sets"
+        for name, x, y in zip(("count", "checksum", "hits"), ca, cb):
+            bad = np.nonzero(x != y)[0]
+            assert len(bad) == 0, (f"{tag} step {step}: candidate {name} differs for {len(bad)} particles, first {bad[:6]}: "
+                                   f"libbcs {x[bad[:6]]} oracle {y[bad[:6]]}; second evaluation libbcs {sim.debug_candidates()[('count', 'checksum', 'hits').index(name)][bad[:6]]} "
+                                   f"oracle {orc.debug_candidates()[('count', 'checksum', 'hits').index(name)][bad[:6]]}")
         ha, hb = sim.debug_vein_hits(), orc.debug_vein_hits()
         for st in (capi.STAGE_VEIN_GATHER, capi.STAGE_SPRINGS, capi.STAGE_PARTICLE_COLLISIONS):
             sim.run_stage(st); orc.run_stage(st)
