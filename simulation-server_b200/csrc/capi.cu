@@ -54,7 +54,13 @@ static T* dev_alloc(size_t count, bool zero = true)
     if (count == 0) count = 1;
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e != cudaSuccess) throw Error{BCS_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
-    if (zero) BCS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    if (zero) {
+        // cudaMemset runs on the legacy default stream and is asynchronous for device memory, while all work of a handle
+        // runs on a NON-BLOCKING stream, which does not wait for it: without this drain a kernel could write into the
+        // buffer before the zero fill lands (seen as rare zeroed debug outputs on a cold first run)
+        BCS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+        BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     return p;
 }
 template <class T>
@@ -329,6 +335,7 @@ void setup_wall(bcs_sim* s)
     w.occ3 = s->track(dev_alloc<unsigned char>((size_t)w.cells));
     w.nearTmp = s->track(dev_alloc<unsigned char>(2 * (size_t)w.cells));
     BCS_CUDA(cudaMemset(w.near, 0, (size_t)w.cells));
+    BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     w.list = s->track(dev_alloc<int>((size_t)w.cap));
     w.vposBuilt = s->track(dev_alloc<float4>(V));
     int4* info = s->track(dev_alloc<int4>(T));
@@ -362,6 +369,7 @@ void setup_wall(bcs_sim* s)
     BCS_CUDA(cudaMemset(w.barrier, 0, 2 * sizeof(unsigned)));
     BCS_CUDA(cudaMemset(w.builds, 0, sizeof(unsigned long long)));
     BCS_CUDA(cudaMemset(w.dirty, 1, sizeof(int)));
+    BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // the fills above vs this handle's non-blocking stream
     launch_wall_slot_info(s->tkeys[1], s->tids[1], s->vidx, T, s->tg, info, verts, s->stream);
     BCS_CUDA(cudaStreamSynchronize(s->stream));
     w.enabled = 1;
@@ -697,6 +705,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             s->numOcc = s->track(dev_alloc<int>(1));
             // triangle grid: dense tables, empty cell = (start 0, end -1)
             BCS_CUDA(cudaMemset(s->tcellEnd, 0xFF, (size_t)s->tg.cells * sizeof(int)));
+            BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
         } else {
             // reference semantics: dense persistent tables, zero fill = (0,0)
             s->cellStart = s->track(dev_alloc<int>(s->pg.cells)); s->cellEnd = s->track(dev_alloc<int>(s->pg.cells));
@@ -766,6 +775,9 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             in.ncclId = slabOpts->nccl_unique_id;
             s->slab = slab_create(in, hs, s->tg, s->tids[1], s->tcellStart, s->tcellEnd, slab_ctx(s));
         }
+        // set-up copies and fills ran on the legacy default stream (a pageable cudaMemcpy returns once the data is staged);
+        // the handle's own stream is non-blocking and would not wait for them
+        BCS_CUDA(cudaDeviceSynchronize());
         *out = s;
         return BCS_OK;
     } catch (const bcs::Error& e) {

@@ -972,6 +972,7 @@ void SortScratch::allocate(int n, int maskWordsHint)
         BCS_CUDA(cudaMemset(scanStatus, 0, tiles * sizeof(unsigned long long)));
         BCS_CUDA(cudaMalloc(&scanCtl, 4 * sizeof(unsigned)));
         BCS_CUDA(cudaMemset(scanCtl, 0, 4 * sizeof(unsigned)));
+        BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // legacy-stream fills vs the handle's non-blocking stream
         const char* scanMode = getenv("BCS_SCAN");
         twoPassScan = !(scanMode && std::string(scanMode) == "fused");   // measured: 2 x (totals + scan) 18 us vs 22 us fused at 1 M particles
     }

@@ -307,6 +307,7 @@ static T* salloc(SlabState* s, size_t count)
     cudaError_t e = cudaMalloc(&p, count * sizeof(T));
     if (e != cudaSuccess) throw Error{BCS_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
     BCS_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // legacy-stream fill vs the handle's non-blocking stream
     s->owned.push_back((void*)p);
     return p;
 }
