@@ -422,8 +422,6 @@ CollideArgs collide_args(bcs_sim* s)
         const char* mode = getenv("BCS_COLLIDE");
         a.tiled = mode && std::string(mode) == "tiled" && !s->sortP.radixForCompact;
         a.rows = mode && std::string(mode) == "rows";
-        const char* occ = getenv("BCS_COLLIDE_OCC");
-        a.occ = occ ? atoi(occ) : 0;
     }
     {
         int l = 0;

@@ -388,73 +388,73 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
     // is a bounded grid that strides over the count (one round without slabs: the grid covers every slot)
     const int nActive = a.nDev ? *a.nDev : a.n;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nActive; slot += gridDim.x * blockDim.x) {
-    // the slot's own record: all three loads issued together, before the activity test
-    const float4 v4 = a.svel[slot];
-    const float4 p4 = a.spos[slot];
-    const int cell = a.keys[slot];
-    if (__float_as_int(v4.w) >= 0) {
-        const GridDev& g = a.grid;
-        const int tag = __float_as_int(v4.w);
-        const int pid = tag & 0x7fffffff;
-        const float3 p1 = xyz(p4), v1 = xyz(v4);
-        int x0, x1, y0, y1, z0, z1;
-        stencil_range(axis_cell_raw(p1.x, g.minx, g.csx), g.nx, x0, x1);
-        stencil_range(axis_cell_raw(p1.y, g.miny, g.csy), g.ny, y0, y1);
-        stencil_range(axis_cell_raw(p1.z, g.minz, g.csz), g.nz, z0, z1);
+        // the slot's own record: all three loads issued together, before the activity test
+        const float4 v4 = a.svel[slot];
+        const float4 p4 = a.spos[slot];
+        const int cell = a.keys[slot];
+        if (__float_as_int(v4.w) >= 0) {
+            const GridDev& g = a.grid;
+            const int tag = __float_as_int(v4.w);
+            const int pid = tag & 0x7fffffff;
+            const float3 p1 = xyz(p4), v1 = xyz(v4);
+            int x0, x1, y0, y1, z0, z1;
+            stencil_range(axis_cell_raw(p1.x, g.minx, g.csx), g.nx, x0, x1);
+            stencil_range(axis_cell_raw(p1.y, g.miny, g.csy), g.ny, y0, y1);
+            stencil_range(axis_cell_raw(p1.z, g.minz, g.csz), g.nz, z0, z1);
 
-        // radius lookup.  Reference semantics: the type whose launch slice contains this SLOT supplies
-        // (modelStart, particlesStart, P) for BOTH particles (particle_collisions.cuh:76,124).
-        int sM = 0, sP0 = 0, sPP = 1;
-        float r1;
-        if (REFERENCE) {
-            int t = 0;
-            while (t + 1 < a.types.n && slot >= a.types.t[t + 1].pStart) ++t;
-            sM = a.types.t[t].mStart; sP0 = a.types.t[t].pStart; sPP = a.types.t[t].P;
-            r1 = __ldg(a.collR + max(0, sM + (pid - sP0) % sPP));
-        } else {
-            r1 = p4.w;
-        }
+            // radius lookup.  Reference semantics: the type whose launch slice contains this SLOT supplies
+            // (modelStart, particlesStart, P) for BOTH particles (particle_collisions.cuh:76,124).
+            int sM = 0, sP0 = 0, sPP = 1;
+            float r1;
+            if (REFERENCE) {
+                int t = 0;
+                while (t + 1 < a.types.n && slot >= a.types.t[t + 1].pStart) ++t;
+                sM = a.types.t[t].mStart; sP0 = a.types.t[t].pStart; sPP = a.types.t[t].P;
+                r1 = __ldg(a.collR + max(0, sM + (pid - sP0) % sPP));
+            } else {
+                r1 = p4.w;
+            }
 
-        PairAccum acc{f3(0.f, 0.f, 0.f), 0};
-        int cnt = 0;
-        unsigned long long sum = 0;
-        const int plane = g.nx * g.ny;
-        if (REFERENCE) {
-            for (int z = z0; z <= z1; ++z) {
-                for (int y = y0; y <= y1; ++y) {
-                    const int row = cell + z * plane + y * g.nx;
-                    // tables may hold stale ranges: every cell is scanned on its own, exactly as stored
-                    for (int x = x0; x <= x1; ++x) {
-                        const int c = row + x;
-                        if (c < 0 || c >= g.cells) continue;
-                        const int s = a.cellStart[c], e = a.cellEnd[c];
-                        for (int j = s; j <= e; ++j) {
-                            const float4 q4 = a.spos[j];
-                            const int qid = __float_as_int(q4.w);
-                            if (qid == pid) continue;
-                            if (DEBUG) { ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull; }
-                            const float r2 = __ldg(a.collR + max(0, sM + (qid - sP0) % sPP));
-                            test_pair(a.phys, p1, v1, r1, q4, r2, a.svel, j, acc);
-                            if (STATS) ++myTests;
+            PairAccum acc{f3(0.f, 0.f, 0.f), 0};
+            int cnt = 0;
+            unsigned long long sum = 0;
+            const int plane = g.nx * g.ny;
+            if (REFERENCE) {
+                for (int z = z0; z <= z1; ++z) {
+                    for (int y = y0; y <= y1; ++y) {
+                        const int row = cell + z * plane + y * g.nx;
+                        // tables may hold stale ranges: every cell is scanned on its own, exactly as stored
+                        for (int x = x0; x <= x1; ++x) {
+                            const int c = row + x;
+                            if (c < 0 || c >= g.cells) continue;
+                            const int s = a.cellStart[c], e = a.cellEnd[c];
+                            for (int j = s; j <= e; ++j) {
+                                const float4 q4 = a.spos[j];
+                                const int qid = __float_as_int(q4.w);
+                                if (qid == pid) continue;
+                                if (DEBUG) { ++cnt; sum += (unsigned long long)(qid + 1) * 0x9E3779B97F4A7C15ull; }
+                                const float r2 = __ldg(a.collR + max(0, sM + (qid - sP0) % sPP));
+                                test_pair(a.phys, p1, v1, r1, q4, r2, a.svel, j, acc);
+                                if (STATS) ++myTests;
+                            }
                         }
                     }
                 }
+            } else {
+                clean_slot_walk<DEBUG, STATS, FLAT>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests, seg);
             }
-        } else {
-            clean_slot_walk<DEBUG, STATS, FLAT>(a, slot, p1, v1, r1, cell, x0, x1, y0, y1, z0, z1, acc, cnt, sum, myTests, seg);
+            if (DEBUG) {
+                a.dbgCount[pid] = cnt;
+                a.dbgSum[pid] = sum;
+                a.dbgHits[pid] = acc.hits;
+            } else if (acc.hits) {
+                // F[pid] += acc: only this thread updates this particle, so the three reductions (performed in L2, no value
+                // returned - the warp does not wait for a load at its very end) give the same IEEE sum as load-add-store
+                float* f = reinterpret_cast<float*>(a.frc + pid);
+                atomicAdd(f, acc.F.x); atomicAdd(f + 1, acc.F.y); atomicAdd(f + 2, acc.F.z);
+            }
+            myHits += acc.hits;
         }
-        if (DEBUG) {
-            a.dbgCount[pid] = cnt;
-            a.dbgSum[pid] = sum;
-            a.dbgHits[pid] = acc.hits;
-        } else if (acc.hits) {
-            // F[pid] += acc: only this thread updates this particle, so the three reductions (performed in L2, no value
-            // returned - the warp does not wait for a load at its very end) give the same IEEE sum as load-add-store
-            float* f = reinterpret_cast<float*>(a.frc + pid);
-            atomicAdd(f, acc.F.x); atomicAdd(f + 1, acc.F.y); atomicAdd(f + 2, acc.F.z);
-        }
-        myHits += acc.hits;
-    }
     }
     if (STATS && !DEBUG) {
         // warp-aggregated counters
@@ -486,8 +486,6 @@ void launch_particle_collisions(const CollideArgs& a, cudaStream_t st)
     } else if (!a.rows) {
         if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, true, false, true><<<blocks, threads, 0, st>>>(a));
         else if (a.stats) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, true, true><<<blocks, threads, 0, st>>>(a));
-        else if (a.occ == 12) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true, 12><<<blocks, threads, 0, st>>>(a));
-        else if (a.occ == 16) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true, 16><<<blocks, threads, 0, st>>>(a));
         else BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, false, false, true><<<blocks, threads, 0, st>>>(a));
     } else {
         if (dbg) BCS_LAUNCH("particle_collisions", st, particle_collisions_kernel<false, true, false><<<blocks, threads, 0, st>>>(a));

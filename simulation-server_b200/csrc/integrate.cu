@@ -103,89 +103,89 @@ __global__ void __launch_bounds__(FINISH_THREADS) finish_step_kernel(const Integ
     // count; without slabs the grid covers every group (one round)
     const int totalGroups = lists.cells ? lists.blockStart[a.types.n] : plan.totalBlocks;
     for (int vb = blockIdx.x; vb < totalGroups; vb += gridDim.x) {
-    int t = 0, firstIdx, nCells;
-    if (lists.cells) {
-        while (t + 1 < a.types.n && vb >= lists.blockStart[t + 1]) ++t;
-        firstIdx = (vb - lists.blockStart[t]) * plan.cellsPerBlock[t];
-        nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
-    } else {
-        while (t + 1 < a.types.n && vb >= plan.blockStart[t + 1]) ++t;
-        firstIdx = (vb - plan.blockStart[t]) * plan.cellsPerBlock[t];
-        nCells = min(plan.cellsPerBlock[t], a.types.t[t].count - firstIdx);
-    }
-    const TypeDev ty = a.types.t[t];
-    const int nPart = nCells * ty.P;
-    __syncthreads();   // shared arrays of the previous round are free (and the staged endings are visible)
-    if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
-    __syncthreads();
-    const bool mine = tid < nPart;
-    const int myCell = mine ? tid / ty.P : 0;
-    const int gidx = ty.pStart + (sCellId[myCell] - ty.cStart) * ty.P + (tid - myCell * ty.P);
+        int t = 0, firstIdx, nCells;
+        if (lists.cells) {
+            while (t + 1 < a.types.n && vb >= lists.blockStart[t + 1]) ++t;
+            firstIdx = (vb - lists.blockStart[t]) * plan.cellsPerBlock[t];
+            nCells = min(plan.cellsPerBlock[t], lists.count[t] - firstIdx);
+        } else {
+            while (t + 1 < a.types.n && vb >= plan.blockStart[t + 1]) ++t;
+            firstIdx = (vb - plan.blockStart[t]) * plan.cellsPerBlock[t];
+            nCells = min(plan.cellsPerBlock[t], a.types.t[t].count - firstIdx);
+        }
+        const TypeDev ty = a.types.t[t];
+        const int nPart = nCells * ty.P;
+        __syncthreads();   // shared arrays of the previous round are free (and the staged endings are visible)
+        if (tid < nCells) sCellId[tid] = lists.cells ? lists.cells[lists.typeFirst[t] + firstIdx + tid] : ty.cStart + firstIdx + tid;
+        __syncthreads();
+        const bool mine = tid < nPart;
+        const int myCell = mine ? tid / ty.P : 0;
+        const int gidx = ty.pStart + (sCellId[myCell] - ty.cStart) * ty.P + (tid - myCell * ty.P);
 
-    float4 x = make_float4(0, 0, 0, 0), v = x;
-    bool out = false;
-    if (mine) {
-        const float4 F = a.frc[gidx];
-        v = a.vel[gidx];
-        x = a.pos[gidx];
-        const float3 v0 = f3(v.x, v.y, v.z);
-        const float3 v1 = v0 + ph.dt * xyz(F);
-        const float3 dx = (0.5f * ph.dt) * (v1 + v0);
-        v = make_float4(v1.x, v1.y, v1.z, v.w);
-        x = make_float4(x.x + dx.x, x.y + dx.y, x.z + dx.z, x.w);
-        if (ph.useBloodFlow) {
-            if (!ty.warpSync) {
-                for (int e = 0; e < nEnd; ++e) {
-                    const float r = sEnd[4 * e + 3];
-                    out = out || length_squared(f3(x.x - sEnd[4 * e], x.y - sEnd[4 * e + 1], x.z - sEnd[4 * e + 2])) <= r * r;
+        float4 x = make_float4(0, 0, 0, 0), v = x;
+        bool out = false;
+        if (mine) {
+            const float4 F = a.frc[gidx];
+            v = a.vel[gidx];
+            x = a.pos[gidx];
+            const float3 v0 = f3(v.x, v.y, v.z);
+            const float3 v1 = v0 + ph.dt * xyz(F);
+            const float3 dx = (0.5f * ph.dt) * (v1 + v0);
+            v = make_float4(v1.x, v1.y, v1.z, v.w);
+            x = make_float4(x.x + dx.x, x.y + dx.y, x.z + dx.z, x.w);
+            if (ph.useBloodFlow) {
+                if (!ty.warpSync) {
+                    for (int e = 0; e < nEnd; ++e) {
+                        const float r = sEnd[4 * e + 3];
+                        out = out || length_squared(f3(x.x - sEnd[4 * e], x.y - sEnd[4 * e + 1], x.z - sEnd[4 * e + 2])) <= r * r;
+                    }
+                    for (int e = nEnd; e < ph.nEndings; ++e) {
+                        const float r = a.endR[e];
+                        out = out || length_squared(f3(x.x - a.endC[3 * e], x.y - a.endC[3 * e + 1], x.z - a.endC[3 * e + 2])) <= r * r;
+                    }
                 }
-                for (int e = nEnd; e < ph.nEndings; ++e) {
-                    const float r = a.endR[e];
-                    out = out || length_squared(f3(x.x - a.endC[3 * e], x.y - a.endC[3 * e + 1], x.z - a.endC[3 * e + 2])) <= r * r;
-                }
+                out = out || x.y <= ph.lowerY || x.y >= ph.upperY || x.x <= ph.leftX || x.x >= ph.rightX || x.z <= ph.backZ || x.z >= ph.frontZ;
             }
-            out = out || x.y <= ph.lowerY || x.y >= ph.upperY || x.x <= ph.leftX || x.x >= ph.rightX || x.z <= ph.backZ || x.z >= ph.frontZ;
         }
-    }
-    sOut[tid] = out ? 1 : 0;
-    __syncthreads();
-    if (tid < nCells) {
-        int any = 0;
-        for (int k = 0; k < ty.P; ++k) any |= sOut[tid * ty.P + k];
-        sCell[tid] = any;
-        if (any) atomicAdd(&a.counters->teleported, 1ull);
-    }
-    __syncthreads();
-    if (mine) {
-        const int cell = tid / ty.P, k = tid - cell * ty.P;
-        if (sCell[cell]) {
-            unsigned ctr[4] = {(unsigned)sCellId[cell], (unsigned)step, (unsigned)(step >> 32), 0u};
-            philox4x32_10(ctr, (unsigned)a.seed, (unsigned)(a.seed >> 32));
-            const float u1 = u01(ctr[0]), u2 = u01(ctr[1]);
-            const float bx = (u1 - 0.5f) * 1.2f * ph.cylinder_radius, bz = (u2 - 0.5f) * 1.2f * ph.cylinder_radius;
-            x = make_float4(bx + a.mx[ty.mStart + k] - a.mx[ty.mStart], ph.min_spawn_y + a.my[ty.mStart + k] - a.my[ty.mStart],
-                            bz + a.mz[ty.mStart + k] - a.mz[ty.mStart], x.w);
-            v = make_float4(ph.initvx, ph.initvy, ph.initvz, v.w);
-        }
-        a.pos[gidx] = x;
-        a.vel[gidx] = v;
-    }
-    if (a.slab.enabled) {
-        // ownership follows the blood cell's centre: which slab does it lie in after this step?
-        sY[tid] = x.y;
+        sOut[tid] = out ? 1 : 0;
         __syncthreads();
         if (tid < nCells) {
-            float cy = 0.f;
-            for (int k = 0; k < ty.P; ++k) cy += sY[tid * ty.P + k];
-            cy /= (float)ty.P;
-            int target = -1;
-            if (sCell[tid]) target = a.slab.spawnRank;                               // respawned at the top of the vein
-            else if (cy >= a.slab.yHi && a.slab.rank > 0) target = a.slab.rank - 1;
-            else if (cy < a.slab.yLo && a.slab.rank < a.slab.world - 1) target = a.slab.rank + 1;
-            if (target == a.slab.rank) target = -1;
-            a.moveTo[sCellId[tid]] = (signed char)target;
+            int any = 0;
+            for (int k = 0; k < ty.P; ++k) any |= sOut[tid * ty.P + k];
+            sCell[tid] = any;
+            if (any) atomicAdd(&a.counters->teleported, 1ull);
         }
-    }
+        __syncthreads();
+        if (mine) {
+            const int cell = tid / ty.P, k = tid - cell * ty.P;
+            if (sCell[cell]) {
+                unsigned ctr[4] = {(unsigned)sCellId[cell], (unsigned)step, (unsigned)(step >> 32), 0u};
+                philox4x32_10(ctr, (unsigned)a.seed, (unsigned)(a.seed >> 32));
+                const float u1 = u01(ctr[0]), u2 = u01(ctr[1]);
+                const float bx = (u1 - 0.5f) * 1.2f * ph.cylinder_radius, bz = (u2 - 0.5f) * 1.2f * ph.cylinder_radius;
+                x = make_float4(bx + a.mx[ty.mStart + k] - a.mx[ty.mStart], ph.min_spawn_y + a.my[ty.mStart + k] - a.my[ty.mStart],
+                                bz + a.mz[ty.mStart + k] - a.mz[ty.mStart], x.w);
+                v = make_float4(ph.initvx, ph.initvy, ph.initvz, v.w);
+            }
+            a.pos[gidx] = x;
+            a.vel[gidx] = v;
+        }
+        if (a.slab.enabled) {
+            // ownership follows the blood cell's centre: which slab does it lie in after this step?
+            sY[tid] = x.y;
+            __syncthreads();
+            if (tid < nCells) {
+                float cy = 0.f;
+                for (int k = 0; k < ty.P; ++k) cy += sY[tid * ty.P + k];
+                cy /= (float)ty.P;
+                int target = -1;
+                if (sCell[tid]) target = a.slab.spawnRank;                               // respawned at the top of the vein
+                else if (cy >= a.slab.yHi && a.slab.rank > 0) target = a.slab.rank - 1;
+                else if (cy < a.slab.yLo && a.slab.rank < a.slab.world - 1) target = a.slab.rank + 1;
+                if (target == a.slab.rank) target = -1;
+                a.moveTo[sCellId[tid]] = (signed char)target;
+            }
+        }
     }
     // the last CTA to finish advances the step counter: by then every CTA has read `step`.  No fence: the only thing
     // that must be ordered is this CTA's read of `step` before its own arrival, and the arrival's operand carries a

@@ -111,7 +111,6 @@ struct CollideArgs {
     const unsigned* cellMask;   // compact cell index (clean semantics), see grid.cu
     const int* cellRank;
     const int* occStart;
-    int occ;                    // BCS_COLLIDE_OCC: minimum resident CTAs per SM the kernel is compiled for (register cap)
     bool rows;                  // BCS_COLLIDE=rows: row-after-row candidate walk instead of the flattened one
     bool tiled;                 // shared-memory tiled kernel (needs the counting-sort grid: cellRank is a full prefix there)
     unsigned long long nxMagic; // exact division by grid.nx: q = (n * nxMagic) >> nxShift

@@ -127,57 +127,57 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
     // bounded grid striding over the rank's owned items (or, before the lists exist, over all particles)
     const int total = items.cells ? items.cellPrefix[types->n] * items.maxP : n;
     for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
-    int i = item;
-    if (items.cells) {
-        // enumerate the owned particles through the owned-cell lists (ghost flags were expired by slab_expire_ghosts)
-        int fl = 0;
-        i = active_item(items, i, fl);
-        if (i < 0 || fl != 1) continue;
-    } else {
-        const unsigned char f = pflag[i];
-        if (!(f & 1)) {
-            if (f) pflag[i] = 0;   // last step's ghost expires
+        int i = item;
+        if (items.cells) {
+            // enumerate the owned particles through the owned-cell lists (ghost flags were expired by slab_expire_ghosts)
+            int fl = 0;
+            i = active_item(items, i, fl);
+            if (i < 0 || fl != 1) continue;
+        } else {
+            const unsigned char f = pflag[i];
+            if (!(f & 1)) {
+                if (f) pflag[i] = 0;   // last step's ghost expires
+                continue;
+            }
+        }
+        int t;
+        const int c = cell_of_particle(types, i, &t);
+        const int target = moveTo[c];
+        const float4 p = pos[i], v = vel[i];
+        if (target >= 0) {
+            // the blood cell leaves: full state goes to its new owner
+            const int d = dest_of(slab, target);
+            const int k = atomicAdd(&buf.send[d]->nMig, 1);
+            if (k < buf.capMig) {
+                MigRecord r;
+                r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z;
+                const float4 F = frc[i];
+                r.fx = F.x; r.fy = F.y; r.fz = F.z;
+                buf.mig[d][k] = r;
+            } else {
+                atomicExch(errorFlag, 1);
+            }
+            // on this side its particles stay around as ghosts for the next step if they are near the face they crossed
+            const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth) || (d == 1 && p.y < slab.yLo + slab.haloWidth);
+            pflag[i] = keep ? 2 : 0;
+            if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
+            if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
             continue;
         }
-    }
-    int t;
-    const int c = cell_of_particle(types, i, &t);
-    const int target = moveTo[c];
-    const float4 p = pos[i], v = vel[i];
-    if (target >= 0) {
-        // the blood cell leaves: full state goes to its new owner
-        const int d = dest_of(slab, target);
-        const int k = atomicAdd(&buf.send[d]->nMig, 1);
-        if (k < buf.capMig) {
-            MigRecord r;
-            r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z;
-            const float4 F = frc[i];
-            r.fx = F.x; r.fy = F.y; r.fz = F.z;
-            buf.mig[d][k] = r;
-        } else {
-            atomicExch(errorFlag, 1);
-        }
-        // on this side its particles stay around as ghosts for the next step if they are near the face they crossed
-        const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth) || (d == 1 && p.y < slab.yLo + slab.haloWidth);
-        pflag[i] = keep ? 2 : 0;
-        if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
-        if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
-        continue;
-    }
-    // stays: mirror it on the neighbours whose slab it is close to
+        // stays: mirror it on the neighbours whose slab it is close to
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-        const bool near = d == 0 ? (slab.rank > 0 && p.y >= slab.yHi - slab.haloWidth) : (slab.rank < slab.world - 1 && p.y < slab.yLo + slab.haloWidth);
-        if (!near) continue;
-        const int k = atomicAdd(&buf.send[d]->nHalo, 1);
-        if (k < buf.capHalo) {
-            HaloRecord r;
-            r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z; r.pad = 0.f;
-            buf.halo[d][k] = r;
-        } else {
-            atomicExch(errorFlag, 1);
+        for (int d = 0; d < 2; ++d) {
+            const bool near = d == 0 ? (slab.rank > 0 && p.y >= slab.yHi - slab.haloWidth) : (slab.rank < slab.world - 1 && p.y < slab.yLo + slab.haloWidth);
+            if (!near) continue;
+            const int k = atomicAdd(&buf.send[d]->nHalo, 1);
+            if (k < buf.capHalo) {
+                HaloRecord r;
+                r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z; r.pad = 0.f;
+                buf.halo[d][k] = r;
+            } else {
+                atomicExch(errorFlag, 1);
+            }
         }
-    }
     }
 }
 

@@ -358,93 +358,93 @@ __global__ void __launch_bounds__(256) wall_filter_kernel(const VeinCollideArgs 
     const int nNear = w.useNearList ? *w.nearCount : 0;
     const int total = w.useNearList ? nNear + (SLAB ? *a.ghostCount : 0) : (SLAB ? item_total(a.items) : a.n);
     for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
-    const int i = base + threadIdx.x;
-    int pid = -1, ghost = 0;
-    if (w.useNearList) {
-        if (i < nNear) pid = w.nearList[i];
-        else if (i < total) { pid = a.ghostList[i - nNear]; ghost = 1; }
-    } else if (SLAB) {
-        if (i < total) {
-            int fl = 0;
-            pid = active_item(a.items, i, fl);
-            ghost = fl == 2;   // ghosts only deposit their wall-force splat (owner updates the particle)
+        const int i = base + threadIdx.x;
+        int pid = -1, ghost = 0;
+        if (w.useNearList) {
+            if (i < nNear) pid = w.nearList[i];
+            else if (i < total) { pid = a.ghostList[i - nNear]; ghost = 1; }
+        } else if (SLAB) {
+            if (i < total) {
+                int fl = 0;
+                pid = active_item(a.items, i, fl);
+                ghost = fl == 2;   // ghosts only deposit their wall-force splat (owner updates the particle)
+            }
+        } else if (i < a.n) {
+            pid = i;
         }
-    } else if (i < a.n) {
-        pid = i;
-    }
-    unsigned pass = 0;          // bit b: cell (b%3, (b/3)%3, b/9) of the segment's box passed the slab test
-    int wx0 = 0, wy0 = 0, wz0 = 0;
-    bool sequential = false;
-    if (pid >= 0) {
-        const float4 p4 = a.pos[pid], v4 = a.vel[pid];
-        const float3 pos = xyz(p4);
-        // one byte answers "can this particle reach the wall at all": its own cell +-2 holds no triangle -> done
-        const int hx = wall_axis(pos.x, w.ox, w.invh, w.nx), hy = wall_axis(pos.y, w.oy, w.invh, w.ny), hz = wall_axis(pos.z, w.oz, w.invh, w.nz);
-        if (__ldg(w.near + (hz * w.ny + hy) * w.nx + hx)) {
-            const float3 dir = normalize(xyz(v4));
-            const float3 tip = pos + reach * dir;
-            constexpr float EPSB = 1e-3f;
-            wx0 = wall_axis(fminf(pos.x, tip.x) - EPSB, w.ox, w.invh, w.nx);
-            wy0 = wall_axis(fminf(pos.y, tip.y) - EPSB, w.oy, w.invh, w.ny);
-            wz0 = wall_axis(fminf(pos.z, tip.z) - EPSB, w.oz, w.invh, w.nz);
-            const int wx1 = wall_axis(fmaxf(pos.x, tip.x) + EPSB, w.ox, w.invh, w.nx);
-            const int wy1 = wall_axis(fmaxf(pos.y, tip.y) + EPSB, w.oy, w.invh, w.ny);
-            const int wz1 = wall_axis(fmaxf(pos.z, tip.z) + EPSB, w.oz, w.invh, w.nz);
-            // reach <= 2 cells: the box spans at most 3 cells per axis.  Occupancy of all of them, branch-free: one byte
-            // per (y,z) row holds the bits of its three x-adjacent cells.
-            unsigned occ = 0;
-            const unsigned xmask = (1u << (wx1 - wx0 + 1)) - 1u;
+        unsigned pass = 0;          // bit b: cell (b%3, (b/3)%3, b/9) of the segment's box passed the slab test
+        int wx0 = 0, wy0 = 0, wz0 = 0;
+        bool sequential = false;
+        if (pid >= 0) {
+            const float4 p4 = a.pos[pid], v4 = a.vel[pid];
+            const float3 pos = xyz(p4);
+            // one byte answers "can this particle reach the wall at all": its own cell +-2 holds no triangle -> done
+            const int hx = wall_axis(pos.x, w.ox, w.invh, w.nx), hy = wall_axis(pos.y, w.oy, w.invh, w.ny), hz = wall_axis(pos.z, w.oz, w.invh, w.nz);
+            if (__ldg(w.near + (hz * w.ny + hy) * w.nx + hx)) {
+                const float3 dir = normalize(xyz(v4));
+                const float3 tip = pos + reach * dir;
+                constexpr float EPSB = 1e-3f;
+                wx0 = wall_axis(fminf(pos.x, tip.x) - EPSB, w.ox, w.invh, w.nx);
+                wy0 = wall_axis(fminf(pos.y, tip.y) - EPSB, w.oy, w.invh, w.ny);
+                wz0 = wall_axis(fminf(pos.z, tip.z) - EPSB, w.oz, w.invh, w.nz);
+                const int wx1 = wall_axis(fmaxf(pos.x, tip.x) + EPSB, w.ox, w.invh, w.nx);
+                const int wy1 = wall_axis(fmaxf(pos.y, tip.y) + EPSB, w.oy, w.invh, w.ny);
+                const int wz1 = wall_axis(fmaxf(pos.z, tip.z) + EPSB, w.oz, w.invh, w.nz);
+                // reach <= 2 cells: the box spans at most 3 cells per axis.  Occupancy of all of them, branch-free: one byte
+                // per (y,z) row holds the bits of its three x-adjacent cells.
+                unsigned occ = 0;
+                const unsigned xmask = (1u << (wx1 - wx0 + 1)) - 1u;
 #pragma unroll
-            for (int r = 0; r < 9; ++r) {
-                const int y = wy0 + r % 3, z = wz0 + r / 3;
-                const bool in = y <= wy1 && z <= wz1;
-                const unsigned bits = __ldg(w.occ3 + (in ? (z * w.ny + y) * w.nx + wx0 : 0));
-                occ |= in ? (bits & xmask) << (3 * r) : 0u;
-            }
-            while (occ) {
-                const int b = __ffs(occ) - 1;
-                occ &= occ - 1;
-                const int c = ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3;
-                const int4 r0 = __ldg(w.rec + 2 * c), r1 = __ldg(w.rec + 2 * c + 1);
-                const CellSlab sl{__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y), __int_as_float(r1.z)};
-                if (slab_segment(sl, pos, dir, reach)) pass |= 1u << b;
-            }
-            if (pass) {
-                const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
-                          pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
-                sequential = pcx >= g.nx || pcy >= g.ny || pcz >= g.nz;   // outside the triangle grid
+                for (int r = 0; r < 9; ++r) {
+                    const int y = wy0 + r % 3, z = wz0 + r / 3;
+                    const bool in = y <= wy1 && z <= wz1;
+                    const unsigned bits = __ldg(w.occ3 + (in ? (z * w.ny + y) * w.nx + wx0 : 0));
+                    occ |= in ? (bits & xmask) << (3 * r) : 0u;
+                }
+                while (occ) {
+                    const int b = __ffs(occ) - 1;
+                    occ &= occ - 1;
+                    const int c = ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3;
+                    const int4 r0 = __ldg(w.rec + 2 * c), r1 = __ldg(w.rec + 2 * c + 1);
+                    const CellSlab sl{__int_as_float(r0.z), __int_as_float(r0.w), __int_as_float(r1.x), __int_as_float(r1.y), __int_as_float(r1.z)};
+                    if (slab_segment(sl, pos, dir, reach)) pass |= 1u << b;
+                }
+                if (pass) {
+                    const int pcx = axis_cell(pos.x, g.minx, g.lenx, g.csx), pcy = axis_cell(pos.y, g.miny, g.leny, g.csy),
+                              pcz = axis_cell(pos.z, g.minz, g.lenz, g.csz);
+                    sequential = pcx >= g.nx || pcy >= g.ny || pcz >= g.nz;   // outside the triangle grid
+                }
             }
         }
-    }
-    // warp-aggregated append: entries, then candidates
-    const int mine = sequential ? 0 : __popc(pass);
-    int incl = mine;
+        // warp-aggregated append: entries, then candidates
+        const int mine = sequential ? 0 : __popc(pass);
+        int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned candMask = __ballot_sync(0xffffffffu, pass != 0);
-    if (candMask == 0) continue;
-    int ebase = 0;
-    if (lane == 0 && total) ebase = atomicAdd(w.entryCount, total);
-    ebase = __shfl_sync(0xffffffffu, ebase, 0);
-    if (pass) {
-        int at = ebase + incl - mine;
-        if (!sequential && at + mine > w.entryCap) sequential = true;   // queue full: this particle searches sequentially
-        if (!sequential) {
-            unsigned m = pass;
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                w.entries[at++] = make_int2(pid, ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3);
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
-        w.best[pid] = sequential ? SEQUENTIAL : NO_HIT;
-        w.ghostFlag[pid] = (unsigned char)ghost;
-        if (sequential) w.queue[atomicAdd(w.queueCount, 1)] = pid;   // rare: straight to phase B
-    }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned candMask = __ballot_sync(0xffffffffu, pass != 0);
+        if (candMask == 0) continue;
+        int ebase = 0;
+        if (lane == 0 && total) ebase = atomicAdd(w.entryCount, total);
+        ebase = __shfl_sync(0xffffffffu, ebase, 0);
+        if (pass) {
+            int at = ebase + incl - mine;
+            if (!sequential && at + mine > w.entryCap) sequential = true;   // queue full: this particle searches sequentially
+            if (!sequential) {
+                unsigned m = pass;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    w.entries[at++] = make_int2(pid, ((wz0 + b / 9) * w.ny + wy0 + (b / 3) % 3) * w.nx + wx0 + b % 3);
+                }
+            }
+            w.best[pid] = sequential ? SEQUENTIAL : NO_HIT;
+            w.ghostFlag[pid] = (unsigned char)ghost;
+            if (sequential) w.queue[atomicAdd(w.queueCount, 1)] = pid;   // rare: straight to phase B
+        }
     }
 }
 
