@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Pretty-print a bench.py JSON line (per-kernel table + roofline)."""
-import json, sys
+import json, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 for l in open(sys.argv[1]):
     if not l.startswith('{'): continue
     d = json.loads(l)
