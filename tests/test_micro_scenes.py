@@ -1,0 +1,225 @@
+"""Hand-built micro-scenes: small enough to state the expected result in closed form.
+
+CPU (`-m "not gpu"`): the oracle against numpy restatements of the reference formulas - one blood cell at rest
+(blood_cells.cu:66-120), two particles touching across a grid-cell boundary (physics.cuh:133-145), particles at the
+faces / edges / corners of the grid for the 27 stencil specialisations (particle_collisions.cuh:126-268), empty and
+single-occupant neighbourhoods.  GPU (`-m gpu`): libbcs, through its C ABI, against the oracle on the same scenes, plus
+ray / wall cases (towards the wall, parallel to it, away from it, outside the vein)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import refcheck
+from conftest import capi, make_bcs, make_oracle, pkg
+
+EDGE = 3.0                       # tetrahedron edge = rest length of its six springs; collision radius = EDGE / 6 = 0.5
+RADIUS = EDGE / 6.0
+
+
+def tetra_def(count):
+    v = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], np.float64) * (EDGE / (2.0 * np.sqrt(2.0)))
+    springs = np.array(list(itertools.combinations(range(4), 2)), np.int32)
+    return pkg.CellDef(count, 4, springs, np.full(len(springs), EDGE, np.float32), v.astype(np.float32))
+
+
+def micro_scene(count, use_blood_flow=0):
+    vp, vi, ec, er = pkg.make_cylinder_vein(length=150.0)
+    sc = pkg.Scene(user_defs=[tetra_def(count)], vein_pos=vp, vein_indices=vi, ending_centers=ec, ending_radii=er)
+    sc.flags["use_blood_flow"] = use_blood_flow
+    return sc
+
+
+def state_from(sc, centres, velocities=None):
+    """every blood cell = its model translated to `centres[c]`, moving with `velocities[c]`, zero force"""
+    lay = sc.layout()
+    model = lay.model[:4]
+    centres = np.asarray(centres, np.float32)
+    vel = np.zeros_like(centres) if velocities is None else np.asarray(velocities, np.float32)
+    pos = (centres[:, None, :] + model[None, :, :]).reshape(-1, 3)
+    v = np.repeat(vel, 4, axis=0)
+    z = np.zeros(len(pos), np.float32)
+    return {"pos_x": pos[:, 0].copy(), "pos_y": pos[:, 1].copy(), "pos_z": pos[:, 2].copy(),
+            "vel_x": v[:, 0].copy(), "vel_y": v[:, 1].copy(), "vel_z": v[:, 2].copy(),
+            "frc_x": z.copy(), "frc_y": z.copy(), "frc_z": z.copy()}
+
+
+def run_stages(sim, st, stages):
+    sim.upload_state(st)
+    for s in stages:
+        sim.run_stage(s)
+
+
+# ------------------------------------------------------------------------------------------------ closed forms
+def expected_collision_force(ph, p1, v1, r1, p2, v2, r2):
+    """physics::addResilientForceOnCollision with intensity 0.5 for the particle at p1 (physics.cuh:133-145), float64"""
+    rel = p1 - p2
+    d = np.linalg.norm(rel)
+    assert 1e-2 <= d <= r1 + r2
+    dirv = rel / d
+    rv = v1 - v2
+    tang = rv - np.dot(rv, dirv) * dirv
+    return 0.5 * (-ph["collision_spring_coeff"] * (2.0 * r1 - d) * dirv + ph["collision_damping_coeff"] * rv
+                  + ph["collision_shear_coeff"] * tang)
+
+
+def brute_force_candidates(pos, lay_min, cell_size, dims):
+    """candidate count per particle by the reference's stencil rule (particle_collisions.cuh:117-268): per axis the
+    neighbours are {0,+1} if the (unclamped) cell index is < 1, {-1,0} if it is > count-2, else {-1,0,+1}"""
+    idx = np.floor((pos.astype(np.float32) - lay_min.astype(np.float32)) / np.float32(cell_size)).astype(np.int64)
+    n = len(pos)
+    cnt = np.zeros(n, np.int64)
+    for i in range(n):
+        ok = np.ones(n, bool)
+        for a in range(3):
+            c = idx[i, a]
+            lo, hi = (0, 1) if c < 1 else ((-1, 0) if c > dims[a] - 2 else (-1, 1))
+            d = idx[:, a] - c
+            ok &= (d >= lo) & (d <= hi)
+        ok[i] = False
+        cnt[i] = ok.sum()
+    return cnt
+
+
+# ------------------------------------------------------------------------------------------------ scenes
+def scene_cell_at_rest():
+    sc = micro_scene(1)
+    return sc, state_from(sc, [[3.0, -61.0, -7.0]])
+
+
+def scene_touching_pair():
+    """two blood cells; particle 1 of the second one sits 0.8 from particle 0 of the first, on the other side of a
+    grid-cell boundary (cells are 2 units wide: x = 0 is a cell face of the r = 50 vein's grid, margins are even); all
+    other pairs of the two translated tetrahedra are >= 3 apart"""
+    sc = micro_scene(2)
+    lay = sc.layout()
+    m0, m1 = lay.model[0].astype(np.float64), lay.model[1].astype(np.float64)
+    a = np.array([-0.3, -60.5, 0.5]) - m0            # particle 0 of cell 0 lands at (-0.3, -60.5, 0.5)
+    b = np.array([0.5, -60.5, 0.5]) - m1             # particle 1 of cell 1 lands at ( 0.5, -60.5, 0.5): 0.8 apart
+    return sc, state_from(sc, [a, b], [[4.0, -70.0, 1.0], [-3.0, -64.0, 0.0]])
+
+
+def scene_grid_boundaries():
+    """blood cells centred in the corner / edge / face cells of the particle grid and one deep inside; the last two
+    share a neighbourhood so that non-empty candidate sets appear as well"""
+    sc = micro_scene(10)
+    lay = sc.layout()
+    lo, hi = np.asarray(lay.grid_min, np.float64), np.asarray(lay.grid_max, np.float64)
+    mid = 0.5 * (lo + hi)
+    inset = 1.4          # model half-extent is 1.06: every particle stays inside the grid, some in the outermost cells
+    pts = [
+        [lo[0] + inset, lo[1] + inset, lo[2] + inset],      # corner (min, min, min)
+        [hi[0] - inset, hi[1] - inset, hi[2] - inset],      # corner (max, max, max)
+        [lo[0] + inset, hi[1] - inset, mid[2]],             # edge
+        [mid[0], lo[1] + inset, hi[2] - inset],             # edge
+        [lo[0] + inset, mid[1], mid[2]],                    # face x-
+        [hi[0] - inset, mid[1], mid[2]],                    # face x+
+        [mid[0], hi[1] - inset, mid[2]],                    # face y+
+        [mid[0], mid[1], lo[2] + inset],                    # face z-
+        [mid[0], mid[1], mid[2]],                           # interior
+        [mid[0] + 1.7, mid[1] + 0.4, mid[2] - 0.9],         # interior, interleaved with the previous one
+    ]
+    return sc, state_from(sc, pts)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle vs closed form
+def test_oracle_cell_at_rest_feels_only_gravity(oracle_lib):
+    sc, st = scene_cell_at_rest()
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_GRID_PARTICLES, capi.STAGE_SPRINGS])
+        F = refcheck.down(orc, capi.PARTICLE_FRC)
+        ph = sc.physics
+        want = 0.5 * np.array([ph["gx"], ph["gy"], ph["gz"]])       # F <- (F_old + F_new) / 2, springs at rest, v = 0
+        assert np.abs(F - want).max() < 2e-3, F                      # rest lengths are met to float rounding: |(len-L) k| ~ 1e-4
+        c = np.stack(orc.download(capi.CELL_CENTERS), 1)
+        assert np.allclose(c[0], [3.0, -61.0, -7.0], atol=1e-5)
+
+
+def test_oracle_touching_pair_matches_the_closed_form(oracle_lib):
+    sc, st = scene_touching_pair()
+    pos = np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1).astype(np.float64)
+    vel = np.stack([st["vel_x"], st["vel_y"], st["vel_z"]], 1).astype(np.float64)
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=2) + 10.0 * np.eye(8)
+    touching = np.argwhere(d <= 2 * RADIUS)
+    assert sorted(map(tuple, touching)) == [(0, 5), (5, 0)], "exactly one pair within reach, by construction"
+    assert int(np.floor(pos[0, 0] / 2.0)) != int(np.floor(pos[5, 0] / 2.0)), "the pair straddles a grid-cell face"
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_GRID_PARTICLES])
+        cnt, _, hits = orc.debug_candidates()
+        assert hits.tolist() == [1, 0, 0, 0, 0, 1, 0, 0]
+        assert cnt[0] >= 4 and cnt[5] >= 4                           # own blood cell (3) + at least the partner
+        orc.run_stage(capi.STAGE_PARTICLE_COLLISIONS)
+        F = refcheck.down(orc, capi.PARTICLE_FRC).astype(np.float64)
+    r = float(RADIUS)
+    want0 = expected_collision_force(sc.physics, pos[0], vel[0], r, pos[5], vel[5], r)
+    want5 = expected_collision_force(sc.physics, pos[5], vel[5], r, pos[0], vel[0], r)
+    assert np.abs(F[0] - want0).max() < 1e-4 * np.abs(want0).max(), (F[0], want0)
+    assert np.abs(F[5] - want5).max() < 1e-4 * np.abs(want5).max(), (F[5], want5)
+    assert np.abs(F[[1, 2, 3, 4, 6, 7]]).max() == 0.0               # nobody else is touched (forces start at zero)
+
+
+def test_oracle_stencils_at_the_grid_boundaries(oracle_lib):
+    sc, st = scene_grid_boundaries()
+    pos = np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1)
+    with make_oracle(oracle_lib, sc) as orc:
+        lay = orc.layout
+        dims = list(lay.grid_dims)
+        run_stages(orc, st, [capi.STAGE_GRID_PARTICLES])
+        keys, ids = orc.grid(0)
+        cnt, _, hits = orc.debug_candidates()
+        idx = np.floor((pos - np.asarray(lay.grid_min, np.float32)) / np.float32(2.0)).astype(np.int64)
+        assert idx.min() >= 0 and np.all(idx.max(0) <= np.asarray(dims) - 1)
+        assert (idx.min(0) == 0).all() and (idx.max(0) == np.asarray(dims) - 1).all(), "outermost cells are occupied on every axis"
+        want_key = (idx[:, 2] * dims[1] + idx[:, 1]) * dims[0] + idx[:, 0]
+        assert np.array_equal(keys, want_key[ids])
+        want = brute_force_candidates(pos, np.asarray(lay.grid_min), 2.0, dims)
+        assert np.array_equal(cnt, want), (cnt, want)
+        assert cnt[:32].min() >= 1 and cnt[32:].max() >= 4           # isolated cells see their mates; the interleaved pair more
+        assert hits.sum() == 0 or hits.sum() % 2 == 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU: libbcs vs oracle
+ALL_STAGES = [capi.STAGE_GRID_PARTICLES, capi.STAGE_VEIN_GATHER, capi.STAGE_SPRINGS, capi.STAGE_PARTICLE_COLLISIONS,
+              capi.STAGE_VEIN_COLLISIONS, capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END]
+
+
+def _gpu_vs_oracle(bcs_lib, oracle_lib, sc, st, semantics, steps=2):
+    with make_bcs(sc, semantics) as sim, make_oracle(oracle_lib, sc, semantics) as orc:
+        sim.upload_state(st)
+        orc.upload_state(st)
+        for step in range(steps):
+            sim.run_stage(capi.STAGE_GRID_PARTICLES)
+            orc.run_stage(capi.STAGE_GRID_PARTICLES)
+            ka, ia = sim.grid(0)
+            kb, ib = orc.grid(0)
+            assert np.array_equal(ka, kb) and np.array_equal(ia, ib), f"step {step}: sorted grid"
+            for name, x, y in zip(("count", "checksum", "hits"), sim.debug_candidates(), orc.debug_candidates()):
+                assert np.array_equal(x, y), f"step {step}: candidate {name}"
+            ta, tb = sim.debug_vein_hits(), orc.debug_vein_hits()
+            assert np.array_equal(ta[0], tb[0]), f"step {step}: first-hit triangles"
+            for s in ALL_STAGES[1:]:
+                sim.run_stage(s)
+                orc.run_stage(s)
+            for which in (capi.PARTICLE_FRC, capi.PARTICLE_VEL, capi.PARTICLE_POS):
+                refcheck.assert_close(refcheck.down(sim, which), refcheck.down(orc, which), f"step {step} array {which}")
+        return sim.stats()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
+@pytest.mark.parametrize("scene", [scene_cell_at_rest, scene_touching_pair, scene_grid_boundaries])
+def test_micro_scenes_gpu_vs_oracle(bcs_lib, oracle_lib, scene, semantics):
+    sc, st = scene()
+    _gpu_vs_oracle(bcs_lib, oracle_lib, sc, st, semantics)
+
+
+@pytest.mark.gpu
+def test_ray_cases_against_the_wall(bcs_lib, oracle_lib):
+    """one blood cell per case, 2 units from the r = 50 wall (inside veinImpactDistance = 6) or elsewhere: flying at the
+    wall, along it, away from it, through the lumen's axis, and outside the vein altogether"""
+    sc = micro_scene(6)
+    centres = [[47.0, -60.0, 0.0], [47.0, -70.0, 0.0], [47.0, -80.0, 0.0], [0.0, -90.0, 0.0], [0.0, -100.0, 46.5], [70.0, -60.0, 0.0]]
+    vels = [[80.0, -5.0, 0.0], [0.0, -80.0, 0.0], [-80.0, -5.0, 0.0], [0.0, -80.0, 0.0], [3.0, -10.0, 70.0], [-80.0, 0.0, 0.0]]
+    st = state_from(sc, centres, vels)
+    stats = _gpu_vs_oracle(bcs_lib, oracle_lib, sc, st, capi.SEM_CLEAN, steps=3)
+    assert stats["vein_hits"] >= 4, "the cells flying at the wall must have hit it"
