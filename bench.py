@@ -160,6 +160,11 @@ def time_oracle(particles: int, steps: int, warmup: int):
     pkg, capi, workloads = _pkg()
     lib = oracle_library()
     lib.orc_threads.restype = ctypes.c_int
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank; only rank 0 runs this leg)
+    if hasattr(lib, "orc_set_threads") and "BCS_REF_THREADS" not in os.environ:
+        lib.orc_set_threads(ctypes.c_int(len(os.sched_getaffinity(0))))
+    elif "BCS_REF_THREADS" in os.environ:
+        lib.orc_set_threads(ctypes.c_int(int(os.environ["BCS_REF_THREADS"])))
     cores = int(lib.orc_threads())
     sc, st, info = workloads.long_vein(particles)
     sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, lib=lib, prefix="orc_")

@@ -816,6 +816,16 @@ int orc_create(const bcs_scene* scene, const bcs_opts* opts, orc_sim** out)
 }
 void orc_destroy(orc_sim* s) { delete s; }
 const char* orc_last_error(void) { return g_err.c_str(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1 for every rank; the CPU baseline runs on ONE rank and takes the
+// host cores it may use (bench.py passes the size of its affinity mask)
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_threads(void)
 {
 #ifdef _OPENMP
