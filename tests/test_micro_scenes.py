@@ -178,6 +178,106 @@ def test_oracle_stencils_at_the_grid_boundaries(oracle_lib):
         assert hits.sum() == 0 or hits.sum() % 2 == 0
 
 
+def test_oracle_integration_closed_form(oracle_lib):
+    """propagateParticleForcesKernel (blood_cells.cu:155-179): v1 = v0 + dt F, x += dt/2 (v1 + v0), F untouched"""
+    sc = micro_scene(2)
+    st = state_from(sc, [[1.0, -60.0, 2.0], [-9.0, -75.0, 4.0]], [[3.0, -70.0, 1.0], [-2.0, -64.0, 5.0]])
+    rng = np.random.default_rng(3)
+    F = rng.normal(0.0, 200.0, (8, 3)).astype(np.float32)
+    st["frc_x"], st["frc_y"], st["frc_z"] = F[:, 0].copy(), F[:, 1].copy(), F[:, 2].copy()
+    x0 = np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1).astype(np.float64)
+    v0 = np.stack([st["vel_x"], st["vel_y"], st["vel_z"]], 1).astype(np.float64)
+    dt = sc.physics["dt"]
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_INTEGRATE_PARTICLES])
+        x, v, f = (refcheck.down(orc, w).astype(np.float64) for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC))
+    v1 = v0 + dt * F
+    assert np.abs(v - v1).max() < 1e-5 * np.abs(v1).max()
+    assert np.abs(x - (x0 + 0.5 * dt * (v1 + v0))).max() < 1e-5 * np.abs(x0).max()
+    assert np.array_equal(f.astype(np.float32), F), "the integrator leaves the force alone (SURVEY Q6)"
+
+
+def test_oracle_vein_end_respawn(oracle_lib):
+    """HandleVeinEnd (vein_end.cu:12-173): a blood cell with ANY particle beyond a threshold is respawned as a whole at
+    y = minSpawnY + (model_k - model_0).y with the initial velocity; its x / z offsets keep the model's shape; the
+    other cell is left alone"""
+    sc = micro_scene(2, use_blood_flow=1)
+    lay = sc.layout()
+    lower = float(lay.grid_min[1]) + sc.physics["grid_y_margin"] / 2.0
+    st = state_from(sc, [[0.0, lower + 0.5, 0.0], [5.0, -60.0, 5.0]], [[1.0, -70.0, 0.0], [0.0, -64.0, 0.0]])
+    y = st["pos_y"][:4]
+    assert (y <= lower).any() and (y > lower).any(), "only some particles of the first cell are past the threshold"
+    before = np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1)
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_VEIN_END])
+        x, v = refcheck.down(orc, capi.PARTICLE_POS), refcheck.down(orc, capi.PARTICLE_VEL)
+        assert orc.stats()["teleported_cells"] == 1
+    model = lay.model[:4]
+    ph = sc.physics
+    assert np.allclose(x[:4, 1], ph["min_spawn_y"] + model[:, 1] - model[0, 1], atol=1e-5)
+    assert np.allclose(x[:4] - x[0], model - model[0], atol=1e-5), "the respawned cell keeps the model's shape"
+    assert np.abs(x[0, [0, 2]]).max() <= 0.6 * ph["cylinder_radius"] + 1e-4, "x, z = (U - 0.5) * 1.2 * cylinderRadius"
+    assert np.allclose(v[:4], [ph["init_velocity_x"], ph["init_velocity_y"], ph["init_velocity_z"]])
+    assert np.array_equal(x[4:], before[4:]) and np.allclose(v[4:], [0.0, -64.0, 0.0])
+
+
+def test_oracle_wall_hit_closed_form(oracle_lib):
+    """detectVeinCollisions (vein_collisions.cu:234-276) for one blood cell flying at the wall: given the triangle and
+    the distance the traversal reports, the effect is closed form - reaction force F -= (F.n) n / (n.n), velocity
+    v <- 0.96 |v| reflect(dir, n), wall splat 0.005 v spread over the triangle's vertices by barycentric weights"""
+    sc = micro_scene(1)
+    st = state_from(sc, [[46.5, -60.0, 0.0]], [[80.0, -5.0, 3.0]])
+    rng = np.random.default_rng(5)
+    F0 = rng.normal(0.0, 50.0, (4, 3)).astype(np.float32)
+    st["frc_x"], st["frc_y"], st["frc_z"] = F0[:, 0].copy(), F0[:, 1].copy(), F0[:, 2].copy()
+    pos = np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1).astype(np.float64)
+    vel = np.stack([st["vel_x"], st["vel_y"], st["vel_z"]], 1).astype(np.float64)
+    ph = sc.physics
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_GRID_PARTICLES])
+        tri, t = orc.debug_vein_hits()
+        orc.run_stage(capi.STAGE_VEIN_COLLISIONS)
+        v = refcheck.down(orc, capi.PARTICLE_VEL).astype(np.float64)
+        F = refcheck.down(orc, capi.PARTICLE_FRC).astype(np.float64)
+        vf = refcheck.down(orc, capi.VEIN_FRC).astype(np.float64)
+        assert orc.stats()["vein_hits"] == int((t <= ph["vein_impact_distance"]).sum())
+    vp, vi = sc.vein_pos.astype(np.float64), sc.vein_indices
+    want_vf = np.zeros_like(vf)
+    acted = 0
+    for k in range(4):
+        assert tri[k] >= 0, "every particle of the cell flies at the wall"
+        a, b, c = vp[vi[tri[k]]]
+        d = vel[k] / np.linalg.norm(vel[k])
+        hit = pos[k] + float(t[k]) * d
+        # the reported hit point lies in the reported triangle's plane, inside it
+        n = np.cross(c - a, b - a)
+        n /= np.linalg.norm(n)
+        assert abs(np.dot(hit - a, n)) < 1e-3
+        if t[k] > ph["vein_impact_distance"]:
+            assert np.allclose(v[k], vel[k]) and np.allclose(F[k], F0[k])
+            continue
+        acted += 1
+        refl = d - 2.0 * np.dot(d, n) * n
+        want_v = ph["velocity_collision_damping"] * np.linalg.norm(vel[k]) * refl
+        assert np.abs(v[k] - want_v).max() < 1e-4 * np.linalg.norm(vel[k]), (v[k], want_v)
+        want_F = F0[k] - np.dot(F0[k], n) * n
+        assert np.abs(F[k] - want_F).max() < 1e-4 * np.abs(F0[k]).max(), (F[k], want_F)
+        # the hit point is inside the triangle (true barycentric coordinates) ...
+        T = np.stack([a, b, c], 1)
+        w = np.linalg.lstsq(np.vstack([T, np.ones(3)]), np.append(hit, 1.0), rcond=None)[0]
+        assert w.min() > -1e-3 and abs(w.sum() - 1.0) < 1e-6
+        # ... but the splat weights are calculateBaricentric's (vein_collisions.cu:47-61), whose second edge is v2 - v1,
+        # not v2 - v0 (SURVEY 8(a) a12): weights (bx, by, 1 - bx - by) on (v0, v1, v2)
+        e0, e1, e2 = b - a, c - b, hit - a
+        d00, d01, d11, d20, d21 = e0 @ e0, e0 @ e1, e1 @ e1, e2 @ e0, e2 @ e1
+        den = d00 * d11 - d01 * d01
+        bx, by = (d11 * d20 - d01 * d21) / den, (d00 * d21 - d01 * d20) / den
+        for wgt, vid in zip((bx, by, 1.0 - bx - by), vi[tri[k]]):
+            want_vf[vid] += wgt * ph["vein_collision_force_intensity"] * vel[k]
+    assert acted >= 2
+    assert np.abs(vf - want_vf).max() < 2e-3 * np.abs(want_vf).max(), np.abs(vf - want_vf).max()
+
+
 # ------------------------------------------------------------------------------------------------ GPU: libbcs vs oracle
 ALL_STAGES = [capi.STAGE_GRID_PARTICLES, capi.STAGE_VEIN_GATHER, capi.STAGE_SPRINGS, capi.STAGE_PARTICLE_COLLISIONS,
               capi.STAGE_VEIN_COLLISIONS, capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END]
