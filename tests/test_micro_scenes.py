@@ -178,6 +178,110 @@ def test_oracle_stencils_at_the_grid_boundaries(oracle_lib):
         assert hits.sum() == 0 or hits.sum() % 2 == 0
 
 
+def test_oracle_springs_closed_form(oracle_lib):
+    """gatherForcesKernel (blood_cells.cu:66-120) + physics.cuh:24-27,53-78,102-120 restated in float64 numpy on three
+    tetrahedra: one stretched by 10 % at rest (pure spring pull towards the centroid + gravity), one perturbed with
+    velocities and old forces, one blown up by 60 % so that the big-cell brake (ratio > 1.5) is active"""
+    sc = micro_scene(3)
+    ph = sc.physics
+    lay = sc.layout()
+    model = lay.model[:4].astype(np.float64)
+    centres = np.array([[0.0, -50.0, 0.0], [10.0, -70.0, -5.0], [-12.0, -90.0, 6.0]])
+    rng = np.random.default_rng(11)
+    pos = np.concatenate([centres[0] + 1.1 * model, centres[1] + model + rng.normal(0, 0.15, (4, 3)), centres[2] + 1.6 * model])
+    vel = np.concatenate([np.zeros((4, 3)), rng.normal(0, 5.0, (4, 3)) + [0, -70, 0], rng.normal(0, 2.0, (4, 3)) + [0, -60, 0]])
+    frc = np.concatenate([np.zeros((4, 3)), rng.normal(0, 40.0, (4, 3)), rng.normal(0, 10.0, (4, 3))])
+    st = {f"{a}_{c}": arr[:, i].astype(np.float32).copy() for a, arr in (("pos", pos), ("vel", vel), ("frc", frc)) for i, c in enumerate("xyz")}
+    pos, vel, frc = (np.stack([st[f"{a}_x"], st[f"{a}_y"], st[f"{a}_z"]], 1).astype(np.float64) for a in ("pos", "vel", "frc"))
+    with make_oracle(oracle_lib, sc) as orc:
+        run_stages(orc, st, [capi.STAGE_SPRINGS])
+        got = refcheck.down(orc, capi.PARTICLE_FRC).astype(np.float64)
+    dt, k, d = ph["dt"], ph["particle_k_sniff"], ph["particle_d_fact"]
+    G = np.array([ph["gx"], ph["gy"], ph["gz"]])
+    init_r = np.linalg.norm(model - model.mean(0), axis=1)
+    want = np.empty_like(frc)
+    braked = 0
+    for c in range(3):
+        P = slice(4 * c, 4 * c + 4)
+        p, v, f = pos[P], vel[P], frc[P]
+        centre = p.sum(0) / 4.0
+        for i in range(4):
+            new = np.zeros(3)
+            for j in range(4):
+                if j == i:
+                    continue
+                dP = p[i] - p[j]
+                n = dP / np.linalg.norm(dP)
+                dv = v[i] - v[j] + dt * (f[i] - f[j])
+                new += ((np.linalg.norm(dP) - EDGE) * k + np.dot(n, dv) * d) * (-n)
+            ratio = np.linalg.norm(p[i] - centre) / init_r[i]
+            brake = ratio * ph["big_particle_braking_intensity"] if ratio > ph["max_cell_size_factor_before_brake"] else 1.0
+            braked += ratio > ph["max_cell_size_factor_before_brake"]
+            new += G - ph["viscous_damping"] * brake * v[i]
+            want[4 * c + i] = (f[i] + new) / 2.0
+    assert braked == 4, "exactly the blown-up cell brakes"
+    assert np.abs(got - want).max() < 2e-5 * np.abs(want).max(), np.abs(got - want).max()
+    # the stretched cell at rest: 0.3 * k towards each mate = sqrt(6) * 0.3 * k towards the centroid, plus gravity, halved
+    inward = (centres[0] - pos[:4]) / np.linalg.norm(centres[0] - pos[:4], axis=1)[:, None]
+    assert np.abs(got[:4] - 0.5 * (np.sqrt(6.0) * 0.1 * EDGE * k * inward + G)).max() < 1e-3
+
+
+def test_oracle_vein_springs_closed_form(oracle_lib):
+    """VeinTriangles::gatherForcesFromNeighbors (vein_triangles.cu:126-154, physics.cuh:38-41) + the vertex integrator
+    (:88-117): the neighbour slots are rebuilt here from the triangle list by the reference's rule (vein_factory.hpp:
+    130-174: every triangle pushes both other vertices - each mesh edge twice -, the list is sorted and cut to 9, SURVEY
+    Q10) and the force on a displaced patch of the wall is restated in float64"""
+    sc = micro_scene(1)
+    ph = sc.physics
+    vp0, vi = sc.vein_pos.astype(np.float64), sc.vein_indices.astype(np.int64)
+    V = len(vp0)
+    nbrs = [[] for _ in range(V)]
+    for a, b, c in vi:
+        nbrs[a] += [b, c]; nbrs[b] += [a, c]; nbrs[c] += [a, b]
+    slots = np.full((9, V), -1, np.int64)
+    for v in range(V):
+        lst = sorted(nbrs[v])[:9]
+        slots[:len(lst), v] = lst
+    with make_oracle(oracle_lib, sc) as orc:
+        ids = orc.table(capi.TABLE_VEIN_NBR_IDS).reshape(9, V)
+        rest = orc.table(capi.TABLE_VEIN_NBR_LEN).reshape(9, V).astype(np.float64)
+        assert np.array_equal(ids, slots), "neighbour slots: duplicates kept, sorted, cut to 9"
+        want_rest = np.where(slots >= 0, np.linalg.norm(vp0[np.maximum(slots, 0)] - vp0[None, :, :], axis=2), 0.0)
+        assert np.abs(rest - want_rest)[slots >= 0].max() < 1e-4
+        # displace a patch of the wall and give it velocities
+        rng = np.random.default_rng(2)
+        patch = np.arange(1500, 1530)
+        vp = sc.vein_pos.copy(); vv = np.zeros_like(vp)
+        vp[patch] += rng.normal(0, 0.3, (len(patch), 3)).astype(np.float32)
+        vv[patch] = rng.normal(0, 2.0, (len(patch), 3)).astype(np.float32)
+        orc.upload_state(state_from(sc, [[0.0, -60.0, 0.0]]))
+        refcheck.up(orc, capi.VEIN_POS, vp)
+        refcheck.up(orc, capi.VEIN_VEL, vv)
+        orc.run_stage(capi.STAGE_VEIN_GATHER)
+        F = refcheck.down(orc, capi.VEIN_FRC).astype(np.float64)
+        orc.run_stage(capi.STAGE_INTEGRATE_VEIN)
+        x1, v1, F1 = (refcheck.down(orc, w).astype(np.float64) for w in (capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC))
+    p, w = vp.astype(np.float64), vv.astype(np.float64)
+    want = np.zeros_like(p)
+    # every vertex that moved or LISTS a vertex that moved (the cut to 9 slots makes the lists asymmetric)
+    touched = set(patch.tolist()) | set(np.nonzero(np.isin(slots, patch).any(0))[0].tolist())
+    for v in touched:
+        for s_ in range(9):
+            q = slots[s_, v]
+            if q < 0:
+                continue
+            dP = p[v] - p[q]
+            n = dP / np.linalg.norm(dP)
+            f = (np.linalg.norm(dP) - rest[s_, v]) * ph["vein_k_sniff"] + np.dot(n, w[v] - w[q]) * ph["vein_d_fact"]
+            want[v] += f * (-n)
+    far = np.setdiff1d(np.arange(V), np.fromiter(touched, int))
+    assert np.abs(F[far]).max() < 1e-4, "the undisturbed wall is at rest"
+    assert np.abs(F - want).max() < 1e-4 * np.abs(want).max() + 1e-5, np.abs(F - want).max()
+    dt = ph["dt"]
+    assert np.abs(v1 - (w + dt * F)).max() < 1e-6 and np.abs(x1 - (p + dt * (w + dt * F))).max() < 1e-4
+    assert np.abs(F1).max() == 0.0, "the vertex integrator clears the forces"
+
+
 def test_oracle_integration_closed_form(oracle_lib):
     """propagateParticleForcesKernel (blood_cells.cu:155-179): v1 = v0 + dt F, x += dt/2 (v1 + v0), F untouched"""
     sc = micro_scene(2)
