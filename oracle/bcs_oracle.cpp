@@ -10,7 +10,9 @@
 // The oracle is pinned instead against dumps of the UNMODIFIED reference CUDA sources run headless on a
 // B200 (oracle/ref_harness, oracle/build_ref.sh), committed under tests/golden/ together with the scripts
 // that made them (tools/gpu_ref_goldens.sh, tools/make_goldens.py); tests/test_oracle_vs_reference.py
-// checks every stage.
+// checks every stage.  Independently of the dumps, tests/test_micro_scenes.py checks every stage against float64
+// numpy restatements of the reference formulas on hand-built scenes (springs incl. the brake, collision force, grid
+// boundary stencils, vein neighbour slots and springs, first-hit traversal, wall-hit effect, integrators, respawn).
 //
 // Reference lines followed (paths relative to the reference's src/):
 //   layout / tables   meta_factory/blood_cell_factory.hpp:52-162,197-333; meta_factory/vein_factory.hpp:21-86,130-174
@@ -27,7 +29,9 @@
 //
 // Floating point: plain IEEE single precision, one rounding per operation, evaluated in the reference's
 // expression order (compile with -ffp-contract=off).  The device code of the reference (and of the
-// product) may contract a*b+c into FMAs, so float results agree to ~1e-6 relative, integers exactly.
+// product) may contract a*b+c into FMAs, so float results agree to ~1e-6 relative, integers exactly.  One
+// expression is a decision threshold and therefore pinned to the FMA chain nvcc emits: d^2 of the touch test
+// (stageParticleCollisions; the CUDA path spells out the same chain).
 // Races of the reference are resolved as "snapshot" (springs read pre-stage forces) and
 // "sequential sum in particle order" (vein force splats, Q9).
 #include <algorithm>
