@@ -250,6 +250,30 @@ def test_free_run_is_bitwise_repeatable(bcs_lib):
             assert np.array_equal(x, y), f"run {run}: array {w} differs from run 0"
 
 
+@pytest.mark.parametrize("switch", ["BCS_GRID=radix", "BCS_SCAN=fused", "BCS_COLLIDE=rows", "BCS_NO_NEAR_PROBE=1", "BCS_NO_OVERLAP=1",
+                                    "BCS_SORT=classic"])
+def test_alternative_paths_equal_the_default_bitwise(bcs_lib, monkeypatch, switch):
+    """every A/B switch of DESIGN.md section 7 selects another route to the SAME result: radix-sorted grid, single-launch
+    scans, row-after-row candidate walk, wall filter without the spring kernel's near list, unforked step"""
+    sc = small_cylinder_scene(120, 100, 120.0)
+    st = pkg.make_initial_state(sc, seed=8, xz_half_width=44.0, y_range=(-25.0, -95.0))
+    arrays = (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL)
+
+    def run():
+        with make_bcs(sc) as sim:
+            sim.upload_state(st)
+            sim.step(25)
+            return [refcheck.down(sim, w) for w in arrays], sim.stats()
+
+    want, stats = run()
+    assert stats["vein_hits"] > 20
+    name, value = switch.split("=")
+    monkeypatch.setenv(name, value)
+    got, _ = run()
+    for w, x, y in zip(arrays, got, want):
+        assert np.array_equal(x, y), f"{switch}: array {w} differs from the default path"
+
+
 def test_tiled_collision_kernel_equals_index_walk(bcs_lib, monkeypatch):
     """BCS_COLLIDE=tiled (neighbour windows staged in shared memory per tile of sorted slots) visits the same candidates
     in the same order as the index walk: bitwise equal forces, equal debug candidate sets."""
