@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the per-step physics hot path (BASELINE.json: particle-steps/s and ms/step at 1 M particles).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|long_vein|cfg5] [--particles P]
+                    [--semantics clean|reference] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" = grid build + forces + integration of ALL particles of the
 workload (bcs_step).  `value` is measured with the state resident in HBM (CUDA events on the library's
 stream around K graph-replayed steps); `e2e` is the same metric through the C ABI with HOST buffers:
 every step uploads positions/velocities/forces from pinned host memory and downloads the positions.
 `--impl reference` times the host-core port of the reference step (oracle/, OpenMP, all host threads) -
-upstream has no CPU path of its own - on a bounded sample of the same workload.
+upstream has no CPU path of its own - on the SAME workload (same_config).  The line carries a `parity` block: at N = 1
+the first steps of the workload against the CPU oracle, at N > 1 the merged N-rank state against a one-GPU replay.
 """
 from __future__ import annotations
 
@@ -29,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_steps_per_s"
 UNIT = "particle-steps/s"
+CONTRACT_KERNELS = ("springs", "particle_collisions")
 
 
 def _pkg():
@@ -152,22 +155,27 @@ def oracle_library():
     path = os.path.join(ROOT, "oracle", "libbcs_oracle.so")
     if not os.path.exists(path):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
-    return ctypes.CDLL(path)
-
-
-def time_oracle(particles: int, steps: int, warmup: int):
-    """Host-core port of the reference step on a bounded sample: a section of the same vein at the same density."""
-    pkg, capi, workloads = _pkg()
-    lib = oracle_library()
+    lib = ctypes.CDLL(path)
     lib.orc_threads.restype = ctypes.c_int
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank; only rank 0 runs this leg)
-    if hasattr(lib, "orc_set_threads") and "BCS_REF_THREADS" not in os.environ:
-        lib.orc_set_threads(ctypes.c_int(len(os.sched_getaffinity(0))))
-    elif "BCS_REF_THREADS" in os.environ:
+    if "BCS_REF_THREADS" in os.environ:
         lib.orc_set_threads(ctypes.c_int(int(os.environ["BCS_REF_THREADS"])))
+    elif hasattr(lib, "orc_set_threads"):
+        lib.orc_set_threads(ctypes.c_int(len(os.sched_getaffinity(0))))
+    return lib
+
+
+def semantics_of(args, capi):
+    return capi.SEM_REFERENCE if args.semantics == "reference" else capi.SEM_CLEAN
+
+
+def time_oracle(args, steps: int, warmup: int):
+    """Host-core port of the reference step (oracle/, OpenMP) on the WHOLE workload the product arm times."""
+    pkg, capi, workloads = _pkg()
+    lib = oracle_library()
     cores = int(lib.orc_threads())
-    sc, st, info = workloads.long_vein(particles)
-    sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, lib=lib, prefix="orc_")
+    sc, st, info = workloads.by_name(args.workload, args.particles)
+    sim = capi.Sim(sc, semantics=semantics_of(args, capi), lib=lib, prefix="orc_")
     sim.upload_state(st)
     sim.step(warmup)
     t0 = time.perf_counter()
@@ -179,23 +187,107 @@ def time_oracle(particles: int, steps: int, warmup: int):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: upstream has no CPU path, so the reference arm is the host-core port of the same step
+    (cpu_baseline.kind "port") on ALL host threads, same workload, same steps (same_config: true)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(args.particles, args.reference_sample)
-    value, ms, cores, n, info = time_oracle(sample, args.steps, args.warmup)
+    value, ms, cores, n, info = time_oracle(args, args.steps, args.warmup)
+    config = dict(info)
+    config.update({"semantics": args.semantics, "same_config": True, "timed_particles": n})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"long_vein_{args.particles}", "particles": args.particles, "timed_sample_particles": n},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n}-particle section of the {args.particles}-particle long-vein workload (same density, same step), "
-                                   f"{args.steps} steps after {args.warmup} warm-up; upstream has no CPU path, this is the host-core port under oracle/"},
+                         "sample": f"the whole {info['workload']} workload ({n} particles), {args.steps} steps after {args.warmup} warm-up; "
+                                   f"upstream has no CPU path, this is the host-core port under oracle/ (OpenMP, {cores} threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def reference_cuda_baseline(workload: str):
+    """The reference's OWN CUDA build timed on a B200 of this pool for the same scene (profiles/reference_cuda.json, written
+    from tools/gpu_ref_bench.sh runs of the unmodified reference sources; oracle/build_ref.sh).  Reported, not a target."""
+    path = os.path.join(ROOT, "profiles", "reference_cuda.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+# ----------------------------------------------------------------------------------------------- parity self-check
+def parity_vs_oracle(args, sc, st, device):
+    """N = 1: the first steps of the SAME workload on a second handle against the CPU oracle: integer outputs of step 0
+    (sorted cell ids, sorted order, candidate counts + checksums, touching pairs) bit-exact, positions after `psteps` free
+    steps within 1e-5 of the travelled distance scale."""
+    pkg, capi, workloads = _pkg()
+    lib = oracle_library()
+    sem = semantics_of(args, capi)
+    psteps = 2
+    with capi.Sim(sc, semantics=sem, device=device) as sim, capi.Sim(sc, semantics=sem, lib=lib, prefix="orc_") as orc:
+        sim.upload_state(st)
+        orc.upload_state(st)
+        sim.run_stage(capi.STAGE_GRID_PARTICLES)
+        orc.run_stage(capi.STAGE_GRID_PARTICLES)
+        (ka, ia), (kb, ib) = sim.grid(0), orc.grid(0)
+        ca, cb = sim.debug_candidates(), orc.debug_candidates()
+        sim.step(psteps)
+        orc.step(psteps)
+        a = np.stack(sim.download(capi.PARTICLE_POS), 1).astype(np.float64)
+        b = np.stack(orc.download(capi.PARTICLE_POS), 1).astype(np.float64)
+        f_a = np.stack(sim.download(capi.PARTICLE_FRC), 1).astype(np.float64)
+        f_b = np.stack(orc.download(capi.PARTICLE_FRC), 1).astype(np.float64)
+    scale = float(np.abs(b).max())
+    fscale = float(np.percentile(np.abs(f_b).max(axis=1), 99))
+    out = {
+        "against": "CPU oracle (oracle/, host-core port pinned on reference-run fixtures)", "steps": psteps,
+        "sorted_cell_ids_equal": bool(np.array_equal(ka, kb)), "sorted_order_equal": bool(np.array_equal(ia, ib)),
+        "candidate_counts_equal": bool(np.array_equal(ca[0], cb[0])), "candidate_checksums_equal": bool(np.array_equal(ca[1], cb[1])),
+        "touching_pairs_equal": bool(np.array_equal(ca[2], cb[2])),
+        "pos_max_abs_diff": float(np.abs(a - b).max()), "pos_max_rel_diff": float(np.abs(a - b).max() / scale),
+        "frc_max_abs_diff": float(np.abs(f_a - f_b).max()), "frc_p99_scale": fscale, "tolerance_rel": 1e-5,
+    }
+    out["ok"] = bool(out["sorted_cell_ids_equal"] and out["sorted_order_equal"] and out["candidate_counts_equal"] and
+                     out["candidate_checksums_equal"] and out["touching_pairs_equal"] and out["pos_max_rel_diff"] <= 1e-5)
+    return out
+
+
+def parity_vs_single_gpu(sim, sc, st, total_steps, rank, world, local_rank, planes, dist, dd, capi):
+    """N > 1: the merged state of the N-rank run (every blood cell from its owner, every vein vertex from the rank whose
+    slab holds its rest position) against the SAME number of steps on one GPU (rank 0 replays): max |diff| must be 0."""
+    lay = sc.layout()
+    mine = {"pos": np.stack(sim.download(capi.PARTICLE_POS), 1), "vel": np.stack(sim.download(capi.PARTICLE_VEL), 1),
+            "frc": np.stack(sim.download(capi.PARTICLE_FRC), 1), "vpos": np.stack(sim.download(capi.VEIN_POS), 1),
+            "owned": sim.ownership()}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    out = None
+    if rank == 0:
+        with capi.Sim(sc, device=local_rank) as ref:
+            ref.upload_state(st)
+            ref.step(total_steps)
+            single = {"pos": np.stack(ref.download(capi.PARTICLE_POS), 1), "vel": np.stack(ref.download(capi.PARTICLE_VEL), 1),
+                      "frc": np.stack(ref.download(capi.PARTICLE_FRC), 1), "vpos": np.stack(ref.download(capi.VEIN_POS), 1)}
+        owned = [g["owned"] for g in gathered]
+        out = {"against": f"the same {total_steps} steps on one GPU (rank 0 replay)", "steps": total_steps}
+        worst = 0.0
+        for key in ("pos", "vel", "frc"):
+            merged = dd.merge_owned([g[key] for g in gathered], owned, lay)
+            d = float(np.abs(merged.astype(np.float64) - single[key]).max())
+            out[f"{key}_max_abs_diff"] = d
+            worst = max(worst, d)
+        y0 = sc.vein_pos[:, 1]
+        vm = np.empty_like(single["vpos"])
+        for r in range(world):
+            sel = (y0 >= planes[r + 1]) & (y0 < planes[r])
+            vm[sel] = gathered[r]["vpos"][sel]
+        out["vein_pos_max_abs_diff"] = float(np.abs(vm.astype(np.float64) - single["vpos"]).max())
+        out["max_abs_diff"] = max(worst, out["vein_pos_max_abs_diff"])
+        out["ok"] = out["max_abs_diff"] == 0.0
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- product arm
@@ -225,15 +317,20 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # slab decomposition along the vein axis.  Default: STRONG scaling, the same 1 M-particle scene split over the ranks
-    # (BASELINE.json's metric); --scaling weak keeps 1 M particles PER RANK (a vein N times as long, same density)
+    # slab decomposition along the vein axis.  Default: STRONG scaling, the same scene split over the ranks
+    # (BASELINE.json's metric); --scaling weak keeps --particles PER RANK (a vein N times as long, same density)
     n_particles = args.particles * (world if args.scaling == "weak" else 1)
-    sc, st, info = workloads.long_vein(n_particles)
+    sc, st, info = workloads.by_name(args.workload, n_particles)
+    sem = semantics_of(args, capi)
+    planes = None
+    parity = None
+    if world == 1 and not args.no_parity:
+        parity = parity_vs_oracle(args, sc, st, local_rank)
     if world > 1:
         planes = dd.slab_boundaries(sc, st, world)
         sim = dd.create_slab_sim(sc, st, rank, world, local_rank, dd.broadcast_unique_id(rank), planes)
     else:
-        sim = capi.Sim(sc, semantics=capi.SEM_CLEAN, device=local_rank, use_graph=True)
+        sim = capi.Sim(sc, semantics=sem, device=local_rank, use_graph=True)
         sim.upload_state(st)
     N, B, V, T = sim.n_particles, sim.n_cells, sim.n_vertices, sim.n_triangles
     view = sim.device_view()
@@ -257,6 +354,8 @@ def run_product(args):
     launches = sim.launch_count() - launches0
     value = N / (ms * 1e-3)
     slab_info = sim.slab_counts() if world > 1 else None
+    if world > 1 and not args.no_parity:
+        parity = parity_vs_single_gpu(sim, sc, st, args.warmup + args.steps, rank, world, local_rank, planes, dist, dd, capi)
 
     # ---- per-kernel times (CUDA events around every launch, plain launches) and the roofline of the dominant kernel
     if world > 1:
@@ -284,13 +383,13 @@ def run_product(args):
         per_launch_ms = prof[name][0] / prof[name][1]
         b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits)
         gbs = b / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-        t = traffic.get(name) if world == 1 else None   # captured at N=1 on this workload
+        t = traffic.get(name) if world == 1 and args.workload == "long_vein" and args.particles == 1_000_000 else None
         return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                 "traffic": t["bytes"] if t else None, "traffic_source": t["source"] if t else None,
                 "algorithmic_bytes_per_launch": b, "ms_per_launch": per_launch_ms, "peak_source": peak_src}
 
     roofline = roof(dominant)
-    roofline["contract_kernels"] = {k: roof(k) for k in ("springs", "particle_collisions") if k in prof}
+    roofline["contract_kernels"] = {k: roof(k) for k in CONTRACT_KERNELS if k in prof}
     step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits) * v[1] / prof_steps for k, v in prof.items())
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}
 
@@ -322,26 +421,30 @@ def run_product(args):
     e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 36 * N, "d2h_bytes_per_step": 12 * N,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps}
 
-    # ---- CPU baseline (rank 0, N=1): the host-core port on a bounded sample
+    # ---- CPU baseline (rank 0, N=1): the host-core port on the whole workload, a few steps
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cv, cms, cores, cn, _ = time_oracle(min(args.particles, args.reference_sample), 3, 1)
+        cv, cms, cores, cn, _ = time_oracle(args, 3, 1)
         cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": cms,
-               "sample": f"{cn}-particle section of the workload (same density), 3 steps after 1 warm-up, OpenMP on {cores} threads"}
+               "sample": f"the whole workload ({cn} particles), 3 steps after 1 warm-up, OpenMP on {cores} threads"}
 
     ws_mb = (16 * 3 * N + 16 * 2 * N + 16 * N + 64 * c_occ + 48 * V + 48 * T) / 1e6
     config = dict(info)
     if world > 1:
         config["parallelism"] = f"y-slab decomposition over {world} ranks, NCCL halo exchange + blood-cell migration (one grouped send/recv per neighbour and step)"
         config["rank0_slab"] = slab_info
-    config.update({"semantics": "clean", "launch": "CUDA graph replay, 1 graph per step (springs / wall search / vein gather on forked branches)" if world == 1 else "CUDA graph replay, 1 graph per step, NCCL send/recv captured in the graph",
-                   "l2": f"no flush: per-step working set ~{ws_mb:.0f} MB exceeds the 126 MB L2 (inputs larger than L2)",
+    config.update({"semantics": args.semantics, "launch": "CUDA graph replay" if world == 1 else "CUDA graph replay, NCCL send/recv captured in the graph",
+                   "timed_window": f"steps {args.warmup}..{args.warmup + args.steps} after the seeded initial state (the workload is not stationary: "
+                                   "blood cells drift towards the wall)",
+                   "l2": f"no flush: per-step working set ~{ws_mb:.0f} MB exceeds the 126 MB L2 (inputs larger than L2)" if ws_mb > 126 else
+                         f"no flush: per-step working set ~{ws_mb:.0f} MB is L2 resident (this scene is smaller than the 126 MB L2)",
                    "occupied_grid_cells": c_occ, "grid_cells": int(sim.layout.grid_cells)})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": reference_cuda_baseline(info["workload"]), "parity": parity,
+        "kernels": kernels,
     }
     sim.close()
     if rank == 0:
@@ -356,14 +459,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="long_vein", choices=["cfg1", "cfg2", "cfg3", "long_vein", "cfg5"],
+                    help="BASELINE.json configs: cfg1 default scene, cfg2 100 k default vein, cfg3 1 M default vein (dense), "
+                         "long_vein 1 M at default density (default; the metric's config), cfg5 10 M high hematocrit")
+    ap.add_argument("--particles", type=int, default=None, help="long_vein / cfg5 only (default 1 M / 10 M)")
+    ap.add_argument("--semantics", default="clean", choices=["clean", "reference"],
+                    help="clean (default) or the reference's quirks bit for bit (stale cell tables, slice radii): single GPU only")
     ap.add_argument("--impl", default="bcs", choices=["bcs", "reference"])
-    ap.add_argument("--reference-sample", type=int, default=100_000, help="particles in the CPU-timed sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = the --particles scene split over the ranks (default, BASELINE metric); weak = --particles per rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.particles is None:
+        args.particles = 10_000_000 if args.workload == "cfg5" else 1_000_000
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -48,11 +48,18 @@ else
 fi
 
 INC="-I$SRC -I$REF/Libraries/include -I$ROOT/include"
-NV="nvcc -std=c++17 -O3 $GEN -Wno-deprecated-gpu-targets --expt-relaxed-constexpr --maxrregcount=40 -rdc=true -w $INC"
+# REF_CONSTEXPR_LIMIT=<n>: raise the host compiler's constexpr evaluation limits (large generated veins: the reference's
+# vein_factory.hpp walks every vertex / triangle at compile time).  Compiler flags only - the sources stay untouched.
+LIM=""; NVLIM=""
+if [ -n "${REF_CONSTEXPR_LIMIT:-}" ]; then
+  LIM="-fconstexpr-loop-limit=$REF_CONSTEXPR_LIMIT -fconstexpr-ops-limit=${REF_CONSTEXPR_LIMIT}00"
+  NVLIM="-Xcompiler -fconstexpr-loop-limit=$REF_CONSTEXPR_LIMIT -Xcompiler -fconstexpr-ops-limit=${REF_CONSTEXPR_LIMIT}00"
+fi
+NV="nvcc -std=c++17 -O3 $GEN -Wno-deprecated-gpu-targets --expt-relaxed-constexpr --maxrregcount=40 -rdc=true -w $NVLIM $INC"
 OBJ=/tmp/bcs_ref_obj_$SUFFIX
 rm -rf "$OBJ"; mkdir -p "$OBJ"
 
-g++ -std=c++17 -O1 -w $INC "$HERE/ref_harness/ref_scene_dump.cpp" -o "$OUT/ref_scene_dump_$CFG" &
+g++ -std=c++17 -O1 -w $LIM $INC "$HERE/ref_harness/ref_scene_dump.cpp" -o "$OUT/ref_scene_dump_$CFG" &
 pids=()
 for f in grids/uniform_grid objects/blood_cells objects/vein_triangles objects/vein_neighbors \
          simulation/vein_collisions simulation/vein_end utilities/cuda_vec3; do
@@ -66,6 +73,6 @@ wait
 $NV "$OBJ"/*.o -o "$OUT/ref_headless_$SUFFIX" -lcurand
 "$OUT/ref_scene_dump_$CFG" "$OUT/scene_$CFG.bcsd"
 # the integration shim compiled inside the reference's header tree must produce the same user-level scene
-g++ -std=c++17 -O1 -w $INC "$HERE/ref_harness/shim_check.cpp" -o "$OUT/shim_check_$CFG" && "$OUT/shim_check_$CFG" "$OUT/shim_scene_$CFG.bcsd"
+g++ -std=c++17 -O1 -w $LIM $INC "$HERE/ref_harness/shim_check.cpp" -o "$OUT/shim_check_$CFG" && "$OUT/shim_check_$CFG" "$OUT/shim_scene_$CFG.bcsd"
 rm -rf "$OBJ"
 echo "build_ref: built $OUT/ref_headless_$SUFFIX and $OUT/scene_$CFG.bcsd"

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import refcheck
+import stagecheck
 from conftest import (capi, golden_dump, golden_scene, make_bcs, make_oracle, pkg, seeded_state, small_cylinder_scene)
 from test_oracle_vs_reference import CASES, TRAJECTORY_CASES, check_trajectory
 
@@ -55,49 +56,6 @@ def test_100_step_trajectory_vs_reference(bcs_lib, cfg, variant):
     check_trajectory(pos, cfg, variant, st)
 
 
-def _compare_step(sim, orc, nsteps, tag):
-    """one step at a time: stage outputs of libbcs vs oracle from identical inputs"""
-    for step in range(nsteps):
-        # identical inputs: copy the oracle's state into the device handle
-        for which in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC):
-            refcheck.up(sim, which, refcheck.down(orc, which))
-        sim.run_stage(capi.STAGE_GRID_PARTICLES); orc.run_stage(capi.STAGE_GRID_PARTICLES)
-        for which in (0, 1):
-            ka, ia = sim.grid(which); kb, ib = orc.grid(which)
-            assert np.array_equal(ka, kb) and np.array_equal(ia, ib), f"{tag} step {step}: grid {which}"
-            ta, tb = sim.cell_table(which), orc.cell_table(which)
-            assert all(np.array_equal(x, y) for x, y in zip(ta, tb)), f"{tag} step {step}: cell table {which}"
-        ca, cb = sim.debug_candidates(), orc.debug_candidates()
-        for name, x, y in zip(("count", "checksum", "hits"), ca, cb):
-            bad = np.nonzero(x != y)[0]
-            assert len(bad) == 0, (f"{tag} step {step}: candidate {name} differs for {len(bad)} particles, first {bad[:6]}: "
-                                   f"libbcs {x[bad[:6]]} oracle {y[bad[:6]]}; second evaluation libbcs {sim.debug_candidates()[('count', 'checksum', 'hits').index(name)][bad[:6]]} "
-                                   f"oracle {orc.debug_candidates()[('count', 'checksum', 'hits').index(name)][bad[:6]]}")
-        ha, hb = sim.debug_vein_hits(), orc.debug_vein_hits()
-        for st in (capi.STAGE_VEIN_GATHER, capi.STAGE_SPRINGS, capi.STAGE_PARTICLE_COLLISIONS):
-            sim.run_stage(st); orc.run_stage(st)
-            refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_FRC), refcheck.down(orc, capi.PARTICLE_FRC), f"{tag} step {step} stage {st} forces")
-        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), refcheck.down(orc, capi.VEIN_FRC), f"{tag} step {step} vein spring forces",
-                              scale=max(0.5, float(np.abs(refcheck.down(orc, capi.VEIN_FRC)).max())))
-        ha, hb = sim.debug_vein_hits(), orc.debug_vein_hits()
-        same = ha[0] == hb[0]
-        assert same.mean() > 0.999, f"{tag} step {step}: first-hit triangles differ for {(~same).sum()} particles"
-        sim.run_stage(capi.STAGE_VEIN_COLLISIONS); orc.run_stage(capi.STAGE_VEIN_COLLISIONS)
-        ok = same
-        refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_FRC)[ok], refcheck.down(orc, capi.PARTICLE_FRC)[ok], f"{tag} step {step} forces after vein collisions")
-        refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_VEL)[ok], refcheck.down(orc, capi.PARTICLE_VEL)[ok], f"{tag} step {step} velocities after vein collisions")
-        vf = refcheck.down(orc, capi.VEIN_FRC)
-        # barycentric weights divide by d00*d11 - d01^2 (cancellation): FMA contraction moves them by up to ~1e-5
-        # relative, so the splats are compared at 1e-4
-        refcheck.assert_close(refcheck.down(sim, capi.VEIN_FRC), vf, f"{tag} step {step} vein forces", rtol=1e-4,
-                              scale=max(0.5, float(np.abs(vf).max())), allowed=0 if same.all() else 9)
-        for st in (capi.STAGE_INTEGRATE_PARTICLES, capi.STAGE_INTEGRATE_VEIN, capi.STAGE_VEIN_END):
-            sim.run_stage(st); orc.run_stage(st)
-        if same.all():
-            refcheck.assert_close(refcheck.down(sim, capi.PARTICLE_POS), refcheck.down(orc, capi.PARTICLE_POS), f"{tag} step {step} positions", scale=0.0)
-            refcheck.assert_close(refcheck.down(sim, capi.VEIN_POS), refcheck.down(orc, capi.VEIN_POS), f"{tag} step {step} vein positions", scale=0.0)
-
-
 @pytest.mark.parametrize("semantics", [capi.SEM_CLEAN, capi.SEM_REFERENCE])
 @pytest.mark.parametrize("cfg,variant", [("mini3", "wide"), ("cfg1", "wide"), ("cfg1", "spawn")])
 def test_vs_oracle_default_vein(bcs_lib, oracle_lib, cfg, variant, semantics):
@@ -105,7 +63,7 @@ def test_vs_oracle_default_vein(bcs_lib, oracle_lib, cfg, variant, semantics):
     st, _ = seeded_state(cfg, variant)
     with make_bcs(sc, semantics) as sim, make_oracle(oracle_lib, sc, semantics) as orc:
         orc.upload_state(st)
-        _compare_step(sim, orc, 6, f"{cfg}/{variant}/sem{semantics}")
+        stagecheck.compare_step(sim, orc, sc, 6, f"{cfg}/{variant}/sem{semantics}")
 
 
 def test_vs_oracle_cylinder_scene(bcs_lib, oracle_lib):
@@ -113,7 +71,7 @@ def test_vs_oracle_cylinder_scene(bcs_lib, oracle_lib):
     st = pkg.make_initial_state(sc, seed=7, xz_half_width=49.0, y_range=(-25.0, -110.0))
     with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
         orc.upload_state(st)
-        _compare_step(sim, orc, 8, "cylinder")
+        stagecheck.compare_step(sim, orc, sc, 8, "cylinder")
 
 
 @pytest.mark.parametrize("semantics,wall_margin", [(capi.SEM_CLEAN, None), (capi.SEM_CLEAN, "0.0002"), (capi.SEM_REFERENCE, None)])
@@ -169,7 +127,8 @@ def test_fused_step_equals_staged_step(bcs_lib, semantics):
                 b.run_stage(stage)
             if step % 10 == 9:
                 for which, name in ((capi.PARTICLE_POS, "pos"), (capi.PARTICLE_VEL, "vel"), (capi.PARTICLE_FRC, "frc"), (capi.VEIN_POS, "vein pos")):
-                    refcheck.assert_close(refcheck.down(a, which), refcheck.down(b, which), f"step {step} {name}", rtol=1e-4)
+                    # the fused tail evaluates the same expressions as the staged kernels: bitwise equal state
+                    assert np.array_equal(refcheck.down(a, which), refcheck.down(b, which)), f"step {step} {name}: fused and staged step differ"
         assert a.step_count() == b.step_count() == 60
         assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
 
@@ -183,7 +142,7 @@ def test_graph_and_plain_launch_agree(bcs_lib):
             sim.upload_state(st)
             sim.step(20)
             out.append(refcheck.down(sim, capi.PARTICLE_POS))
-    refcheck.assert_close(out[0], out[1], "graph replay vs plain launches", rtol=1e-4, scale=0.0)
+    assert np.array_equal(out[0], out[1]), "graph replay and plain launches must give the same bits"
 
 
 def test_headless_cpp_driver_matches_python_path(bcs_lib, tmp_path):
@@ -205,7 +164,7 @@ def test_headless_cpp_driver_matches_python_path(bcs_lib, tmp_path):
         sim.upload_state(st)
         sim.step(25)
         pos = refcheck.down(sim, capi.PARTICLE_POS)
-    refcheck.assert_close(np.stack([out["pos_x"], out["pos_y"], out["pos_z"]], 1), pos, "C++ headless loop vs bcs_step", rtol=1e-4, scale=0.0)
+    assert np.array_equal(np.stack([out["pos_x"], out["pos_y"], out["pos_z"]], 1), pos), "C++ headless loop vs bcs_step: same library, same bits"
 
 
 def test_checkpoint_restart_is_bit_identical(bcs_lib, tmp_path):
