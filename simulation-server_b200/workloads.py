@@ -83,7 +83,7 @@ def cfg1(seed: int = 1234):
 
 
 def cfg2(seed: int = 1234):
-    sc, st, info = default_vein_scene(5000, 0, seed, xz_half_width=34.0, y_range=(-30.0, -400.0))
+    sc, st, info = default_vein_scene(5000, 0, seed, xz_half_width=50.0, y_range=(-30.0, -400.0))
     info.update(workload="cfg2_default_vein_100000", density="5 000 blood cells over 370 units of the default vein's trunk")
     return sc, st, info
 

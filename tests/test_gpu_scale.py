@@ -12,7 +12,7 @@ import pytest
 
 import refcheck
 import stagecheck
-from conftest import capi, make_bcs, make_oracle
+from conftest import capi, make_bcs, make_oracle, pkg
 
 pytestmark = pytest.mark.gpu
 
@@ -38,9 +38,22 @@ def _free_run_agreement(sim, orc, st, steps, tag):
     return med / D, p999 / D
 
 
+def _wide_state(sc, seed=77):
+    """blood cells spread out to the wall, so that particle-wall contacts happen from the first step on"""
+    return pkg.make_initial_state(sc, seed=seed, xz_half_width=44.0, y_range=(-20.0, float(sc.vein_pos[:, 1].min()) + 40.0))
+
+
+def _adopt_state(orc, sim):
+    """oracle <- the device handle's current state (after a free run on the GPU)"""
+    for which in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.VEIN_FRC):
+        refcheck.up(orc, which, refcheck.down(sim, which))
+    orc.set_step_count(sim.step_count())
+
+
 def test_long_vein_100k_staged_vs_oracle(bcs_lib, oracle_lib):
-    """configs[1]-sized section of the bench workload: 3 staged steps, then 20 free steps."""
+    """configs[1]-sized section of the bench workload, blood cells spread to the wall: 3 staged steps, then 20 free steps."""
     sc, st, info = workloads.long_vein(100_000)
+    st = _wide_state(sc)
     with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
         orc.upload_state(st)
         s = stagecheck.compare_step(sim, orc, sc, 3, "long_vein_100k")
@@ -55,9 +68,14 @@ def test_long_vein_1m_staged_vs_oracle(bcs_lib, oracle_lib):
     with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
         orc.upload_state(st)
         s = stagecheck.compare_step(sim, orc, sc, 1, "long_vein_1m")
-        assert s["pair_hits"] > 10000 and s["vein_hits"] > 1000, s
+        assert s["pair_hits"] > 10000, s
         _free_run_agreement(sim, orc, st, 2, "long_vein_1m")
-        stagecheck.compare_step(sim, orc, sc, 1, "long_vein_1m after 3 steps")
+        # the state the timed window of bench.py sees: 60 more steps on the GPU (blood cells reach the wall), adopted by
+        # the oracle, then one more staged step
+        sim.step(60)
+        _adopt_state(orc, sim)
+        s = stagecheck.compare_step(sim, orc, sc, 1, "long_vein_1m after 63 steps")
+        assert s["pair_hits"] > 10000 and s["vein_hits"] > 300, s
 
 
 def test_default_vein_100k_staged_vs_oracle(bcs_lib, oracle_lib):
@@ -73,6 +91,7 @@ def test_default_vein_100k_staged_vs_oracle(bcs_lib, oracle_lib):
 def test_culled_wall_search_equals_exhaustive_100k(bcs_lib):
     """wall grid + near-wall probe vs the reference's exhaustive in-order traversal on the 100 k long-vein scene: bitwise."""
     sc, st, info = workloads.long_vein(100_000)
+    st = _wide_state(sc)
     arrays = (capi.PARTICLE_FRC, capi.PARTICLE_VEL)
     hits = 0
     with make_bcs(sc) as fast, make_bcs(sc, exhaustive_vein_traversal=True) as slow:
