@@ -98,7 +98,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- roofline
-def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, hits: int = 0):
+def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, hits: int = 0, rows: int = 0):
     """Compulsory bytes of one launch (fp32 vec3 = 12 B, ids = 4 B); DESIGN.md section 'Kernels and rooflines'.
     The spring and collision figures are SURVEY.md 8(d)'s contract numbers."""
     table = {
@@ -110,7 +110,16 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "radix_scatter": 16 * N,
         "clear_cells": 4 * N + 8 * c_occ,
         "count_cell_starts": 4 * N,
-        "finalize_grid": 8 * N + 12 * c_occ + 48 * N,   # R key+id; W start+key (+mask bit) per occupied cell; reorder pos+vel R+W
+        # compact cell index: R key+id; W start+key (+mask bit) per occupied cell; reorder pos+vel R+W.
+        # row directory (rows > 0): R (key, id) 8N + pos 12N, W key+id 8N + sorted pos 12N
+        "finalize_grid": 40 * N if rows else 8 * N + 12 * c_occ + 48 * N,
+        "row_start_totals": 4 * rows, "row_start_scan": 8 * rows,      # R counts (twice), W starts
+        "row_scatter": 20 * N,                     # R (key, place) 8N + row start 4N, W (key, id) 8N
+        "pair_walk": 0,                            # fall-back of the pair search: returns at once
+        "pair_apply": 120 * hits,                  # forces of the touching pairs (a few % of the particles)
+        # end of step k + springs / row count of step k+1 in one pass: R pos,vel,frc 36N, W pos,vel,frc 36N, W (key, place) 8N,
+        # W centres 12B.  (The three stages it replaces: finish_step 72N + springs 48N + 12B + cell_keys 20N.)
+        "advance": 80 * N + 12 * B,
         "vein_gather": 120 * V,
         "springs": 48 * N + 12 * B,                # R pos,vel,frc 36N, W frc 12N, W centres 12B
         "particle_collisions": 56 * N + 8 * c_occ,
@@ -379,9 +388,11 @@ def run_product(args):
     peak, peak_src = measured_peaks()
     traffic = ncu_traffic()
 
+    rows = int(sim.layout.grid_dims[1]) * int(sim.layout.grid_dims[2]) if "row_scatter" in prof else 0
+
     def roof(name):
         per_launch_ms = prof[name][0] / prof[name][1]
-        b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits)
+        b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits, rows)
         gbs = b / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         t = traffic.get(name) if world == 1 and args.workload == "long_vein" and args.particles == 1_000_000 else None
         return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
@@ -390,7 +401,17 @@ def run_product(args):
 
     roofline = roof(dominant)
     roofline["contract_kernels"] = {k: roof(k) for k in CONTRACT_KERNELS if k in prof}
-    step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits) * v[1] / prof_steps for k, v in prof.items())
+    if "pair_apply" in prof:
+        # the collision STAGE is pair search + (idle) fall-back + pair apply: SURVEY 8(d)'s stage figure over their summed time
+        c = roofline["contract_kernels"]["particle_collisions"]
+        stage_ms = sum(prof[k][0] / prof[k][1] for k in ("particle_collisions", "pair_walk", "pair_apply") if k in prof)
+        c.update({"kernel": "particle_collisions + pair_walk + pair_apply (the stage)", "search_ms_per_launch": c["ms_per_launch"], "ms_per_launch": stage_ms,
+                  "achieved": c["algorithmic_bytes_per_launch"] / (stage_ms * 1e-3) / 1e9})
+        c["frac"] = c["achieved"] / peak
+    if "advance" in prof:
+        roofline["contract_kernels"]["advance"] = roof("advance")
+        roofline["contract_kernels"]["advance"]["stages_replaced_bytes"] = 140 * N_alg + 12 * B_alg
+    step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits, rows) * v[1] / prof_steps for k, v in prof.items())
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region

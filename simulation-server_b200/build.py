@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libbcs.so")
 
-CUDA_SOURCES = ["grid.cu", "springs.cu", "collide.cu", "vein.cu", "wall.cu", "integrate.cu", "slab.cu", "capi.cu"]
+CUDA_SOURCES = ["grid.cu", "cellpass.cu", "collide.cu", "pairs.cu", "vein.cu", "wall.cu", "integrate.cu", "slab.cu", "capi.cu"]
 HOST_SOURCES = ["scene_host.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

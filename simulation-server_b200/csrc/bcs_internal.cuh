@@ -87,6 +87,8 @@ struct GridDev {
     int cells;
     int n;                      // objects
     int keyBits;                // bits needed for a cell id
+    float icsx, icsy, icsz;     // 1 / cell size, exact when pow2 != 0 (the reference's 2-unit particle grid)
+    int pow2;                   // all three cell sizes are powers of two: (p - min) / cs == (p - min) * ics bit for bit
 };
 
 struct PhysDev {

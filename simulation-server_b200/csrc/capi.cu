@@ -171,8 +171,19 @@ struct bcs_sim {
     GridDev pg{}, tg{};
     PhysDev phys{};
     SpringPlan plan{};
+    int* slotTab = nullptr;         // per-type tables of the cell pass (cellpass.cu)
+    int2* adjTab = nullptr;
+    // row-directory grid + symmetric pair search (clean semantics, sparse scenes; grid.cu / pairs.cu)
+    RowsGrid rows{};
+    PairLists pairs{};
+    unsigned long long* phaseClock = nullptr;   // BCS_CP_CLOCK: per-phase cycle sums of the cell pass (developer aid)
+    bool collideWalk = false;       // BCS_COLLIDE=walk: every slot scans its whole stencil (A/B partner of the pair search)
+    bool fuseSteps = false;         // bcs_step(n): end of step k + springs / row count of step k + 1 in one pass (cellpass.cu)
     bool gridBuilt = false;
     cudaGraphExec_t graphExec = nullptr;
+    cudaGraphExec_t graphMid = nullptr, graphLast = nullptr;   // fused run: a step that hands over to the next one / the last step
+    unsigned long long kernelsMid = 0, kernelsLast = 0;
+    cudaEvent_t evRebuilt = nullptr, evGrid = nullptr;
     LaunchCtx ctx;
     unsigned long long kernelsPerGraph = 0;
     SlabState* slab = nullptr;   // multi-GPU slab mode
@@ -201,6 +212,8 @@ GridDev make_grid(const HostScene& hs, const int cs[3], const int dims[3], int n
     g.cells = dims[0] * dims[1] * dims[2];
     g.n = n;
     g.keyBits = bits_for(g.cells);
+    g.icsx = 1.0f / (float)cs[0]; g.icsy = 1.0f / (float)cs[1]; g.icsz = 1.0f / (float)cs[2];
+    g.pow2 = ((cs[0] & (cs[0] - 1)) == 0 && (cs[1] & (cs[1] - 1)) == 0 && (cs[2] & (cs[2] - 1)) == 0) ? 1 : 0;
     return g;
 }
 
@@ -247,6 +260,7 @@ GridBuildArgs particle_grid_args(bcs_sim* s)
     a.occStart = s->occStart; a.occKey = s->occKey; a.numOcc = s->numOcc;
     a.reorder = true;
     a.pos = s->pos; a.vel = s->vel; a.spos = s->spos; a.svel = s->svel;
+    a.rows = s->rows;
     if (s->slab) {
         a.pflag = s->slab->pflag; a.nDev = s->slab->nActive; a.nDevOut = s->slab->nActive;
         a.items.cells = s->slab->listCells; a.items.cellPrefix = s->slab->listCellPrefix;
@@ -433,6 +447,10 @@ CollideArgs collide_args(bcs_sim* s)
     a.reference = s->semantics == BCS_SEM_REFERENCE; a.stats = s->stats;
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
     a.nDev = s->slab ? s->slab->nActive : nullptr;
+    a.rowsMode = s->rows.enabled != 0; a.fullWalk = s->collideWalk;
+    a.rowStart = s->rows.rowStart; a.nRows = s->rows.nRows; a.ids = s->ids[1]; a.vel = s->vel;
+    a.irregular = s->rows.irregular ? s->rows.irregular + 1 : nullptr;   // latched copy (row_order_kernel)
+    a.pairs = s->pairs;
     return a;
 }
 
@@ -465,7 +483,8 @@ void stage(bcs_sim* s, int st)
     }
     case BCS_STAGE_PARTICLE_COLLISIONS:
         BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle collisions need a built grid (bcs_build_grid)");
-        launch_particle_collisions(collide_args(s), s->stream);
+        if (s->rows.enabled) launch_particle_collisions_rows(collide_args(s), s->stream);
+        else launch_particle_collisions(collide_args(s), s->stream);
         break;
     case BCS_STAGE_VEIN_COLLISIONS: {
         VeinCollideArgs a = vein_collide_args(s);
@@ -503,8 +522,9 @@ SpringArgs spring_args(bcs_sim* s, bool withProbe)
     SpringArgs a{};
     a.types = s->types; a.typesDev = s->typesDev; a.plan = s->plan; a.phys = s->phys;
     a.pos = s->pos; a.vel = s->vel; a.frc = s->frc; a.centers = s->centers;
-    a.adjJ = s->adjJ; a.adjL = s->adjL; a.adjS = s->adjS; a.sprAB = s->sprAB; a.sprL = s->sprL; a.initR = s->initR;
+    a.slotTab = s->slotTab; a.adjTab = s->adjTab; a.initR = s->initR;
     if (s->slab) a.lists = slab_lists(s->slab, s->types);
+    a.phaseClock = s->phaseClock;
     if (withProbe && s->wall.enabled) {
         const WallGridDev& w = s->wall;
         a.probe = NearProbe{w.near, w.nearList, w.nearCount, w.ox, w.oy, w.oz, w.invh, w.nx, w.ny, w.nz};
@@ -536,7 +556,7 @@ void enqueue_step(bcs_sim* s)
         } else {
             for (int st = BCS_STAGE_GRID_PARTICLES; st <= BCS_STAGE_VEIN_COLLISIONS; ++st) stage(s, st);
         }
-        launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, m);
+        launch_finish_step(integrate_args(s), spring_args(s), s->doneBlocks, m);
         stage(s, BCS_STAGE_INTEGRATE_VEIN);
     } else {
         // Data flow of a step (reference order main.cu:175-208 + simulation_controller.cu:246-331, which serialises every
@@ -587,10 +607,126 @@ void enqueue_step(bcs_sim* s)
         BCS_CUDA(cudaStreamWaitEvent(s->side[2], s->evMasked, 0));
         launch_vein_integrate(vein_args(s), s->side[2]);
         BCS_CUDA(cudaEventRecord(s->evVein, s->side[2]));
-        launch_finish_step(integrate_args(s), s->plan, s->doneBlocks, m);
+        launch_finish_step(integrate_args(s), spring_args(s), s->doneBlocks, m);
         BCS_CUDA(cudaStreamWaitEvent(m, s->evVein, 0));
     }
     if (s->slab) slab_end_of_step(s->slab, slab_ctx(s));   // migration + halo exchange for the next step
+}
+
+// ---- fused run (bcs_step(n) in row-directory mode) ---------------------------------------------------------------------
+// The spring stage of step k + 1 reads exactly what the tail of step k writes (positions, velocities; forces are never
+// zeroed), group by group of whole blood cells, so both run as ONE pass over the particle state (launch_advance,
+// cellpass.cu) that also counts the new positions into the row directory of the next grid build.  A run of n steps is
+//   head   springs + row count                                        (one launch)
+//   body   row scan, scatter, order (+ near-wall probe) | pair search + apply | wall search + apply | vein
+//   end    advance = integrate + vein end + springs + row count (steps 1 .. n-1) / finish_step (step n)
+// with the same results, bit for bit, as n unfused steps (test_fused_run_equals_single_steps).
+void enqueue_head(bcs_sim* s)
+{
+    launch_springs_count(spring_args(s), s->pg, s->rows, s->counters, s->stream);
+}
+
+void enqueue_body(bcs_sim* s, bool last)
+{
+    cudaStream_t m = s->stream;
+    const bool fork = s->overlap && !s->ctx.timing && s->side[0];
+    VeinCollideArgs va = vein_collide_args(s);
+    const bool wall = va.wall.enabled != 0;
+    const bool probeOn = wall && s->nearProbe;
+    GridBuildArgs ga = particle_grid_args(s);
+    ga.rows.countDone = 1;
+    NearProbe probe{};
+    if (probeOn) {
+        const WallGridDev& w = s->wall;
+        probe = NearProbe{w.near, w.nearList, w.nearCount, w.ox, w.oy, w.oz, w.invh, w.nx, w.ny, w.nz};
+        ga.probe = &probe;
+        va.wall.useNearList = 1;
+    }
+    cudaStream_t sWall = fork ? s->side[0] : m, sVein = fork ? s->side[2] : m;
+    if (fork) {
+        BCS_CUDA(cudaEventRecord(s->evFork, m));
+        BCS_CUDA(cudaStreamWaitEvent(sWall, s->evFork, 0));
+        BCS_CUDA(cudaStreamWaitEvent(sVein, s->evFork, 0));
+    }
+    // wall structure up to date before anything probes it
+    if (wall) {
+        launch_wall_reset(va, sWall);
+        launch_wall_rebuild(va, s->hs.V, s->numSMs, sWall);
+        if (fork) BCS_CUDA(cudaEventRecord(s->evRebuilt, sWall));
+    }
+    launch_vein_gather(vein_args(s), sVein);
+    if (fork) BCS_CUDA(cudaEventRecord(s->evGather, sVein));
+    if (fork && wall) BCS_CUDA(cudaStreamWaitEvent(m, s->evRebuilt, 0));
+    launch_grid_build(ga, m);
+    s->gridBuilt = true;
+    if (wall) {
+        if (fork) {
+            BCS_CUDA(cudaEventRecord(s->evGrid, m));
+            BCS_CUDA(cudaStreamWaitEvent(sWall, s->evGrid, 0));
+        }
+        launch_wall_search(va, sWall);
+        if (fork) BCS_CUDA(cudaEventRecord(s->evWall, sWall));
+    }
+    launch_particle_collisions_rows(collide_args(s), m);
+    if (fork) {
+        if (wall) BCS_CUDA(cudaStreamWaitEvent(m, s->evWall, 0));
+        BCS_CUDA(cudaStreamWaitEvent(m, s->evGather, 0));
+    }
+    if (wall) {
+        launch_wall_apply(va, m);
+    } else {
+        launch_tri_refit(va, m);
+        launch_vein_collisions(va, m);
+    }
+    if (fork) {
+        BCS_CUDA(cudaEventRecord(s->evMasked, m));
+        BCS_CUDA(cudaStreamWaitEvent(sVein, s->evMasked, 0));
+    }
+    launch_vein_integrate(vein_args(s), sVein);
+    if (fork) BCS_CUDA(cudaEventRecord(s->evVein, sVein));
+    if (last) launch_finish_step(integrate_args(s), spring_args(s), s->doneBlocks, m);
+    else launch_advance(integrate_args(s), spring_args(s), s->pg, s->rows, s->doneBlocks, m);
+    if (fork) BCS_CUDA(cudaStreamWaitEvent(m, s->evVein, 0));
+}
+
+cudaGraphExec_t capture_body(bcs_sim* s, bool last, unsigned long long* kernels)
+{
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    BCS_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long before = s->ctx.launches;
+    try {
+        enqueue_body(s, last);
+        *kernels = s->ctx.launches - before;
+        s->ctx.launches = before;   // captured, not executed
+    } catch (...) {
+        cudaStreamEndCapture(s->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    BCS_CUDA(cudaStreamEndCapture(s->stream, &graph));
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    BCS_CUDA(e);
+    return exec;
+}
+
+void run_fused(bcs_sim* s, int nsteps)
+{
+    if (nsteps <= 0) return;
+    enqueue_head(s);
+    if (!s->useGraph || s->ctx.timing) {
+        for (int i = 0; i < nsteps; ++i) enqueue_body(s, i == nsteps - 1);
+        return;
+    }
+    if (nsteps > 1 && !s->graphMid) s->graphMid = capture_body(s, false, &s->kernelsMid);
+    if (!s->graphLast) s->graphLast = capture_body(s, true, &s->kernelsLast);
+    for (int i = 0; i + 1 < nsteps; ++i) {
+        BCS_CUDA(cudaGraphLaunch(s->graphMid, s->stream));
+        s->ctx.launches += s->kernelsMid;
+    }
+    BCS_CUDA(cudaGraphLaunch(s->graphLast, s->stream));
+    s->ctx.launches += s->kernelsLast;
 }
 
 struct Array {
@@ -617,13 +753,25 @@ void destroy(bcs_sim* s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->phaseClock) {
+        unsigned long long c[8] = {};
+        cudaMemcpy(c, s->phaseClock, sizeof c, cudaMemcpyDeviceToHost);
+        unsigned long long tot = 0;
+        for (int k = 0; k < 7; ++k) tot += c[k];
+        static const char* names[7] = {"setup+issue", "tile wait", "integrate", "centres", "springs", "gather+env", "count+writeback"};
+        fprintf(stderr, "cell pass phases (share of summed warp cycles):");
+        for (int k = 0; k < 7; ++k) fprintf(stderr, "  %s %.1f%%", names[k], tot ? 100.0 * (double)c[k] / (double)tot : 0.0);
+        fprintf(stderr, "\n");
+    }
     if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
     slab_destroy(s->slab);
     for (void* p : s->owned) cudaFree(p);
     s->sortP.release();
     s->sortT.release();
     for (cudaStream_t q : s->side) if (q) cudaStreamDestroy(q);
-    for (cudaEvent_t e : {s->evFork, s->evSprings, s->evWall, s->evGather, s->evMasked, s->evVein}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s->evFork, s->evSprings, s->evWall, s->evGather, s->evMasked, s->evVein, s->evRebuilt, s->evGrid}) if (e) cudaEventDestroy(e);
+    if (s->graphMid) cudaGraphExecDestroy(s->graphMid);
+    if (s->graphLast) cudaGraphExecDestroy(s->graphLast);
     if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -680,7 +828,8 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             const HostType& h = hs.types[i];
             s->types.t[i] = TypeDev{h.count, h.P, h.pStart, h.cStart, h.mStart, h.warpSync, hs.adjStart[i], hs.maxDeg[i], hs.sprStart[i], hs.nSpr[i]};
         }
-        s->plan = make_spring_plan(s->types);
+        SpringTables springTables;
+        s->plan = make_spring_plan(s->types, hs, springTables);
         s->pg = make_grid(hs, hs.cellSize, hs.gdims, N);
         s->tg = make_grid(hs, hs.triCellSize, hs.tdims, T);
         fill_phys(hs, s->phys);
@@ -689,7 +838,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->spos = s->track(dev_alloc<float4>(N)); s->svel = s->track(dev_alloc<float4>(N));
         s->centers = s->track(dev_alloc<float4>(B));
         for (int k = 0; k < 2; ++k) {
-            s->keys[k] = s->track(dev_alloc<int>(N)); s->ids[k] = s->track(dev_alloc<int>(N));
+            s->keys[k] = s->track(dev_alloc<int>((size_t)N + 4)); s->ids[k] = s->track(dev_alloc<int>(N));   // + key sentinels (pairs.cu)
             s->tkeys[k] = s->track(dev_alloc<int>(T)); s->tids[k] = s->track(dev_alloc<int>(T));
         }
         s->tcellStart = s->track(dev_alloc<int>(s->tg.cells)); s->tcellEnd = s->track(dev_alloc<int>(s->tg.cells));
@@ -701,6 +850,37 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             s->occStart = s->track(dev_alloc<int>((size_t)N + 1));
             s->occKey = s->track(dev_alloc<int>(N));
             s->numOcc = s->track(dev_alloc<int>(1));
+            // Row-directory grid + symmetric pair search: the default where rows are short (sparse scenes such as the long
+            // vein: ~5 particles per occupied row); dense scenes (hundreds of particles per row) keep the compact cell index.
+            // BCS_GRID=rows / cells / radix overrides.
+            {
+                const char* gm = getenv("BCS_GRID");
+                const long long nRows = (long long)s->pg.ny * s->pg.nz;
+                const bool sparse = (double)N <= 4.0 * (double)nRows;
+                const bool want = gm ? std::string(gm) == "rows" : sparse;
+                if (want && nRows < (1ll << 30)) {
+                    RowsGrid& R = s->rows;
+                    R.enabled = 1;
+                    R.nRows = (int)nRows;
+                    R.rowCount = s->track(dev_alloc<unsigned>((size_t)nRows + 16));
+                    R.rowStart = s->track(dev_alloc<int>((size_t)nRows + 16));
+                    R.kp = s->track(dev_alloc<int2>(N));
+                    R.tmp = s->track(dev_alloc<int2>(N));
+                    R.irregular = s->track(dev_alloc<int>(2));
+                    int l = 0;
+                    while ((1ll << l) < s->pg.nx) ++l;
+                    R.nxShift = 32 + l;
+                    R.nxMagic = ((1ull << R.nxShift) + (unsigned long long)s->pg.nx - 1ull) / (unsigned long long)s->pg.nx;
+                    PairLists& L = s->pairs;
+                    L.head = s->track(dev_alloc<int>(N, false));
+                    BCS_CUDA(cudaMemset(L.head, 0xFF, (size_t)N * sizeof(int)));
+                    L.poolStart = 8 * N; L.pool = 2 * N + 1024;
+                    L.entries = s->track(dev_alloc<int2>((size_t)L.poolStart + L.pool, false));
+                    L.ctl = s->track(dev_alloc<int>(4));
+                    const char* cm = getenv("BCS_COLLIDE");
+                    s->collideWalk = cm && std::string(cm) == "walk";
+                }
+            }
             // triangle grid: dense tables, empty cell = (start 0, end -1)
             BCS_CUDA(cudaMemset(s->tcellEnd, 0xFF, (size_t)s->tg.cells * sizeof(int)));
             BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
@@ -729,10 +909,13 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->endC = s->track(dev_upload(hs.endC)); s->endR = s->track(dev_upload(hs.endR));
         s->adjJ = s->track(dev_upload(hs.adjJ)); s->adjL = s->track(dev_upload(hs.adjL));
         s->adjS = s->track(dev_upload(hs.adjS)); s->sprAB = s->track(dev_upload(hs.sprAB)); s->sprL = s->track(dev_upload(hs.sprL));
+        s->slotTab = s->track(dev_upload(springTables.slot)); s->adjTab = s->track(dev_upload(springTables.adj));
+        cell_pass_prepare(s->plan);   // function attributes are per device: set for THIS handle's device
+        if (getenv("BCS_CP_CLOCK")) s->phaseClock = s->track(dev_alloc<unsigned long long>(8));
         s->counters = s->track(dev_alloc<Counters>(1));
         s->stagingLen = std::max(std::max(N, V), std::max(B, T));
         s->staging = s->track(dev_alloc<float>(3 * (size_t)s->stagingLen));
-        s->sortP.allocate(N, s->pg.cells / 32 + 2);
+        s->sortP.allocate(N, std::max(s->pg.cells / 32 + 2, s->pg.ny * s->pg.nz + 2));
         s->sortT.allocate(T);
 
         // vein vertices -> device, triangle centres (calculateCentersKernel, run once), static triangle grid
@@ -751,9 +934,11 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->nearProbe = !getenv("BCS_NO_NEAR_PROBE");
         if (s->overlap) {
             for (cudaStream_t& q : s->side) BCS_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
-            for (cudaEvent_t* e : {&s->evFork, &s->evSprings, &s->evWall, &s->evGather, &s->evMasked, &s->evVein})
+            for (cudaEvent_t* e : {&s->evFork, &s->evSprings, &s->evWall, &s->evGather, &s->evMasked, &s->evVein, &s->evRebuilt, &s->evGrid})
                 BCS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         }
+        // fused run (bcs_step(n), n > 1): needs the row-directory grid (its count pass rides in the cell pass); single GPU
+        s->fuseSteps = s->rows.enabled && !slabOpts && !getenv("BCS_NO_FUSE");
         if (slabOpts) {
             BCS_REQUIRE(slabOpts->struct_size == sizeof(bcs_slab_opts), BCS_ERR_INVALID, "bcs_slab_opts.struct_size mismatch");
             BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN, BCS_ERR_UNSUPPORTED, "slab decomposition needs clean semantics");
@@ -1034,7 +1219,9 @@ int bcs_step(bcs_sim* s, int32_t nsteps)
     CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
     if (s->slab && !s->slab->primed) slab_prime(s->slab, slab_ctx(s));   // ownership + first halo exchange, outside any capture
-    if (!s->useGraph) {
+    if (s->fuseSteps) {
+        run_fused(s, nsteps);
+    } else if (!s->useGraph) {
         for (int i = 0; i < nsteps; ++i) enqueue_step(s);
     } else {
         if (!s->graphExec) {
@@ -1082,7 +1269,8 @@ int bcs_profile_steps(bcs_sim* s, int32_t nsteps, int32_t cap, char (*names)[BCS
     s->ctx.records.clear();
     s->ctx.timing = true;
     try {
-        for (int i = 0; i < nsteps; ++i) enqueue_step(s);
+        if (s->fuseSteps) run_fused(s, nsteps);
+        else for (int i = 0; i < nsteps; ++i) enqueue_step(s);
     } catch (...) {
         s->ctx.timing = false;
         throw;
@@ -1187,6 +1375,27 @@ int bcs_download_cell_table(bcs_sim* s, int which, int32_t cap, int32_t* cells, 
     BCS_API_BEGIN
     BCS_REQUIRE(s && cells && starts && ends && count, BCS_ERR_INVALID, "null argument");
     BCS_CUDA(cudaSetDevice(s->device));
+    if (!which && s->rows.enabled) {
+        // row-directory mode keeps no per-cell table: the (debug) view is derived from the sorted keys
+        BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
+        int n = s->hs.N;
+        if (s->slab) BCS_CUDA(cudaMemcpyAsync(&n, s->slab->nActive, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        std::vector<int> keys((size_t)std::max(n, 1));
+        BCS_CUDA(cudaMemcpyAsync(keys.data(), s->keys[1], (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        int k = 0;
+        for (int i = 0; i < n; ++i) {
+            if (i == 0 || keys[i] != keys[i - 1]) {
+                if (k < cap) { cells[k] = keys[i]; starts[k] = i; }
+                ++k;
+            }
+            if (k - 1 < cap) ends[k - 1] = i;
+        }
+        *count = k;
+        BCS_REQUIRE(k <= cap, BCS_ERR_INVALID, "capacity too small for the cell table");
+        return BCS_OK;
+    }
     if (!which && s->semantics == BCS_SEM_CLEAN) {
         // compact index: the occupied cells are stored explicitly
         BCS_REQUIRE(s->gridBuilt, BCS_ERR_STATE, "particle grid has not been built yet");
@@ -1236,7 +1445,8 @@ int bcs_debug_candidates(bcs_sim* s, int32_t* counts, uint64_t* sums, int32_t* h
     a.dbgCount = dc; a.dbgSum = ds; a.dbgHits = dh;
     cudaError_t e = cudaSuccess;
     try {
-        launch_particle_collisions(a, s->stream);
+        if (s->rows.enabled) launch_particle_collisions_rows(a, s->stream);
+        else launch_particle_collisions(a, s->stream);
         BCS_CUDA(cudaMemcpyAsync(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         BCS_CUDA(cudaMemcpyAsync(hits, dh, n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         BCS_CUDA(cudaMemcpyAsync(sums, ds, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));

@@ -18,51 +18,11 @@
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include "pair_device.cuh"
 
 #include <algorithm>
 
 namespace bcs {
-
-__device__ __forceinline__ void stencil_range(int id, int count, int& lo, int& hi)
-{
-    // particle_collisions.cuh:126-268: `id < 1` / `id > count - 2` / else
-    if (id < 1) { lo = 0; hi = 1; }
-    else if (id > count - 2) { lo = -1; hi = 0; }
-    else { lo = -1; hi = 1; }
-}
-
-struct PairAccum {
-    float3 F;
-    int hits;
-};
-
-// detectCollision (particle_collisions.cuh:26-38): the distance test
-__device__ __forceinline__ bool pair_touches(const float3 p1, const float r1, const float4 q4, const float r2)
-{
-    // The touch decision is a threshold on d2, so its rounding sequence is pinned (the compiler is otherwise free to
-    // contract x*x + y*y + z*z in either association): the FMA chain nvcc emits for the reference's length_squared.
-    // The oracle evaluates the same chain (std::fmaf), which makes hit sets bit-identical, not just the candidate sets.
-    const float3 rel = p1 - xyz(q4);
-    const float d2 = __fmaf_rn(rel.z, rel.z, __fmaf_rn(rel.y, rel.y, __fmul_rn(rel.x, rel.x)));
-    const float minD = r1 + r2;
-    return d2 <= __fmul_rn(minD, minD) && d2 >= 0.0001f;
-}
-
-// addResilientForceOnCollision with intensityCoefficient 0.5 (physics.cuh:133-145) for a pair that touches
-__device__ __forceinline__ void pair_force(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,
-                                           const float4* __restrict__ svel, int j, PairAccum& acc)
-{
-    const float3 rel = p1 - xyz(q4);
-    const float d2 = length_squared(rel);
-    const float3 rv = v1 - xyz(svel[j]);
-    const float3 dir = normalize(rel);
-    const float3 tang = rv - dot(rv, dir) * dir;
-    const float3 spring = (-ph.coll_spring * (r1 * 2 - sqrtf(d2))) * dir;
-    const float3 damp = ph.coll_damping * rv;
-    const float3 shear = ph.coll_shear * tang;
-    acc.F = acc.F + 0.5f * (spring + damp + shear);
-    ++acc.hits;
-}
 
 // detectCollision + addResilientForceOnCollision with intensityCoefficient 0.5
 __device__ __forceinline__ void test_pair(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4,

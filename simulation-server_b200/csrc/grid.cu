@@ -7,6 +7,7 @@
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include "rows_device.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -854,6 +855,114 @@ __global__ void __launch_bounds__(256) cs_order_kernel(int nArg, const int* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-directory grid build (RowsGrid, kernels.cuh): count -> scan -> scatter -> order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_count_kernel(const float4* __restrict__ pos, const unsigned char* __restrict__ pflag, const GridDev g,
+                                                        const RowsGrid R, Counters* __restrict__ counters, int* __restrict__ nActive,
+                                                        const ActiveItems act)
+{
+    const int total = act.cells ? item_total(act) : g.n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x, f = 1;
+        bool on;
+        if (act.cells) {
+            i = i < total ? active_item(act, i, f) : -1;
+            on = i >= 0;
+        } else {
+            on = i < g.n;
+            if (on && pflag) { f = pflag[i]; on = f != 0; }
+        }
+        if (on) rows_count_particle(g, R, pos[i], i, f, counters);
+        if (nActive) {
+            const int blockActive = __syncthreads_count(on);
+            if (threadIdx.x == 0 && blockActive) atomicAdd(nActive, blockActive);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) row_scatter_kernel(const unsigned char* __restrict__ pflag, int n, const RowsGrid R, const ActiveItems act)
+{
+    const int total = act.cells ? item_total(act) : n;
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        int i = base + threadIdx.x, f = 1;
+        if (act.cells) {
+            if (i >= total) continue;
+            i = active_item(act, i, f);
+            if (i < 0) continue;
+        } else {
+            if (i >= n) continue;
+            if (pflag) { f = pflag[i]; if (!f) continue; }
+        }
+        const int2 kp = R.kp[i];
+        const int row = rows_div((unsigned)kp.x, R.nxMagic, R.nxShift);
+        R.tmp[R.rowStart[row] + kp.y] = make_int2(kp.x, (f & 1) ? i : (i | (int)0x80000000));
+    }
+}
+
+// order: final slot = row start + number of row mates that sort before (cell id, particle id).  Also the near-wall probe
+// of the wall search (NearProbe, kernels.cuh) when the step is fused: every position passes through here anyway.
+template <bool PROBE>
+__global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __restrict__ nDev, const RowsGrid R, int* __restrict__ keys,
+                                                        int* __restrict__ ids, const float4* __restrict__ pos, float4* __restrict__ spos,
+                                                        const NearProbe probe)
+{
+    const int n = nDev ? *nDev : nArg;
+    // latch the "irregular particle" flag of this build (the count pass of the NEXT build may already run - fused into
+    // the cell pass - before this build's collision stages are through with it)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { R.irregular[1] = R.irregular[0]; R.irregular[0] = 0; }
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int j = base + threadIdx.x;
+        bool isNear = false;
+        int pidOut = 0;
+        if (j < n) {
+            const int2 me = R.tmp[j];
+            const int key = me.x, tag = me.y, pid = tag & 0x7fffffff;
+            const float4 p = pos[pid];
+            const int row = rows_div((unsigned)key, R.nxMagic, R.nxShift);
+            const int s = R.rowStart[row], e = R.rowStart[row + 1];
+            int before = 0;
+            for (int k = s; k < e; ++k) {
+                const int2 o = R.tmp[k];
+                before += (o.x < key) || (o.x == key && (o.y & 0x7fffffff) < pid);
+            }
+            const int slot = s + before;
+            keys[slot] = key;
+            ids[slot] = tag;
+            spos[slot] = p;
+            if (j == s) R.rowCount[row] = 0u;   // consumed by the scan; clean for the next count pass
+            if (j == n - 1) {
+                // sentinels: the pair search scans keys until one exceeds its window
+                keys[n] = 0x7fffffff; keys[n + 1] = 0x7fffffff; keys[n + 2] = 0x7fffffff; keys[n + 3] = 0x7fffffff;
+            }
+            if (PROBE && tag >= 0) {
+                const int hx = (int)fminf(fmaxf(floorf((p.x - probe.ox) * probe.invh), 0.f), (float)(probe.nx - 1));
+                const int hy = (int)fminf(fmaxf(floorf((p.y - probe.oy) * probe.invh), 0.f), (float)(probe.ny - 1));
+                const int hz = (int)fminf(fmaxf(floorf((p.z - probe.oz) * probe.invh), 0.f), (float)(probe.nz - 1));
+                isNear = __ldg(probe.near + (hz * probe.ny + hy) * probe.nx + hx) != 0;
+                pidOut = pid;
+            }
+        }
+        if (PROBE) {
+            const unsigned m = __ballot_sync(0xffffffffu, isNear);
+            if (m) {
+                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+                int b = 0;
+                if (lane == leader) b = atomicAdd(probe.count, __popc(m));
+                b = __shfl_sync(0xffffffffu, b, leader);
+                if (isNear) probe.list[b + __popc(m & ((1u << lane) - 1u))] = pidOut;
+            }
+        }
+    }
+}
+
+__global__ void row_empty_kernel(int nArg, const int* __restrict__ nDev, int* __restrict__ keys)
+{
+    // no active particle: only the sentinels
+    const int n = nDev ? *nDev : nArg;
+    if (n == 0 && threadIdx.x < 4) keys[threadIdx.x] = 0x7fffffff;
+}
+
+// ------------------------------------------------------------------------------------------------
 // slab mode: cell keys of the active particles (pflag bit 0 = owned, bit 1 = ghost), compacted in ascending
 // particle id so that the stable sort still ends in (cell id, particle id) order
 // ------------------------------------------------------------------------------------------------
@@ -994,6 +1103,45 @@ void SortScratch::release()
     finTileCount = nullptr;
 }
 
+void launch_row_count(const GridBuildArgs& a, cudaStream_t st)
+{
+    const GridDev& g = a.grid;
+    const int blocks = (g.n + 255) / 256;
+    const int itemBlocks = a.items.cells ? (int)std::min<long long>(((long long)a.itemCapacity + 255) / 256, BOUNDED_BLOCKS) : blocks;
+    if (a.nDevOut) BCS_CUDA(cudaMemsetAsync(a.nDevOut, 0, sizeof(int), st));
+    BCS_LAUNCH("cell_keys", st, row_count_kernel<<<itemBlocks, 256, 0, st>>>(a.objPos, a.pflag, g, a.rows, a.counters, a.nDevOut, a.items));
+    BCS_CUDA(cudaGetLastError());
+}
+
+static void launch_grid_build_rows(const GridBuildArgs& a, cudaStream_t st)
+{
+    const GridDev& g = a.grid;
+    const RowsGrid& R = a.rows;
+    const int n = g.n, blocks = (n + 255) / 256;
+    const int itemBlocks = a.items.cells ? (int)std::min<long long>(((long long)a.itemCapacity + 255) / 256, BOUNDED_BLOCKS) : blocks;
+    const int orderBlocks = a.nDev ? std::min(blocks, BOUNDED_BLOCKS) : blocks;
+    SortScratch* sc = a.scratch;
+    if (!R.countDone) launch_row_count(a, st);
+    // rowStart = exclusive scan of the per-row counts; rowStart[nRows] = number of sorted slots
+    const int tiles = (R.nRows + SCAN_TILE - 1) / SCAN_TILE;
+    ScanCtl* ctl = reinterpret_cast<ScanCtl*>(sc->scanCtl);
+    if (sc->twoPassScan) {
+        BCS_LAUNCH("row_start_totals", st, cs_tile_totals_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals));
+        BCS_LAUNCH("row_start_scan", st,
+                   cs_scan_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals, R.rowStart, nullptr, n, a.nDev));
+    } else {
+        BCS_LAUNCH("row_start_scan", st,
+                   cs_scan_fused_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanStatus, ctl, R.rowStart, nullptr, n, a.nDev));
+    }
+    BCS_LAUNCH("row_scatter", st, row_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, R, a.items));
+    if (a.probe && a.probe->near)
+        BCS_LAUNCH("finalize_grid", st, row_order_kernel<true><<<orderBlocks, 256, 0, st>>>(n, a.nDev, R, a.keys[1], a.ids[1], a.pos, a.spos, *a.probe));
+    else
+        BCS_LAUNCH("finalize_grid", st, row_order_kernel<false><<<orderBlocks, 256, 0, st>>>(n, a.nDev, R, a.keys[1], a.ids[1], a.pos, a.spos, NearProbe{}));
+    if (a.nDev) BCS_LAUNCH("row_empty", st, row_empty_kernel<<<1, 32, 0, st>>>(n, a.nDev, a.keys[1]));
+    BCS_CUDA(cudaGetLastError());
+}
+
 static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
 {
     const GridDev& g = a.grid;
@@ -1043,6 +1191,10 @@ static void launch_grid_build_counting(const GridBuildArgs& a, cudaStream_t st)
 
 void launch_grid_build(const GridBuildArgs& a, cudaStream_t st)
 {
+    if (a.rows.enabled) {
+        launch_grid_build_rows(a, st);
+        return;
+    }
     if (a.compact && !a.scratch->radixForCompact) {
         launch_grid_build_counting(a, st);
         return;

@@ -24,6 +24,30 @@ struct SortScratch {
     void release();
 };
 
+// Row-directory grid build (clean semantics, sparse scenes; BCS_GRID=rows).  A "row" is the run of nx x-adjacent cells
+// of one (y, z): cell ids are x-fastest (uniform_grid.cu:33-35), so row r = id / nx and the sorted list is row-major.
+//   count    per particle: key, place = atomicAdd(rowCount[row])            (rides in the cell pass of the previous step)
+//   scan     rowStart = exclusive scan of rowCount                          (nRows entries: 0.7 M for the 1 M-particle vein)
+//   scatter  tmp[rowStart[row] + place] = (key, id)                         rows contiguous, unordered inside
+//   order    per slot: rank of (key, id) inside its row (rows hold ~5 particles) -> keys / ids / sorted positions,
+//            rowCount cleared for the next build
+// The (cell id, particle id) order is unique, so keys / ids are bit-identical to the other grid builds.
+struct RowsGrid {
+    int enabled;
+    int nRows;
+    unsigned* rowCount;       // [nRows + 1] all zero between builds
+    int* rowStart;            // [nRows + 2] first sorted slot of each row; rowStart[nRows] = number of sorted slots
+    int2* kp;                 // [N] by particle id: (cell id, place inside its row)
+    int2* tmp;                // [N] row-contiguous (cell id, id | ghost tag)
+    int* irregular;           // [2] device flags: a particle sits outside the grid (its stencil is not symmetric).  [0] raised by
+                              // the count pass, latched into [1] (and cleared) by the order pass; the collision stage reads [1]
+    unsigned long long nxMagic;   // exact division by nx: q = (n * nxMagic) >> nxShift
+    int nxShift;
+    int countDone;            // 1: the count pass of THIS build already ran (fused into the previous step's cell pass)
+};
+
+struct NearProbe;
+
 struct GridBuildArgs {
     GridDev grid;
     const float4* objPos;     // positions the keys are computed from (particles or triangle centres)
@@ -52,20 +76,35 @@ struct GridBuildArgs {
     const float4* vel;
     float4* spos;
     float4* svel;
+    RowsGrid rows;            // rows.enabled: row-directory build (no compact cell index, no svel)
+    const NearProbe* probe;   // rows mode: near-wall probe carried by the order pass (null: none)
 };
 void launch_grid_build(const GridBuildArgs& a, cudaStream_t st);
+void launch_row_count(const GridBuildArgs& a, cudaStream_t st);   // the count pass alone (head of a bcs_step run)
 
-// ---- springs.cu ----------------------------------------------------------------------------------------
+// ---- cellpass.cu: the per-blood-cell pass (springs, integration, vein end, row count) ------------------------------
+// Work unit: a GROUP of whole blood cells of one type handled by ONE WARP out of warp-private shared memory (no CTA
+// barrier anywhere).  The plan fixes the group size per type and the offsets of the per-type tables.
 struct SpringPlan {
-    int blockStart[BCS_MAX_TYPES + 1];   // first block of each type
-    int cellsPerBlock[BCS_MAX_TYPES];
-    bool pairwise[BCS_MAX_TYPES];        // springs evaluated once per undirected spring (shared-memory exchange)
-    int totalBlocks;
-    int sharedBytes;                     // dynamic shared memory of the spring kernel
-    int sfCap;                           // entries of the parked spring-force array
-    int tableInts;                       // words of the per-type table area
+    int blockStart[BCS_MAX_TYPES + 1];   // first group of each type
+    int cellsPerBlock[BCS_MAX_TYPES];    // blood cells per group: 1, 2, 4 or 8
+    int totalBlocks;                     // groups over all types
+    int sharedBytes;                     // dynamic shared memory per CTA
+    int warpBytes;                       // ... of which per warp
+    int warps;                           // warps per CTA
+    int tileMax;                         // tile capacity per warp: P * (cellsPerBlock + 1) float4, maximum over the types
+    int slotOff[BCS_MAX_TYPES];          // slot table: [P] particle index | degree << 16, sorted by degree
+    int adjOff[BCS_MAX_TYPES];           // adjacency: [adjDeg][P] (mate particle index, rest length bits) per slot, ascending mates
+    int adjDeg[BCS_MAX_TYPES];
+    unsigned cellMagic[BCS_MAX_TYPES];   // i / P == (i * cellMagic) >> 20 for i < 512
+    int tabAdj, tabSlot, tabModel, tabEnd;   // sizes (entries) of the tables staged in shared memory per CTA
+    int tabBytes;                        // ... in bytes, 0 = tables are read from global memory
 };
-SpringPlan make_spring_plan(const TypesDev& types);
+struct SpringTables {                    // host copies of the per-type tables (uploaded once per handle)
+    std::vector<int> slot;
+    std::vector<int2> adj;
+};
+SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTables& tables);
 // Near-wall probe carried by the spring kernel (every particle's position passes through its registers anyway): one byte
 // of the wall grid's dilated occupancy answers "can this particle reach the wall at all"; the few that can are listed
 // for the wall filter, which then never streams the other ~97 % of the particles.  near == null: disabled.
@@ -85,18 +124,27 @@ struct SpringArgs {
     const float4* vel;
     float4* frc;
     float4* centers;            // [B]
-    const int* adjJ;            // ELL adjacency: mate index per (degree slot, particle-in-cell)
-    const float* adjL;          //                rest length
-    const int* adjS;            //                undirected spring index (bit 31: minus sign)
-    const int* sprAB;           // undirected springs: a | b << 16
-    const float* sprL;
+    const int* slotTab;         // per-type slot tables (SpringPlan::slotOff)
+    const int2* adjTab;         // per-type adjacency in slot order (SpringPlan::adjOff)
     const float* initR;         // [nModel]
     OwnedLists lists;           // slab mode: owned blood cells (lists.cells == null otherwise)
     NearProbe probe;            // probe.near == null: no probe
+    unsigned long long* phaseClock;   // developer aid (BCS_CP_CLOCK): summed SM cycles per phase of the cell pass; null in production
 };
 void launch_springs(const SpringArgs& a, cudaStream_t st);
+void cell_pass_prepare(const SpringPlan& plan);   // per device: opt in to the dynamic shared memory of every variant
 
-// ---- collide.cu ----------------------------------------------------------------------------------------
+// ---- collide.cu / pairs.cu ------------------------------------------------------------------------------
+// Touching pairs found by the symmetric search: every pair (i < j, sorted slots) is recorded ONCE as two half-hits, one
+// in the list of each end; a slot's list is walked in ascending partner order when the forces are evaluated, which is
+// the encounter order of the per-slot stencil walk (rows ascend with the cell id) - same sums, same bits.
+struct PairLists {
+    int* head;                  // [N] newest half-hit of the sorted slot, -1 = none (reset by the apply pass)
+    int2* entries;              // [8 N + pool] (partner slot, next entry of the same slot); slot i owns entries [8 i, 8 i + 8)
+    int* ctl;                   // [3] overflow flag (the pool ran dry), CTA counter of the apply pass, pool entries used
+    int poolStart, pool;        // shared entries for slots with more than 4 touching forward partners
+};
+
 struct CollideArgs {
     GridDev grid;
     TypesDev types;
@@ -124,8 +172,18 @@ struct CollideArgs {
     int* dbgCount;
     unsigned long long* dbgSum;
     int* dbgHits;
+    // row-directory mode (pairs.cu): symmetric pair search over the sorted keys + per-slot hit lists
+    bool rowsMode;
+    bool fullWalk;              // BCS_COLLIDE=walk: every slot scans its whole stencil (the fallback path) instead
+    const int* rowStart;
+    int nRows;
+    const int* ids;             // sorted particle ids (bit 31: ghost)
+    const float4* vel;          // velocities by particle id
+    const int* irregular;       // raised by the grid build when a particle sits outside the grid
+    PairLists pairs;
 };
 void launch_particle_collisions(const CollideArgs& a, cudaStream_t st);
+void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st);   // pairs.cu
 
 // ---- wall.cu: lazily rebuilt wall grid (production path of the vein-collision stage, clean semantics) ----
 // A uniform grid of `h`-unit cells over the vein's bounding box.  Every cell lists the sorted triangle slots whose
@@ -266,7 +324,12 @@ struct IntegrateArgs {
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter
-// integrate_particles + vein_end + step counter fused (bcs_step)
-void launch_finish_step(const IntegrateArgs& a, const SpringPlan& plan, unsigned* doneBlocks, cudaStream_t st);
+// integrate_particles + vein_end + step counter fused (bcs_step): the cell pass without its spring stage
+void launch_finish_step(const IntegrateArgs& a, const SpringArgs& sp, unsigned* doneBlocks, cudaStream_t st);
+// end of step k fused with the head of step k + 1: integrate + vein end + step counter, then - on the new state - blood
+// cell centres + springs, and the row count of the next grid build
+void launch_advance(const IntegrateArgs& a, const SpringArgs& sp, const GridDev& grid, const RowsGrid& rows, unsigned* doneBlocks, cudaStream_t st);
+// springs + row count (head of a bcs_step run)
+void launch_springs_count(const SpringArgs& sp, const GridDev& grid, const RowsGrid& rows, Counters* counters, cudaStream_t st);
 
 }  // namespace bcs

@@ -209,11 +209,13 @@ def test_free_run_is_bitwise_repeatable(bcs_lib):
             assert np.array_equal(x, y), f"run {run}: array {w} differs from run 0"
 
 
-@pytest.mark.parametrize("switch", ["BCS_GRID=radix", "BCS_SCAN=fused", "BCS_COLLIDE=rows", "BCS_NO_NEAR_PROBE=1", "BCS_NO_OVERLAP=1",
-                                    "BCS_SORT=classic"])
+@pytest.mark.parametrize("switch", ["BCS_GRID=radix", "BCS_GRID=cells", "BCS_GRID=cells,BCS_COLLIDE=rows", "BCS_SCAN=fused", "BCS_COLLIDE=walk",
+                                    "BCS_NO_NEAR_PROBE=1", "BCS_NO_OVERLAP=1", "BCS_SORT=classic", "BCS_NO_FUSE=1", "BCS_NO_FUSE=1,BCS_NO_OVERLAP=1",
+                                    "BCS_SPRING_G=3", "BCS_SPRING_WARPS=2"])
 def test_alternative_paths_equal_the_default_bitwise(bcs_lib, monkeypatch, switch):
-    """every A/B switch of DESIGN.md section 7 selects another route to the SAME result: radix-sorted grid, single-launch
-    scans, row-after-row candidate walk, wall filter without the spring kernel's near list, unforked step"""
+    """every A/B switch of DESIGN.md section 7 selects another route to the SAME result: compact cell index instead of the
+    row directory (counting or radix sorted), per-slot stencil walks instead of the symmetric pair search, single-launch
+    scans, wall filter without the near list, unforked step, unfused run, other blood-cell group sizes, directed springs"""
     sc = small_cylinder_scene(120, 100, 120.0)
     st = pkg.make_initial_state(sc, seed=8, xz_half_width=44.0, y_range=(-25.0, -95.0))
     arrays = (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL)
@@ -226,11 +228,65 @@ def test_alternative_paths_equal_the_default_bitwise(bcs_lib, monkeypatch, switc
 
     want, stats = run()
     assert stats["vein_hits"] > 20
-    name, value = switch.split("=")
-    monkeypatch.setenv(name, value)
+    for one in switch.split(","):
+        name, value = one.split("=")
+        monkeypatch.setenv(name, value)
     got, _ = run()
     for w, x, y in zip(arrays, got, want):
         assert np.array_equal(x, y), f"{switch}: array {w} differs from the default path"
+
+
+def test_fused_run_equals_single_steps(bcs_lib):
+    """bcs_step(n) in row-directory mode runs the end of step k and the springs / row count of step k + 1 as one pass over
+    the particle state (cellpass.cu: launch_advance); n calls of bcs_step(1) never fuse.  Same bits, teleports included."""
+    sc = small_cylinder_scene(120, 100, 120.0)
+    st = pkg.make_initial_state(sc, seed=5, xz_half_width=40.0, y_range=(-25.0, -95.0))
+    arrays = (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.CELL_CENTERS)
+    with make_bcs(sc) as a, make_bcs(sc) as b:
+        a.upload_state(st)
+        b.upload_state(st)
+        for block in (1, 2, 7, 30, 20):
+            a.step(block)
+            for _ in range(block):
+                b.step(1)
+            for w in arrays:
+                assert np.array_equal(refcheck.down(a, w), refcheck.down(b, w)), f"after a fused run of {block}: array {w} differs"
+        assert a.step_count() == b.step_count() == 60
+        assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
+
+
+def test_particles_outside_the_grid_take_the_full_walk(bcs_lib, oracle_lib, monkeypatch):
+    """A particle outside the grid has a one-sided stencil (particle_collisions.cuh:126-268 trims by the unclamped index),
+    so the symmetric pair search hands the whole build to the per-slot walk over the row directory.  Candidate sets and
+    forces must equal the oracle's and the compact-cell-index path's."""
+    sc = small_cylinder_scene(60, 40, 150.0)
+    sc.flags["use_blood_flow"] = 0
+    st = pkg.make_initial_state(sc, seed=7, xz_half_width=49.0, y_range=(-25.0, -110.0))
+    lay = sc.layout()
+    # push three blood cells out of the grid on different sides (whole cells, so that their springs stay sane)
+    for cell, (dx, dy, dz) in ((3, (400.0, 0.0, 0.0)), (47, (0.0, 900.0, 0.0)), (80, (-300.0, 0.0, -300.0))):
+        t = int(np.searchsorted(np.asarray(lay.cell_starts[:lay.n_types]), cell, side="right") - 1)
+        p, ps, cs = int(lay.particles_in_cell[t]), int(lay.particle_starts[t]), int(lay.cell_starts[t])
+        sl = slice(ps + (cell - cs) * p, ps + (cell - cs + 1) * p)
+        st["pos_x"][sl] += np.float32(dx); st["pos_y"][sl] += np.float32(dy); st["pos_z"][sl] += np.float32(dz)
+    results = []
+    for mode in ("rows", "cells"):
+        monkeypatch.setenv("BCS_GRID", mode)
+        with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
+            sim.upload_state(st)
+            orc.upload_state(st)
+            for step in range(3):
+                sim.run_stage(capi.STAGE_GRID_PARTICLES); orc.run_stage(capi.STAGE_GRID_PARTICLES)
+                (ka, ia), (kb, ib) = sim.grid(0), orc.grid(0)
+                assert np.array_equal(ka, kb) and np.array_equal(ia, ib), f"{mode} step {step}: grid"
+                for x, y in zip(sim.debug_candidates(), orc.debug_candidates()):
+                    assert np.array_equal(x, y), f"{mode} step {step}: candidate sets"
+                sim.step(1); orc.step(1)
+            assert sim.stats()["out_of_bounds"] > 0
+            results.append([refcheck.down(sim, w) for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC)])
+            refcheck.assert_close(results[-1][0], refcheck.down(orc, capi.PARTICLE_POS), f"{mode}: positions vs oracle", scale=0.0)
+    for x, y in zip(*results):
+        assert np.array_equal(x, y), "row-directory walk and compact-cell-index walk differ"
 
 
 def test_tiled_collision_kernel_equals_index_walk(bcs_lib, monkeypatch):
@@ -239,6 +295,7 @@ def test_tiled_collision_kernel_equals_index_walk(bcs_lib, monkeypatch):
     sc = small_cylinder_scene(300, 300, 400.0)
     st = pkg.make_initial_state(sc, seed=11, xz_half_width=45.0, y_range=(-25.0, -360.0))
     out = []
+    monkeypatch.setenv("BCS_GRID", "cells")   # the per-slot walks live on the compact cell index
     for mode in (None, "tiled"):
         if mode:
             monkeypatch.setenv("BCS_COLLIDE", mode)
