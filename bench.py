@@ -116,7 +116,7 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "row_start_totals": 4 * rows, "row_start_scan": 8 * rows,      # R counts (twice), W starts
         "row_scatter": 20 * N,                     # R (key, place) 8N + row start 4N, W (key, id) 8N
         "pair_walk": 0,                            # fall-back of the pair search: returns at once
-        "pair_apply": 120 * hits,                  # forces of the touching pairs (a few % of the particles)
+        "pair_force": 0, "pair_fold": 0,           # forces of the touching pairs (a few % of the particles): part of the collision stage
         # end of step k + springs / row count of step k+1 in one pass: R pos,vel,frc 36N, W pos,vel,frc 36N, W (key, place) 8N,
         # W centres 12B.  (The three stages it replaces: finish_step 72N + springs 48N + 12B + cell_keys 20N.)
         "advance": 80 * N + 12 * B,
@@ -401,11 +401,11 @@ def run_product(args):
 
     roofline = roof(dominant)
     roofline["contract_kernels"] = {k: roof(k) for k in CONTRACT_KERNELS if k in prof}
-    if "pair_apply" in prof:
-        # the collision STAGE is pair search + (idle) fall-back + pair apply: SURVEY 8(d)'s stage figure over their summed time
+    if "pair_force" in prof:
+        # the collision STAGE is pair search + (idle) fall-back + pair force + fold: SURVEY 8(d)'s stage figure over their summed time
         c = roofline["contract_kernels"]["particle_collisions"]
-        stage_ms = sum(prof[k][0] / prof[k][1] for k in ("particle_collisions", "pair_walk", "pair_apply") if k in prof)
-        c.update({"kernel": "particle_collisions + pair_walk + pair_apply (the stage)", "search_ms_per_launch": c["ms_per_launch"], "ms_per_launch": stage_ms,
+        stage_ms = sum(prof[k][0] / prof[k][1] for k in ("particle_collisions", "pair_walk", "pair_force", "pair_fold") if k in prof)
+        c.update({"kernel": "particle_collisions + pair_walk + pair_force + pair_fold (the stage)", "search_ms_per_launch": c["ms_per_launch"], "ms_per_launch": stage_ms,
                   "achieved": c["algorithmic_bytes_per_launch"] / (stage_ms * 1e-3) / 1e9})
         c["frac"] = c["achieved"] / peak
     if "advance" in prof:

@@ -867,16 +867,16 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
                     R.kp = s->track(dev_alloc<int2>(N));
                     R.tmp = s->track(dev_alloc<int2>(N));
                     R.irregular = s->track(dev_alloc<int>(2));
+                    R.nx = s->pg.nx;
                     int l = 0;
                     while ((1ll << l) < s->pg.nx) ++l;
                     R.nxShift = 32 + l;
                     R.nxMagic = ((1ull << R.nxShift) + (unsigned long long)s->pg.nx - 1ull) / (unsigned long long)s->pg.nx;
                     PairLists& L = s->pairs;
-                    L.head = s->track(dev_alloc<int>(N, false));
-                    BCS_CUDA(cudaMemset(L.head, 0xFF, (size_t)N * sizeof(int)));
-                    L.poolStart = 8 * N; L.pool = 2 * N + 1024;
-                    L.entries = s->track(dev_alloc<int2>((size_t)L.poolStart + L.pool, false));
+                    L.cap = 4 * N + 4096;
+                    L.pairs = s->track(dev_alloc<int2>((size_t)L.cap, false));
                     L.ctl = s->track(dev_alloc<int>(4));
+                    L.acc = s->track(dev_alloc<long long>(3 * (size_t)N));
                     const char* cm = getenv("BCS_COLLIDE");
                     s->collideWalk = cm && std::string(cm) == "walk";
                 }

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TILE) particle_collisions_tiled_kernel(const C
         stencil_range(axis_cell_raw(p1.x, g.minx, g.csx), g.nx, x0, x1);
         stencil_range(axis_cell_raw(p1.y, g.miny, g.csy), g.ny, y0, y1);
         stencil_range(axis_cell_raw(p1.z, g.minz, g.csz), g.nz, z0, z1);
-        PairAccum acc{f3(0.f, 0.f, 0.f), 0};
+        PairAccum acc = pair_accum_zero();
         int cnt = 0;
         unsigned long long sum = 0;
         if (fallback) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TILE) particle_collisions_tiled_kernel(const C
             a.dbgHits[pid] = acc.hits;
         } else if (acc.hits) {
             float4 f = a.frc[pid];
-            f.x += acc.F.x; f.y += acc.F.y; f.z += acc.F.z;
+            f.x += fx_value(acc.x); f.y += fx_value(acc.y); f.z += fx_value(acc.z);
             a.frc[pid] = f;
         }
         myHits = acc.hits;
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
                 r1 = p4.w;
             }
 
-            PairAccum acc{f3(0.f, 0.f, 0.f), 0};
+            PairAccum acc = pair_accum_zero();
             int cnt = 0;
             unsigned long long sum = 0;
             const int plane = g.nx * g.ny;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) particle_collisions_kernel
                 // F[pid] += acc: only this thread updates this particle, so the three reductions (performed in L2, no value
                 // returned - the warp does not wait for a load at its very end) give the same IEEE sum as load-add-store
                 float* f = reinterpret_cast<float*>(a.frc + pid);
-                atomicAdd(f, acc.F.x); atomicAdd(f + 1, acc.F.y); atomicAdd(f + 2, acc.F.z);
+                atomicAdd(f, fx_value(acc.x)); atomicAdd(f + 1, fx_value(acc.y)); atomicAdd(f + 2, fx_value(acc.z));
             }
             myHits += acc.hits;
         }

@@ -44,6 +44,7 @@ struct RowsGrid {
     unsigned long long nxMagic;   // exact division by nx: q = (n * nxMagic) >> nxShift
     int nxShift;
     int countDone;            // 1: the count pass of THIS build already ran (fused into the previous step's cell pass)
+    int nx;                   // cells per row
 };
 
 struct NearProbe;
@@ -135,14 +136,13 @@ void launch_springs(const SpringArgs& a, cudaStream_t st);
 void cell_pass_prepare(const SpringPlan& plan);   // per device: opt in to the dynamic shared memory of every variant
 
 // ---- collide.cu / pairs.cu ------------------------------------------------------------------------------
-// Touching pairs found by the symmetric search: every pair (i < j, sorted slots) is recorded ONCE as two half-hits, one
-// in the list of each end; a slot's list is walked in ascending partner order when the forces are evaluated, which is
-// the encounter order of the per-slot stencil walk (rows ascend with the cell id) - same sums, same bits.
+// Touching pairs found by the symmetric search (pairs.cu): a global list of (slot i < slot j), filled with one atomic per
+// CTA, and per-particle fixed-point force accumulators (pair_device.cuh) that make the sums independent of arrival order.
 struct PairLists {
-    int* head;                  // [N] newest half-hit of the sorted slot, -1 = none (reset by the apply pass)
-    int2* entries;              // [8 N + pool] (partner slot, next entry of the same slot); slot i owns entries [8 i, 8 i + 8)
-    int* ctl;                   // [3] overflow flag (the pool ran dry), CTA counter of the apply pass, pool entries used
-    int poolStart, pool;        // shared entries for slots with more than 4 touching forward partners
+    int2* pairs;                // [cap] touching pairs of this step (sorted slots)
+    int cap;
+    int* ctl;                   // [4] pairs listed, overflow flag (pair_walk redoes the stage), CTA counter of the fold pass
+    long long* acc;             // [3 N] by particle id, unit 2^-40; zero between steps
 };
 
 struct CollideArgs {

@@ -1,4 +1,4 @@
-// Particle-particle collision stage over the ROW DIRECTORY (RowsGrid, kernels.cu): symmetric pair search.
+// Particle-particle collision stage over the ROW DIRECTORY (RowsGrid, kernels.cuh): symmetric pair search.
 //
 // Stands in for sim::calculateParticleCollisions<UniformGrid> (simulation/particle_collisions.cuh:104-269)
 // -> detectCollisionsInNeighborCells (:53-83) -> detectCollision (:26-38)
@@ -9,16 +9,19 @@
 // active, 0.17 of the HBM roofline (round 1).  Here:
 //   * the candidate relation is symmetric (j is in i's stencil <=> i is in j's, for particles inside the grid), so a slot
 //     only looks FORWARD in the sorted order - the rest of its own row, the row above it, and the three rows of the next
-//     z layer - and every touching pair is recorded once, for both ends;
+//     z layer - and every touching pair is found once, for both ends;
 //   * cell ids are x-fastest, so "own row forward + next row" is the run of slots that starts right after the slot
 //     itself (no lookup at all), and the three rows of the next layer are ONE contiguous run found with one load from
 //     the row directory.  Inside a run the stencil test is integer work on the sorted keys;
 //   * candidates are only queued during the scan and tested together afterwards (all lanes test their k-th candidate in
-//     the same iteration), touching pairs go to per-slot lists;
-//   * pair_apply walks each slot's list in ascending partner order - the encounter order of the per-slot walk - so the
-//     sums, and therefore the forces, are bit-identical to collide.cu's.
+//     the same iteration); touching pairs are collected per CTA in shared memory and appended to a global pair list
+//     with ONE atomic per CTA;
+//   * pair_force takes a thread per touching pair (dense: no lane waits for a neighbour's hit), evaluates both ends and
+//     adds the two contributions to per-particle FIXED-POINT accumulators (pair_device.cuh): integer sums do not depend
+//     on the order of arrival, so the force is bit-identical to the per-slot walk's, run after run;
+//   * pair_fold streams the accumulators in particle order and adds the non-zero sums to the float forces.
 // A build in which some particle sits outside the grid (one-sided stencils: the relation is no longer symmetric), or
-// whose pair lists overflow, is handled by pair_walk: every slot scans its whole stencil through the row directory.
+// whose pair list overflows, is handled by pair_walk: every slot scans its whole stencil through the row directory.
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
@@ -26,41 +29,36 @@
 #include "rows_device.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace bcs {
 
 namespace {
 
 constexpr int PS_THREADS = 128;
-constexpr int PS_QCAP = 16;   // queued candidates per slot before they are tested (8 KB of shared memory per CTA)
+constexpr int PS_QCAP = 16;      // queued candidates per slot before they are tested (8 KB of shared memory per CTA)
+constexpr int PS_PAIRS = 384;    // touching pairs a CTA collects before it spills to the global list directly
 constexpr unsigned long long DBG_MIX = 0x9E3779B97F4A7C15ull;
 
-// Half-hit entries are owned by the FORWARD end of a pair: slot i keeps entries 2 * (i * PS_FWD + h) and + 1 for its h-th
-// touching forward partner, so nothing is allocated at run time and the only atomics are the exchanges on the two list
-// heads (distinct addresses).  A slot with more than PS_FWD touching forward partners takes entries from a small shared
-// pool; only when that runs dry is the overflow flag raised and the stage redone by pair_walk (dense clusters; the
-// row-directory mode is meant for sparse scenes).
-constexpr int PS_FWD = 4;
+// ctl words of PairLists
+enum { CTL_COUNT = 0, CTL_OVERFLOW = 1, CTL_DONE = 2 };
 
-__device__ __forceinline__ void record_pair(const PairLists& L, int i, int j, int h)
+__device__ __forceinline__ void emit_pair(const PairLists& L, int2* sPairs, int* sCount, int i, int j)
 {
-    int e = 2 * (i * PS_FWD + h);
-    if (h >= PS_FWD) {
-        // beyond the slot's own entries: the shared pool behind them (rare, so its counter is not contended)
-        const int k = atomicAdd(&L.ctl[2], 2);
-        if (k + 2 > L.pool) {
-            L.ctl[0] = 1;
-            return;
-        }
-        e = L.poolStart + k;
+    const int k = atomicAdd(sCount, 1);
+    if (k < PS_PAIRS) {
+        sPairs[k] = make_int2(i, j);
+    } else {
+        // the CTA's buffer is full (a dense cluster): straight to the global list
+        const int g = atomicAdd(&L.ctl[CTL_COUNT], 1);
+        if (g < L.cap) L.pairs[g] = make_int2(i, j);
+        else L.ctl[CTL_OVERFLOW] = 1;   // pair_walk redoes the stage
     }
-    L.entries[e] = make_int2(j, atomicExch(&L.head[i], e));
-    L.entries[e + 1] = make_int2(i, atomicExch(&L.head[j], e + 1));
 }
 
 template <bool DEBUG, bool SLAB>
 __device__ __forceinline__ void test_queued(const CollideArgs& a, int (*q)[PS_THREADS], int cnt, int slot, int tag, const float3 p1, const float r1,
-                                            unsigned long long& tests, int& hits)
+                                            unsigned long long& tests, int& hits, int2* sPairs, int* sCount)
 {
     const int tid = threadIdx.x;
     for (int t = 0; t < cnt; ++t) {
@@ -83,26 +81,38 @@ __device__ __forceinline__ void test_queued(const CollideArgs& a, int (*q)[PS_TH
                 if (touch) atomicAdd(&a.dbgHits[pj], 1);
             }
         } else if (touch) {
-            record_pair(a.pairs, slot, j, hits);
+            emit_pair(a.pairs, sPairs, sCount, slot, j);
             ++hits;
         }
         ++tests;
     }
 }
 
+#define BCS_QUEUE_PUSH(J)                                                                               \
+    {                                                                                                   \
+        q[cnt][tid] = (J);                                                                              \
+        if (++cnt == PS_QCAP) {                                                                         \
+            test_queued<DEBUG, SLAB>(a, q, cnt, slot, tag, p1, r1, tests, hits, sPairs, &sCount);       \
+            cnt = 0;                                                                                    \
+        }                                                                                               \
+    }
+
 template <bool DEBUG, bool SLAB, bool STATS>
 __global__ void __launch_bounds__(PS_THREADS) pair_search_kernel(const CollideArgs a)
 {
     __shared__ int q[PS_QCAP][PS_THREADS];
+    __shared__ int2 sPairs[PS_PAIRS];
+    __shared__ int sCount, sBase;
     if (*a.irregular) return;   // pair_walk takes the build
     const GridDev& g = a.grid;
     const int n = a.nDev ? *a.nDev : a.n;
     const int tid = threadIdx.x;
     const int plane = g.nx * g.ny;
     unsigned long long tests = 0;
-    int hitsAll = 0;
+    int hits = 0;
+    if (tid == 0) sCount = 0;
+    __syncthreads();
     for (int slot = blockIdx.x * blockDim.x + tid; slot < n; slot += gridDim.x * blockDim.x) {
-        int hits = 0;   // touching forward partners of this slot so far
         const float4 p4 = a.spos[slot];
         const int c = a.keys[slot];
         int tag = 0;
@@ -125,13 +135,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_search_kernel(const CollideAr
             while (k <= hi) {
                 const int kn = a.keys[j + 1];
                 const bool in = (unsigned)(k - c) <= (unsigned)x1 || (y1 > 0 && (unsigned)(k - wRow) < nb);
-                if (in) {
-                    q[cnt][tid] = j;
-                    if (++cnt == PS_QCAP) {
-                        test_queued<DEBUG, SLAB>(a, q, cnt, slot, tag, p1, r1, tests, hits);
-                        cnt = 0;
-                    }
-                }
+                if (in) BCS_QUEUE_PUSH(j)
                 ++j;
                 k = kn;
             }
@@ -148,104 +152,95 @@ __global__ void __launch_bounds__(PS_THREADS) pair_search_kernel(const CollideAr
             while (k <= hi) {
                 const int kn = a.keys[j + 1];
                 const bool in = (unsigned)(k - w0) < nb || (unsigned)(k - w1) < nb || (unsigned)(k - w2) < nb;
-                if (in) {
-                    q[cnt][tid] = j;
-                    if (++cnt == PS_QCAP) {
-                        test_queued<DEBUG, SLAB>(a, q, cnt, slot, tag, p1, r1, tests, hits);
-                        cnt = 0;
-                    }
-                }
+                if (in) BCS_QUEUE_PUSH(j)
                 ++j;
                 k = kn;
             }
         }
-        test_queued<DEBUG, SLAB>(a, q, cnt, slot, tag, p1, r1, tests, hits);
-        hitsAll += hits;
+        test_queued<DEBUG, SLAB>(a, q, cnt, slot, tag, p1, r1, tests, hits, sPairs, &sCount);
+    }
+    if (!DEBUG) {
+        // the CTA's touching pairs -> global list: one atomic per CTA
+        __syncthreads();
+        const int mine = min(sCount, PS_PAIRS);
+        if (tid == 0 && mine) sBase = atomicAdd(&a.pairs.ctl[CTL_COUNT], mine);
+        __syncthreads();
+        if (mine) {
+            const int base = sBase;
+            if (base + mine <= a.pairs.cap) {
+                for (int k = tid; k < mine; k += PS_THREADS) a.pairs.pairs[base + k] = sPairs[k];
+            } else if (tid == 0) {
+                a.pairs.ctl[CTL_OVERFLOW] = 1;
+            }
+        }
     }
     if (STATS && !DEBUG) {
         for (int o = 16; o; o >>= 1) {
             tests += __shfl_xor_sync(0xffffffffu, tests, o);
-            hitsAll += __shfl_xor_sync(0xffffffffu, hitsAll, o);
+            hits += __shfl_xor_sync(0xffffffffu, hits, o);
         }
         if ((threadIdx.x & 31) == 0) {
             // both ends of a pair test / feel each other (the per-slot walk counts a pair from either side)
             atomicAdd(&a.counters->pairTests, 2ull * tests);
-            atomicAdd(&a.counters->pairHits, 2ull * (unsigned long long)hitsAll);
+            atomicAdd(&a.counters->pairHits, 2ull * (unsigned long long)hits);
         }
     }
 }
 
-// force of one touching pair on the particle at (p1, v1, r1): addResilientForceOnCollision, same expression as
-// pair_force (pair_device.cuh) with the partner's velocity gathered by particle id
-__device__ __forceinline__ void pair_force_v(const PhysDev& ph, const float3 p1, const float3 v1, const float r1, const float4 q4, const float3 v2,
-                                             PairAccum& acc)
-{
-    const float3 rel = p1 - xyz(q4);
-    const float d2 = length_squared(rel);
-    const float3 rv = v1 - v2;
-    const float3 dir = normalize(rel);
-    const float3 tang = rv - dot(rv, dir) * dir;
-    const float3 spring = (-ph.coll_spring * (r1 * 2 - sqrtf(d2))) * dir;
-    const float3 damp = ph.coll_damping * rv;
-    const float3 shear = ph.coll_shear * tang;
-    acc.F = acc.F + 0.5f * (spring + damp + shear);
-    ++acc.hits;
-}
-
-// one thread per sorted slot: a slot with half-hits takes its partners in ascending slot order, F[pid] += sum, and clears
-// its list head
-__global__ void __launch_bounds__(256) pair_apply_kernel(const CollideArgs a)
+// one thread per touching pair: both contributions, added to the ends' fixed-point accumulators
+__global__ void __launch_bounds__(256) pair_force_kernel(const CollideArgs a)
 {
     const PairLists& L = a.pairs;
-    const int n = a.nDev ? *a.nDev : a.n;
-    const bool skip = L.ctl[0] != 0 || *a.irregular != 0;   // pair_walk did the stage: only clear the lists
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-        const int first = L.head[slot];
-        if (first < 0) continue;
-        L.head[slot] = -1;
-        const int tag = a.ids[slot];
-        if (skip || tag < 0) continue;   // ghosts are partners only (forces go to owned particles, particle_collisions.cuh:36)
-        const int pid = tag;
-        const float4 p4 = a.spos[slot];
-        const float3 p1 = xyz(p4), v1 = xyz(a.vel[pid]);
-        PairAccum acc{f3(0.f, 0.f, 0.f), 0};
-        int last = -1;
-        while (true) {
-            // next partner in ascending slot order (lists hold a handful of entries)
-            int best = 0x7fffffff;
-            for (int e = first; e >= 0;) {
-                const int2 en = L.entries[e];
-                if (en.x > last && en.x < best) best = en.x;
-                e = en.y;
-            }
-            if (best == 0x7fffffff) break;
-            const float3 v2 = xyz(a.vel[a.ids[best] & 0x7fffffff]);
-            pair_force_v(a.phys, p1, v1, p4.w, a.spos[best], v2, acc);
-            last = best;
+    if (L.ctl[CTL_OVERFLOW] != 0 || *a.irregular != 0) return;   // pair_walk did the stage
+    const int count = min(L.ctl[CTL_COUNT], L.cap);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const int2 pr = L.pairs[t];
+        const int ti = a.ids[pr.x], tj = a.ids[pr.y];
+        const float4 pi = a.spos[pr.x], pj = a.spos[pr.y];
+        const float3 vi = xyz(a.vel[ti & 0x7fffffff]), vj = xyz(a.vel[tj & 0x7fffffff]);
+        if (ti >= 0) {   // ghosts are partners only (forces go to owned particles, particle_collisions.cuh:36)
+            const float3 c = pair_contribution(a.phys, xyz(pi), vi, pi.w, pj, vj);
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)ti;
+            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
         }
+        if (tj >= 0) {
+            const float3 c = pair_contribution(a.phys, xyz(pj), vj, pj.w, pi, vi);
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)tj;
+            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
+        }
+    }
+}
+
+// one thread per particle, in particle order (coalesced): non-zero sums are folded into the float force and cleared; the
+// last CTA to leave rewinds the pair list for the next search
+__global__ void __launch_bounds__(256) pair_fold_kernel(const CollideArgs a, int nParticles)
+{
+    const PairLists& L = a.pairs;
+    for (int pid = blockIdx.x * blockDim.x + threadIdx.x; pid < nParticles; pid += gridDim.x * blockDim.x) {
+        long long* acc = L.acc + 3 * (size_t)pid;
+        const long long sx = acc[0], sy = acc[1], sz = acc[2];
+        if ((sx | sy | sz) == 0) continue;   // a sum of exactly zero adds nothing
         float4 f = a.frc[pid];
-        f.x += acc.F.x; f.y += acc.F.y; f.z += acc.F.z;
+        f.x += fx_value(sx); f.y += fx_value(sy); f.z += fx_value(sz);
+        acc[0] = 0; acc[1] = 0; acc[2] = 0;
         a.frc[pid] = f;
     }
-    // the last CTA to leave lowers the overflow flag for the next search
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&L.ctl[1], 1) == (int)gridDim.x - 1) {
-            L.ctl[0] = 0; L.ctl[1] = 0; L.ctl[2] = 0;
-            __threadfence();
+        if (atomicAdd(&L.ctl[CTL_DONE], 1) == (int)gridDim.x - 1) {
+            L.ctl[CTL_COUNT] = 0; L.ctl[CTL_OVERFLOW] = 0; L.ctl[CTL_DONE] = 0;
         }
     }
 }
 
 // Every slot scans its WHOLE stencil through the row directory (the per-slot walk of collide.cu without the compact cell
-// index): the fallback for builds with particles outside the grid or overflowing pair lists, the A/B partner of the
+// index): the fallback for builds with particles outside the grid or an overflowing pair list, the A/B partner of the
 // symmetric search (BCS_COLLIDE=walk), and - windows being plain linear cell ranges [c0, c0 + nb) exactly as
 // particle_collisions.cuh:53-83 forms them - correct for any key, clamped ones included.
 template <bool DEBUG, bool ALWAYS, bool STATS>
 __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs a)
 {
-    if (!ALWAYS && !(*a.irregular != 0 || a.pairs.ctl[0] != 0)) return;
+    if (!ALWAYS && !(*a.irregular != 0 || a.pairs.ctl[CTL_OVERFLOW] != 0)) return;
     const GridDev& g = a.grid;
     const int n = a.nDev ? *a.nDev : a.n;
     const int plane = g.nx * g.ny;
@@ -265,7 +260,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs
         stencil_range(axis_cell_raw(p1.z, g.minz, g.csz), g.nz, z0, z1);
         const int nbi = x1 - x0 + 1;
         const unsigned nb = (unsigned)nbi;
-        PairAccum acc{f3(0.f, 0.f, 0.f), 0};
+        PairAccum acc = pair_accum_zero();
         int cnt = 0;
         unsigned long long sum = 0;
         for (int dz = z0; dz <= z1; ++dz) {
@@ -289,7 +284,11 @@ __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs
                     const int qid = a.ids[j] & 0x7fffffff;
                     ++cnt; sum += (unsigned long long)(qid + 1) * DBG_MIX;
                 }
-                if (pair_touches(p1, r1, q4, q4.w)) pair_force_v(a.phys, p1, v1, r1, q4, xyz(a.vel[a.ids[j] & 0x7fffffff]), acc);
+                if (pair_touches(p1, r1, q4, q4.w)) {
+                    const float3 f = pair_contribution(a.phys, p1, v1, r1, q4, xyz(a.vel[a.ids[j] & 0x7fffffff]));
+                    acc.x += fx_of(f.x); acc.y += fx_of(f.y); acc.z += fx_of(f.z);
+                    ++acc.hits;
+                }
                 if (STATS) ++tests;
             }
         }
@@ -299,7 +298,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs
             a.dbgHits[pid] = acc.hits;
         } else if (acc.hits) {
             float4 f = a.frc[pid];
-            f.x += acc.F.x; f.y += acc.F.y; f.z += acc.F.z;
+            f.x += fx_value(acc.x); f.y += fx_value(acc.y); f.z += fx_value(acc.z);
             a.frc[pid] = f;
         }
         hitsAll += acc.hits;
@@ -331,28 +330,37 @@ void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st)
         BCS_CUDA(cudaGetLastError());
         return;
     }
+    // template dispatch over (debug, slab, stats)
+    auto search = [&](auto D, auto SL, auto ST) {
+        BCS_LAUNCH("particle_collisions", st, pair_search_kernel<decltype(D)::value, decltype(SL)::value, decltype(ST)::value><<<blocks, threads, 0, st>>>(a));
+    };
+    using T = std::true_type;
+    using F = std::false_type;
     if (dbg) {
         // candidate counts / checksums / touching pairs per particle (test instrumentation): both ends of a pair are
         // credited with integer atomics by the same search the production path runs
         BCS_CUDA(cudaMemsetAsync(a.dbgCount, 0, (size_t)a.n * sizeof(int), st));
         BCS_CUDA(cudaMemsetAsync(a.dbgSum, 0, (size_t)a.n * sizeof(unsigned long long), st));
         BCS_CUDA(cudaMemsetAsync(a.dbgHits, 0, (size_t)a.n * sizeof(int), st));
-        if (slab) BCS_LAUNCH("particle_collisions", st, pair_search_kernel<true, true, false><<<blocks, threads, 0, st>>>(a));
-        else BCS_LAUNCH("particle_collisions", st, pair_search_kernel<true, false, false><<<blocks, threads, 0, st>>>(a));
+        if (slab) search(T{}, T{}, F{});
+        else search(T{}, F{}, F{});
         BCS_LAUNCH("pair_walk", st, pair_walk_kernel<true, false, false><<<walkBlocks, threads, 0, st>>>(a));
         BCS_CUDA(cudaGetLastError());
         return;
     }
     if (slab) {
-        if (a.stats) BCS_LAUNCH("particle_collisions", st, pair_search_kernel<false, true, true><<<blocks, threads, 0, st>>>(a));
-        else BCS_LAUNCH("particle_collisions", st, pair_search_kernel<false, true, false><<<blocks, threads, 0, st>>>(a));
+        if (a.stats) search(F{}, T{}, T{});
+        else search(F{}, T{}, F{});
     } else {
-        if (a.stats) BCS_LAUNCH("particle_collisions", st, pair_search_kernel<false, false, true><<<blocks, threads, 0, st>>>(a));
-        else BCS_LAUNCH("particle_collisions", st, pair_search_kernel<false, false, false><<<blocks, threads, 0, st>>>(a));
+        if (a.stats) search(F{}, F{}, T{});
+        else search(F{}, F{}, F{});
     }
     if (a.stats) BCS_LAUNCH("pair_walk", st, pair_walk_kernel<false, false, true><<<walkBlocks, threads, 0, st>>>(a));
     else BCS_LAUNCH("pair_walk", st, pair_walk_kernel<false, false, false><<<walkBlocks, threads, 0, st>>>(a));
-    BCS_LAUNCH("pair_apply", st, pair_apply_kernel<<<std::min((a.n + 255) / 256, 2 * BOUNDED_BLOCKS), 256, 0, st>>>(a));
+    // sized for a few touching pairs per ten particles; both stride over the device-side pair count
+    const int pairBlocks = std::max(1, std::min((a.n / 4 + 255) / 256, BOUNDED_BLOCKS));
+    BCS_LAUNCH("pair_force", st, pair_force_kernel<<<pairBlocks, 256, 0, st>>>(a));
+    BCS_LAUNCH("pair_fold", st, pair_fold_kernel<<<std::min((a.n + 255) / 256, 2 * BOUNDED_BLOCKS), 256, 0, st>>>(a, a.n));
     BCS_CUDA(cudaGetLastError());
 }
 
