@@ -110,7 +110,7 @@ _lib_cache: Dict[str, C.CDLL] = {}
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
     """Loads the product library.  Fails loudly if it has not been built (no fallback of any kind)."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("BCS_LIBRARY") or LIB_PATH   # BCS_LIBRARY: another BUILD of libbcs (A/B measurements)
     if path not in _lib_cache:
         if not os.path.exists(path):
             raise BcsError(f"{path} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`; "

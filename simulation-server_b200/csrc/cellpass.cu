@@ -39,6 +39,11 @@
 
 namespace bcs {
 
+#ifndef BCS_CP_UNROLL
+#define BCS_CP_UNROLL 2
+#endif
+constexpr int CP_UNROLL = BCS_CP_UNROLL;   // mates of a particle in flight together
+
 constexpr int CP_MAX_CELL = 256;     // particles per blood cell supported by the pass
 constexpr int CP_MAX_ROUNDS = 8;     // a group is at most 8 warp rounds (256 particles)
 
@@ -146,23 +151,22 @@ __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-// spring term of physics.cuh:24-27,53-78 for the pair (i <- j): returns the force on i.
-// length(dP), normalize(dP) and normalize(-1*dP) of the reference share one reciprocal square root refined to <= 1 ulp
-// (|dP| = d2 * rsqrt(d2) with one Newton step; n = dP / |dP| as a product); normalize(-dP) = -n exactly.  Deviation
-// from the divided IEEE form: <= 2 ulp per component, far inside the 1e-5 contract.
-__device__ __forceinline__ float3 spring_force(float dt, float kSniff, float dFact, float3 pi, float3 vi, float3 fi, float3 pj, float3 vj, float3 fj, float L)
+// spring term of physics.cuh:24-27,53-78 for the pair (i <- j), added to `sum`.
+// length(dP), normalize(dP) and normalize(-1*dP) of the reference share one reciprocal square root (MUFU.RSQ, <= 2 ulp):
+// |dP| = d2 * rsqrt(d2), n = dP * rsqrt(d2); normalize(-dP) = -n exactly.  Deviation from the divided IEEE form: a few
+// ulp per component, far inside the 1e-5 contract.
+__device__ __forceinline__ void spring_accumulate(float dt, float kSniff, float dFact, float3 pi, float3 vi, float3 fi, float3 pj, float3 vj, float3 fj, float L,
+                                                  float3& sum)
 {
     const float3 dP = pi - pj;
     const float d2 = dot(dP, dP);
     float inv = rsqrtf(d2);
-    float len = d2 * inv;
-    len = fmaf(fmaf(-len, len, d2), 0.5f * inv, len);
-    inv = fmaf(fmaf(-len, inv, 1.0f), inv, inv);
-    if (!(d2 > 0.f)) { inv = 0.f; len = 0.f; }   // coincident particles: normalize() of the reference yields the zero vector
+    if (!(d2 > 0.f)) inv = 0.f;   // coincident particles: normalize() of the reference yields the zero vector (and |dP| = 0)
+    const float len = d2 * inv;
     const float3 n = f3(dP.x * inv, dP.y * inv, dP.z * inv);
     const float3 dv2 = (vi - vj) + dt * (fi - fj);
     const float s = (len - L) * kSniff + dot(n, dv2) * dFact;
-    return f3(-s * n.x, -s * n.y, -s * n.z);
+    sum.x = fmaf(-s, n.x, sum.x); sum.y = fmaf(-s, n.y, sum.y); sum.z = fmaf(-s, n.z, sum.z);
 }
 
 template <bool INTEGRATE, bool SPRINGS, bool COUNT, bool LISTS, int MB = 4>
@@ -363,13 +367,13 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 const int maxd = __reduce_max_sync(0xffffffffu, deg);
                 float3 sum = f3(0.f, 0.f, 0.f);
                 const int2* ap = at + (s < P ? s : 0);
-#pragma unroll 2
+#pragma unroll CP_UNROLL
                 for (int d = 0; d < maxd; ++d) {
                     if (d < deg) {
                         const int2 e = ap[d * P];
                         const int tj = e.x * stride + cell;
-                        sum = sum + spring_force(ph.dt, ph.particle_k_sniff, ph.particle_d_fact, pi, vi, fi, xyz(tp[tj]), xyz(tv[tj]), xyz(tf[tj]),
-                                                 __int_as_float(e.y));
+                        spring_accumulate(ph.dt, ph.particle_k_sniff, ph.particle_d_fact, pi, vi, fi, xyz(tp[tj]), xyz(tv[tj]), xyz(tf[tj]),
+                                          __int_as_float(e.y), sum);
                     }
                 }
                 if (valid) { sx[ti] = sum.x; sy[ti] = sum.y; sz[ti] = sum.z; }
