@@ -396,6 +396,8 @@ VeinArgs vein_args(bcs_sim* s)
     a.vpos = s->vpos; a.vvel = s->vvel; a.vfrc = s->vfrc; a.vsplat = s->vsplat;
     a.nbrIds = s->nbrIds; a.nbrLen = s->nbrLen; a.vidx = s->vidx;
     a.vOwned = s->slab ? s->slab->vOwned : nullptr;
+    a.vFirst = s->slab ? s->slab->vFirst : 0;
+    a.vCount = s->slab ? s->slab->vCount : s->hs.V;
     if (s->wall.enabled) { a.vposBuilt = s->wall.vposBuilt; a.wallMargin = s->wall.margin; a.wallDirty = s->wall.dirty; }
     return a;
 }
@@ -448,7 +450,7 @@ CollideArgs collide_args(bcs_sim* s)
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
     a.nDev = s->slab ? s->slab->nActive : nullptr;
     a.rowsMode = s->rows.enabled != 0; a.fullWalk = s->collideWalk;
-    a.rowStart = s->rows.rowStart; a.nRows = s->rows.nRows; a.ids = s->ids[1]; a.vel = s->vel;
+    a.rowStart = s->rows.rowStart; a.rowsGrid = s->rows; a.nRows = s->rows.nRows; a.ids = s->ids[1]; a.vel = s->vel;
     a.irregular = s->rows.irregular ? s->rows.irregular + 1 : nullptr;   // latched copy (row_order_kernel)
     a.pairs = s->pairs;
     return a;
@@ -829,7 +831,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             s->types.t[i] = TypeDev{h.count, h.P, h.pStart, h.cStart, h.mStart, h.warpSync, hs.adjStart[i], hs.maxDeg[i], hs.sprStart[i], hs.nSpr[i]};
         }
         SpringTables springTables;
-        s->plan = make_spring_plan(s->types, hs, springTables);
+        s->plan = make_spring_plan(s->types, hs, springTables, slabOpts ? std::max(1, slabOpts->world) : 1);
         s->pg = make_grid(hs, hs.cellSize, hs.gdims, N);
         s->tg = make_grid(hs, hs.triCellSize, hs.tdims, T);
         fill_phys(hs, s->phys);
@@ -855,8 +857,17 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             // BCS_GRID=rows / cells / radix overrides.
             {
                 const char* gm = getenv("BCS_GRID");
-                const long long nRows = (long long)s->pg.ny * s->pg.nz;
-                const bool sparse = (double)N <= 4.0 * (double)nRows;
+                // slab decomposition: only the rank's window of cell rows (slab + halo + slack) enters the row directory
+                int rowY0 = 0, rowNyL = s->pg.ny;
+                if (slabOpts && !getenv("BCS_ROWS_GLOBAL")) {
+                    const float halo = (slabOpts->halo_width > 0 ? slabOpts->halo_width : 32.0f) + 16.0f;
+                    const float lo = std::max(hs.gmin[1], slabOpts->y_lo - halo), hi = std::min(hs.gmax[1], slabOpts->y_hi + halo);
+                    const int c0 = (int)std::floor((lo - hs.gmin[1]) / (float)hs.cellSize[1]) - 1, c1 = (int)std::floor((hi - hs.gmin[1]) / (float)hs.cellSize[1]) + 1;
+                    rowY0 = std::max(0, std::min(c0, s->pg.ny - 1));
+                    rowNyL = std::max(1, std::min(c1, s->pg.ny - 1) - rowY0 + 1);
+                }
+                const long long nRows = (long long)rowNyL * s->pg.nz;
+                const bool sparse = (double)N / (slabOpts ? std::max(1, slabOpts->world) : 1) <= 4.0 * (double)nRows;
                 const bool want = gm ? std::string(gm) == "rows" : sparse;
                 if (want && nRows < (1ll << 30)) {
                     RowsGrid& R = s->rows;
@@ -867,7 +878,15 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
                     R.kp = s->track(dev_alloc<int2>(N));
                     R.tmp = s->track(dev_alloc<int2>(N));
                     R.irregular = s->track(dev_alloc<int>(2));
-                    R.nx = s->pg.nx;
+                    R.error = s->track(dev_alloc<int>(1));
+                    R.nx = s->pg.nx; R.ny = s->pg.ny; R.nyL = rowNyL; R.y0 = rowY0;
+                    R.local = (rowNyL != s->pg.ny) ? 1 : 0;
+                    {
+                        int l2 = 0;
+                        while ((1ll << l2) < s->pg.ny) ++l2;
+                        R.nyShift = 32 + l2;
+                        R.nyMagic = ((1ull << R.nyShift) + (unsigned long long)s->pg.ny - 1ull) / (unsigned long long)s->pg.ny;
+                    }
                     int l = 0;
                     while ((1ll << l) < s->pg.nx) ++l;
                     R.nxShift = 32 + l;
@@ -1116,6 +1135,8 @@ int bcs_upload(bcs_sim* s, int which, const float* x, const float* y, const floa
     BCS_API_END
 }
 
+static void check_device_flags(bcs_sim* s);
+
 int bcs_download(bcs_sim* s, int which, float* x, float* y, float* z, int32_t n)
 {
     BCS_API_BEGIN
@@ -1132,6 +1153,7 @@ int bcs_download(bcs_sim* s, int which, float* x, float* y, float* z, int32_t n)
     BCS_CUDA(cudaMemcpyAsync(y, sy, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     BCS_CUDA(cudaMemcpyAsync(z, sz, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     BCS_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->slab) check_device_flags(s);   // a rank that dropped a halo / migration record must not hand out its state as good
     BCS_API_END
 }
 
@@ -1302,12 +1324,32 @@ int bcs_profile_steps(bcs_sim* s, int32_t nsteps, int32_t cap, char (*names)[BCS
     BCS_API_END
 }
 
+// sticky device-side error flags (halo / migration message overflow, a particle outside the rank's row window, wall-grid
+// list overflow): a run that raised one has silently dropped or misplaced data, so every synchronising entry point reports it
+static void check_device_flags(bcs_sim* s)
+{
+    if (s->slab) BCS_REQUIRE(!slab_check_error(s->slab, s->stream), BCS_ERR_STATE, "a halo / migration message overflowed its capacity (raise bcs_slab_opts capacities)");
+    if (s->rows.enabled && s->rows.local) {
+        int flag = 0;
+        BCS_CUDA(cudaMemcpyAsync(&flag, s->rows.error, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        BCS_REQUIRE(!flag, BCS_ERR_STATE, "an active particle left the rank's window of grid rows (raise bcs_slab_opts.halo_width)");
+    }
+    if (s->wall.enabled) {
+        int overflow = 0;
+        BCS_CUDA(cudaMemcpyAsync(&overflow, s->wall.overflow, sizeof overflow, cudaMemcpyDeviceToHost, s->stream));
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        BCS_REQUIRE(!overflow, BCS_ERR_STATE, "the wall grid outgrew its list capacity (vein deformed far beyond its rest shape)");
+    }
+}
+
 int bcs_synchronize(bcs_sim* s)
 {
     BCS_API_BEGIN
     BCS_REQUIRE(s, BCS_ERR_INVALID, "null handle");
     BCS_CUDA(cudaSetDevice(s->device));
     BCS_CUDA(cudaStreamSynchronize(s->stream));
+    check_device_flags(s);
     BCS_API_END
 }
 
@@ -1347,12 +1389,10 @@ int bcs_get_stats(bcs_sim* s, bcs_stats* o)
     o->wall_rebuilds = 0;
     if (s->wall.enabled) {
         unsigned long long builds = 0;
-        int overflow = 0;
         BCS_CUDA(cudaMemcpy(&builds, s->wall.builds, sizeof builds, cudaMemcpyDeviceToHost));
-        BCS_CUDA(cudaMemcpy(&overflow, s->wall.overflow, sizeof overflow, cudaMemcpyDeviceToHost));
         o->wall_rebuilds = builds;
-        BCS_REQUIRE(!overflow, BCS_ERR_STATE, "the wall grid outgrew its list capacity (vein deformed far beyond its rest shape)");
     }
+    check_device_flags(s);
     BCS_API_END
 }
 

@@ -47,7 +47,7 @@ constexpr int CP_UNROLL = BCS_CP_UNROLL;   // mates of a particle in flight toge
 constexpr int CP_MAX_CELL = 256;     // particles per blood cell supported by the pass
 constexpr int CP_MAX_ROUNDS = 8;     // a group is at most 8 warp rounds (256 particles)
 
-SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTables& tb)
+SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTables& tb, int world)
 {
     SpringPlan p{};
     tb.slot.clear(); tb.adj.clear();
@@ -60,6 +60,10 @@ SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTa
         // cells per group: a power of two, at most 8 (the lanes of a quarter warp), the group at most 8 warp rounds
         int G = 8;
         while (G > 1 && G * P > 32 * CP_MAX_ROUNDS) G >>= 1;
+        // ... and small enough that the machine is not left idle: a group is one warp's work, a B200 holds ~2400 of these
+        // warps, and a rank of a slab decomposition only sees its share of the blood cells
+        const long long share = std::max<long long>(1, (long long)hs.B / std::max(1, world));
+        while (G > 1 && share / G < 2 * 2368) G >>= 1;
         if (forceG) {
             int g = 1;
             while (2 * g <= std::min(atoi(forceG), G)) g <<= 1;
@@ -105,8 +109,8 @@ SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTa
     for (int t = types.n; t <= BCS_MAX_TYPES; ++t) p.blockStart[t] = acc;
     p.totalBlocks = acc;
     p.tileMax = (tileMax + 7) & ~7;
-    // per warp: three state tiles (float4), the spring sums (3 float arrays), 8 cell centres
-    p.warpBytes = 3 * p.tileMax * (int)sizeof(float4) + 3 * p.tileMax * (int)sizeof(float) + 8 * (int)sizeof(float4);
+    // per warp: three state tiles (float4), the spring sums (3 float arrays), 8 cell centres, 8 blood-cell ids (slab mode)
+    p.warpBytes = 3 * p.tileMax * (int)sizeof(float4) + 3 * p.tileMax * (int)sizeof(float) + 8 * (int)sizeof(float4) + 8 * (int)sizeof(int);
     p.warpBytes = (p.warpBytes + 127) & ~127;
     const char* forceW = getenv("BCS_SPRING_WARPS");
     p.warps = forceW ? std::max(1, std::min(4, atoi(forceW))) : 4;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
     float* sy = sx + plan.tileMax;
     float* sz = sy + plan.tileMax;
     float4* sc = reinterpret_cast<float4*>(sz + plan.tileMax);   // [8] blood-cell centres of the group
+    int* sCid = reinterpret_cast<int*>(sc + 8);                  // [8] slab mode: ids of the group's blood cells
     float4* const gpos = const_cast<float4*>(a.s.pos);
     float4* const gvel = const_cast<float4*>(a.s.vel);
 
@@ -238,7 +243,12 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
         const unsigned cellMagic = plan.cellMagic[t];
         const int cell = lane & (G - 1);           // this lane's blood cell within the group
         const int slot0 = lane / G, slotsPerRound = 32 / G;
-        auto cell_id = [&](int c) { return LISTS ? lists.cells[lists.typeFirst[t] + firstIdx + c] : ty.cStart + firstIdx + c; };
+        if (LISTS) {
+            // slab mode: the group's cells are entries of the rank's owned-cell list, anywhere in the arrays
+            if (lane < nCells) sCid[lane] = lists.cells[lists.typeFirst[t] + firstIdx + lane];
+            __syncwarp();
+        }
+        auto cell_id = [&](int c) { return LISTS ? sCid[c] : ty.cStart + firstIdx + c; };
         // memory order within the group: element e = c * P + k
         auto split = [&](int e, int& c, int& k) { c = (int)(((unsigned)e * cellMagic) >> 20); k = e - c * P; };
         auto particle_of = [&](int e, int c, int k) { return LISTS ? ty.pStart + (cell_id(c) - ty.cStart) * P + k : g0 + e; };

@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const unsigned char* _
             if (pflag) { f = pflag[i]; if (!f) continue; }
         }
         const int2 kp = R.kp[i];
-        const int row = rows_div((unsigned)kp.x, R.nxMagic, R.nxShift);
+        const int row = rows_of_key(R, kp.x);
         R.tmp[R.rowStart[row] + kp.y] = make_int2(kp.x, (f & 1) ? i : (i | (int)0x80000000));
     }
 }
@@ -909,7 +909,11 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
     const int n = nDev ? *nDev : nArg;
     // latch the "irregular particle" flag of this build (the count pass of the NEXT build may already run - fused into
     // the cell pass - before this build's collision stages are through with it)
-    if (blockIdx.x == 0 && threadIdx.x == 0) { R.irregular[1] = R.irregular[0]; R.irregular[0] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        R.irregular[1] = R.irregular[0]; R.irregular[0] = 0;
+        // sentinels: the pair search scans keys until one exceeds its window
+        keys[n] = 0x7fffffff; keys[n + 1] = 0x7fffffff; keys[n + 2] = 0x7fffffff; keys[n + 3] = 0x7fffffff;
+    }
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const int j = base + threadIdx.x;
         bool isNear = false;
@@ -918,7 +922,7 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
             const int2 me = R.tmp[j];
             const int key = me.x, tag = me.y, pid = tag & 0x7fffffff;
             const float4 p = pos[pid];
-            const int row = rows_div((unsigned)key, R.nxMagic, R.nxShift);
+            const int row = rows_of_key(R, key);
             const int s = R.rowStart[row], e = R.rowStart[row + 1];
             int before = 0;
             for (int k = s; k < e; ++k) {
@@ -930,10 +934,6 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
             ids[slot] = tag;
             spos[slot] = p;
             if (j == s) R.rowCount[row] = 0u;   // consumed by the scan; clean for the next count pass
-            if (j == n - 1) {
-                // sentinels: the pair search scans keys until one exceeds its window
-                keys[n] = 0x7fffffff; keys[n + 1] = 0x7fffffff; keys[n + 2] = 0x7fffffff; keys[n + 3] = 0x7fffffff;
-            }
             if (PROBE && tag >= 0) {
                 const int hx = (int)fminf(fmaxf(floorf((p.x - probe.ox) * probe.invh), 0.f), (float)(probe.nx - 1));
                 const int hy = (int)fminf(fmaxf(floorf((p.y - probe.oy) * probe.invh), 0.f), (float)(probe.ny - 1));
@@ -953,13 +953,6 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
             }
         }
     }
-}
-
-__global__ void row_empty_kernel(int nArg, const int* __restrict__ nDev, int* __restrict__ keys)
-{
-    // no active particle: only the sentinels
-    const int n = nDev ? *nDev : nArg;
-    if (n == 0 && threadIdx.x < 4) keys[threadIdx.x] = 0x7fffffff;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1119,7 +1112,7 @@ static void launch_grid_build_rows(const GridBuildArgs& a, cudaStream_t st)
     const RowsGrid& R = a.rows;
     const int n = g.n, blocks = (n + 255) / 256;
     const int itemBlocks = a.items.cells ? (int)std::min<long long>(((long long)a.itemCapacity + 255) / 256, BOUNDED_BLOCKS) : blocks;
-    const int orderBlocks = a.nDev ? std::min(blocks, BOUNDED_BLOCKS) : blocks;
+    const int orderBlocks = std::max(1, a.nDev ? std::min(blocks, BOUNDED_BLOCKS) : blocks);
     SortScratch* sc = a.scratch;
     if (!R.countDone) launch_row_count(a, st);
     // rowStart = exclusive scan of the per-row counts; rowStart[nRows] = number of sorted slots
@@ -1138,7 +1131,6 @@ static void launch_grid_build_rows(const GridBuildArgs& a, cudaStream_t st)
         BCS_LAUNCH("finalize_grid", st, row_order_kernel<true><<<orderBlocks, 256, 0, st>>>(n, a.nDev, R, a.keys[1], a.ids[1], a.pos, a.spos, *a.probe));
     else
         BCS_LAUNCH("finalize_grid", st, row_order_kernel<false><<<orderBlocks, 256, 0, st>>>(n, a.nDev, R, a.keys[1], a.ids[1], a.pos, a.spos, NearProbe{}));
-    if (a.nDev) BCS_LAUNCH("row_empty", st, row_empty_kernel<<<1, 32, 0, st>>>(n, a.nDev, a.keys[1]));
     BCS_CUDA(cudaGetLastError());
 }
 

@@ -45,6 +45,12 @@ struct RowsGrid {
     int nxShift;
     int countDone;            // 1: the count pass of THIS build already ran (fused into the previous step's cell pass)
     int nx;                   // cells per row
+    // slab decomposition: the directory only spans the cell rows y0 .. y0 + nyL - 1 of every z layer (the rank's slab plus its
+    // halo), in the same z-major order, so that its scan costs O(local rows) however long the vein is.  local == 0: all rows.
+    int local, ny, nyL, y0;
+    unsigned long long nyMagic;   // exact division by ny
+    int nyShift;
+    int* error;               // sticky device flag raised when an active particle lies outside the local window
 };
 
 struct NearProbe;
@@ -105,7 +111,7 @@ struct SpringTables {                    // host copies of the per-type tables (
     std::vector<int> slot;
     std::vector<int2> adj;
 };
-SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTables& tables);
+SpringPlan make_spring_plan(const TypesDev& types, const HostScene& hs, SpringTables& tables, int world = 1);
 // Near-wall probe carried by the spring kernel (every particle's position passes through its registers anyway): one byte
 // of the wall grid's dilated occupancy answers "can this particle reach the wall at all"; the few that can are listed
 // for the wall filter, which then never streams the other ~97 % of the particles.  near == null: disabled.
@@ -176,6 +182,7 @@ struct CollideArgs {
     bool rowsMode;
     bool fullWalk;              // BCS_COLLIDE=walk: every slot scans its whole stencil (the fallback path) instead
     const int* rowStart;
+    RowsGrid rowsGrid;          // the directory's geometry (row of a cell id: rows_of_key, rows_device.cuh)
     int nRows;
     const int* ids;             // sorted particle ids (bit 31: ghost)
     const float4* vel;          // velocities by particle id
@@ -239,6 +246,8 @@ struct VeinArgs {
     const float* nbrLen;
     const unsigned* vidx;       // [3T]
     const unsigned char* vOwned;   // slab mode: [V] 1 = vertex integrated by this rank; null = all
+    int vFirst, vCount;            // the vertex kernels cover ids [vFirst, vFirst + vCount): everything, or (slab mode) the id range
+                                   // of the rank's slab + vertex halo - meshes are numbered ring by ring, so that is O(local)
     const float4* vposBuilt;       // wall grid: positions at build time, margin and the flag to raise (null: no tracking)
     float wallMargin;
     int* wallDirty;

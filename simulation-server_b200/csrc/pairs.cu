@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_search_kernel(const CollideAr
             const int w1 = nr > 1 ? w0 + g.nx : (int)0x80000000;          // absent row: (unsigned)(k - w) is never below nb
             const int w2 = nr > 2 ? w0 + 2 * g.nx : (int)0x80000000;
             const int hi = c + plane + y1 * g.nx + x1;
-            int j = a.rowStart[rows_div((unsigned)w0, a.nxMagic, a.nxShift)];
+            int j = a.rowStart[rows_of_key(a.rowsGrid, w0)];
             int k = a.keys[j];
             while (k <= hi) {
                 const int kn = a.keys[j + 1];
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs
                 hi = max(hi, c0 + nbi - 1);
             }
             if (hi < 0) continue;
-            int j = a.rowStart[rows_div((unsigned)lo, a.nxMagic, a.nxShift)];
+            int j = a.rowStart[rows_of_key(a.rowsGrid, lo)];
             for (int k = a.keys[j]; k <= hi; k = a.keys[++j]) {
                 if (j >= n) break;
                 const bool in = (unsigned)(k - w[0]) < nb || (unsigned)(k - w[1]) < nb || (unsigned)(k - w[2]) < nb;
@@ -321,7 +321,7 @@ void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st)
 {
     const int threads = PS_THREADS, allBlocks = (a.n + threads - 1) / threads;
     const int blocks = a.nDev ? std::min(allBlocks, 2 * BOUNDED_BLOCKS) : allBlocks;
-    const int walkBlocks = std::min(allBlocks, 2 * BOUNDED_BLOCKS);
+    const int walkBlocks = std::min(allBlocks, BOUNDED_BLOCKS);   // normally idle (returns at once): half a wave is enough
     const bool dbg = a.dbgCount != nullptr, slab = a.nDev != nullptr;
     if (a.fullWalk) {
         if (dbg) BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<true, true, false><<<walkBlocks, threads, 0, st>>>(a));

@@ -12,6 +12,24 @@ __device__ __forceinline__ int rows_div(unsigned n, unsigned long long magic, in
     return (int)(((unsigned long long)n * magic) >> shift);   // exact for n < 2^31 (magic = ceil(2^shift / d), shift = 32 + ceil(log2 d))
 }
 
+// directory row of a cell id: key / nx, re-based to the rank's window of cell rows under slab decomposition
+__device__ __forceinline__ int rows_local(const RowsGrid& R, int cy, int cz)
+{
+    int y = cy - R.y0;
+    if ((unsigned)y >= (unsigned)R.nyL) {
+        *R.error = 1;   // an active particle outside slab + halo: the message capacities / halo width no longer fit the run
+        y = max(0, min(y, R.nyL - 1));
+    }
+    return cz * R.nyL + y;
+}
+__device__ __forceinline__ int rows_of_key(const RowsGrid& R, int key)
+{
+    const int grow = rows_div((unsigned)key, R.nxMagic, R.nxShift);
+    if (!R.local) return grow;
+    const int cz = rows_div((unsigned)grow, R.nyMagic, R.nyShift);
+    return rows_local(R, grow - cz * R.ny, cz);
+}
+
 // Cell id, row and "irregular" flag of a position (calculateIdForCell, grids/uniform_grid.cu:24-36, plus the unclamped
 // per-axis index particle_collisions.cuh:117-119 trims the stencil by).  One quotient per axis serves both.
 struct RowKey {
@@ -36,7 +54,7 @@ __device__ __forceinline__ RowKey rows_key(const GridDev& g, const RowsGrid& R, 
     // (particle_collisions.cuh:126-268 trims by the UNclamped index): the symmetric pair search steps aside for the build
     o.irregular = o.oob || rx != cx || ry != cy || rz != cz || cx >= g.nx || cy >= g.ny || cz >= g.nz;
     o.key = key;
-    o.row = o.irregular ? rows_div((unsigned)key, R.nxMagic, R.nxShift) : cz * g.ny + cy;
+    o.row = o.irregular ? rows_of_key(R, key) : (R.local ? rows_local(R, cy, cz) : cz * g.ny + cy);
     return o;
 }
 

@@ -354,6 +354,16 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
             if (init.rank < init.world - 1 && y < init.yLo + init.vertexHalo) vlist[1].push_back(v);
         }
         BCS_CUDA(cudaMemcpy(s->vOwned, vOwned.data(), ctx.V, cudaMemcpyHostToDevice));
+        {
+            // id range of everything this rank integrates or may splat on: rest position inside slab + vertex halo
+            int lo = ctx.V, hi = -1;
+            for (int v = 0; v < ctx.V; ++v) {
+                const float y = hs.vy[v];
+                if (y >= init.yLo - init.vertexHalo && y < init.yHi + init.vertexHalo) { lo = std::min(lo, v); hi = std::max(hi, v); }
+            }
+            s->vFirst = hi >= lo ? lo : 0;
+            s->vCount = hi >= lo ? hi - lo + 1 : 0;
+        }
         for (int d = 0; d < 2; ++d) {
             s->vertCount[d] = (int)vlist[d].size();
             s->vertList[d] = salloc<int>(s, vlist[d].size());

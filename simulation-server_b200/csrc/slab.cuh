@@ -65,6 +65,7 @@ struct SlabState {
     int capMig = 0, capHalo = 0, capVert = 0;
     int* vertList[2] = {nullptr, nullptr};
     int vertCount[2] = {0, 0};
+    int vFirst = 0, vCount = 0;   // id range of the vertices within slab + vertex halo (what the vertex kernels sweep)
     bool primed = false;
     bool listsValid = false;   // owned-cell lists describe the current ownership
     std::vector<void*> owned;

@@ -33,12 +33,27 @@ void launch_tri_centers(const VeinArgs& a, float4* centers, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
+// Mesh vertices are numbered ring by ring (config/vein_definition.hpp:12 and the generated cylinders alike), so the nine
+// neighbours of a vertex lie within ~a ring of it in the arrays.  A CTA therefore stages a WINDOW of positions and
+// velocities around its 256 vertices in shared memory with coalesced loads and gathers from there; a neighbour outside
+// the window (any mesh is legal) is read from global memory.
+constexpr int VG_THREADS = 256;
+constexpr int VG_HALO = 128;
+constexpr int VG_WINDOW = VG_THREADS + 2 * VG_HALO;
+
+__global__ void __launch_bounds__(VG_THREADS) vein_gather_kernel(const VeinArgs a)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= a.V) return;
+    __shared__ float4 wp[VG_WINDOW], wv[VG_WINDOW];
+    const int base = a.vFirst + blockIdx.x * VG_THREADS - VG_HALO;
+    for (int k = threadIdx.x; k < VG_WINDOW; k += VG_THREADS) {
+        const int v = base + k;
+        if (v >= 0 && v < a.V) { wp[k] = a.vpos[v]; wv[k] = a.vvel[v]; }
+    }
+    __syncthreads();
+    const int id = a.vFirst + blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= a.vFirst + a.vCount) return;
     if (a.vOwned && !a.vOwned[id]) return;   // slab mode: only vertices of this rank's slab
-    const float3 p = xyz(a.vpos[id]), v = xyz(a.vvel[id]);
+    const float3 p = xyz(wp[threadIdx.x + VG_HALO]), v = xyz(wv[threadIdx.x + VG_HALO]);
     float3 F = f3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < BCS_VEIN_MAX_NEIGHBORS; ++s) {
@@ -47,10 +62,14 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
         const int nbRaw = __ldg(a.nbrIds + (size_t)s * a.V + id);
         const int nb = nbRaw < 0 ? id : nbRaw;
         const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
-        const float3 q = xyz(a.vpos[nb]);
+        const unsigned w = (unsigned)(nb - base);
+        float4 q4, qv4;
+        if (w < (unsigned)VG_WINDOW) { q4 = wp[w]; qv4 = wv[w]; }
+        else { q4 = a.vpos[nb]; qv4 = a.vvel[nb]; }
+        const float3 q = xyz(q4);
         // q - p == -(p - q) exactly, so normalize(q-p) == -normalize(p-q).  length() and normalize() share one reciprocal
-        // square root refined to <= 1 ulp (as in the blood-cell spring kernel, springs.cu: spring_force): the IEEE sqrt +
-        // three IEEE divisions per neighbour were ~60 % of this kernel's instructions.  Deviation <= 2 ulp per component.
+        // square root refined to <= 1 ulp (as in the blood-cell spring kernel): the IEEE sqrt + three IEEE divisions per
+        // neighbour were ~60 % of this kernel's instructions.  Deviation <= 2 ulp per component.
         const float3 d = p - q;
         const float d2 = dot(d, d);
         float inv = rsqrtf(d2);
@@ -59,7 +78,7 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
         inv = fmaf(fmaf(-len, inv, 1.0f), inv, inv);
         if (!(d2 > 0.f)) { inv = 0.f; len = 0.f; }   // absent slot / coincident vertices: normalize() yields the zero vector
         const float3 n = f3(d.x * inv, d.y * inv, d.z * inv);
-        const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(a.vvel[nb]))) * a.phys.vein_d_fact;
+        const float sf = (len - L) * a.phys.vein_k_sniff + dot(n, (v - xyz(qv4))) * a.phys.vein_d_fact;
         F = F + sf * f3(-n.x, -n.y, -n.z);
     }
     float4 f = a.vfrc[id];
@@ -69,15 +88,16 @@ __global__ void __launch_bounds__(256) vein_gather_kernel(const VeinArgs a)
 
 void launch_vein_gather(const VeinArgs& a, cudaStream_t st)
 {
-    BCS_LAUNCH("vein_gather", st, vein_gather_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a));
+    if (a.vCount <= 0) return;
+    BCS_LAUNCH("vein_gather", st, vein_gather_kernel<<<(a.vCount + VG_THREADS - 1) / VG_THREADS, VG_THREADS, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
 // v += dt*F; x += dt*v; F = 0   (semi-implicit Euler + the three cudaMemsets of the reference, fused)
 __global__ void __launch_bounds__(256) vein_integrate_kernel(const VeinArgs a)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= a.V) return;
+    const int id = a.vFirst + blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= a.vFirst + a.vCount) return;
     if (a.vOwned && !a.vOwned[id]) {
         // slab mode: not ours - state arrives with the vertex halo; forget the partial splats we accumulated on it
         if (a.vfrc[id].w != 0.f) {
@@ -125,7 +145,8 @@ void launch_vein_fold_splats(const VeinArgs& a, cudaStream_t st)
 
 void launch_vein_integrate(const VeinArgs& a, cudaStream_t st)
 {
-    BCS_LAUNCH("vein_integrate", st, vein_integrate_kernel<<<(a.V + 255) / 256, 256, 0, st>>>(a));
+    if (a.vCount <= 0) return;
+    BCS_LAUNCH("vein_integrate", st, vein_integrate_kernel<<<(a.vCount + 255) / 256, 256, 0, st>>>(a));
     BCS_CUDA(cudaGetLastError());
 }
 
