@@ -502,4 +502,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as e:
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        # a rank that raises must take the job down: its peers would otherwise wait in NCCL for ever
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)

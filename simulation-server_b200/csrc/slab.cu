@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
                 atomicExch(errorFlag, 1);
             }
             // on this side its particles stay around as ghosts for the next step if they are near the face they crossed
-            const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth) || (d == 1 && p.y < slab.yLo + slab.haloWidth);
+            // (a respawned cell goes to the top of the vein, far from any face of this slab, whoever receives it)
+            const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth && p.y < slab.yHi + slab.haloWidth) ||
+                              (d == 1 && p.y < slab.yLo + slab.haloWidth && p.y >= slab.yLo - slab.haloWidth);
             pflag[i] = keep ? 2 : 0;
             if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
             if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
