@@ -264,15 +264,24 @@ int bcs_build_grid(bcs_sim* sim);
 int bcs_compute_forces(bcs_sim* sim);
 /* sim::SimulationController::propagateAll() (simulation_controller.cu:315-331) */
 int bcs_integrate(bcs_sim* sim);
-/* nsteps x { build_grid; compute_forces; integrate } without host round trips (CUDA graph replay). */
+/* nsteps x { build_grid; compute_forces; integrate } without host round trips (CUDA graph replay).  Inside a run of
+ * nsteps > 1 the end of step k and the spring stage of step k + 1 share one pass over the particle state; the state a
+ * caller sees after the call is exactly that of nsteps single steps (bit for bit). */
 int bcs_step(bcs_sim* sim, int32_t nsteps);
+/* Waits for the handle's stream and reports sticky device-side errors with BCS_ERR_STATE (bcs_last_error names them): a
+ * halo / migration message that overflowed its capacity (slab mode: records were dropped, the run is invalid - raise
+ * bcs_slab_opts.migration_capacity / halo_capacity), an active particle outside the rank's window of grid rows (raise
+ * halo_width), a wall grid that outgrew its lists.  bcs_download and bcs_get_stats report the same conditions. */
 int bcs_synchronize(bcs_sim* sim);
 /* number of completed steps (drives the respawn RNG counter) */
 int bcs_get_step_count(const bcs_sim* sim, int64_t* out);
 /* Checkpoint / restart (the reference has none): the complete dynamic state of a simulation is the six
  * state arrays (bcs_download / bcs_upload) plus the step count - the respawn RNG is counter based, keyed by
  * (seed, blood cell, step), so restoring the count restores the random stream.  In slab mode upload the merged global
- * state on every rank: ownership is re-derived from the positions. */
+ * state on every rank: ownership is re-derived from the positions.
+ * BCS_SEM_CLEAN only: under BCS_SEM_REFERENCE the never-cleared particle-grid tables (stale ranges that
+ * double-count pairs) are part of the dynamic state too, so a restored run does not continue bit-identically - restore
+ * is still allowed there (the reference itself has no notion of it), the continuation just starts from clean tables. */
 int bcs_set_step_count(bcs_sim* sim, int64_t steps);
 
 /* Single stages, in the reference's order, for stage-by-stage parity tests. */

@@ -6,5 +6,5 @@ The directory name carries a hyphen, so import it with
 ``importlib.import_module("simulation-server_b200")``.
 """
 from . import bcsd, scene, state  # noqa: F401
-from .scene import CellDef, Scene, Layout, derive_layout, make_cylinder_vein  # noqa: F401
+from .scene import CellDef, Scene, Layout, derive_layout, make_cylinder_vein, make_bifurcated_vein, make_rbc_celldef  # noqa: F401
 from .state import make_initial_state  # noqa: F401

@@ -610,6 +610,15 @@ void launch_wall_slot_info(const int* sortedTriKeys, const int* triIds, const un
 
 void launch_wall_rebuild(const VeinCollideArgs& a, int V, int numSMs, cudaStream_t st)
 {
+    // The rebuild synchronises its CTAs with a spinning grid barrier, so ALL of them must be able to be resident at once:
+    // one CTA per SM, checked against what the device can actually hold (a register count that grew with a compiler
+    // change, or an SM partition, would otherwise make the first real rebuild spin for ever).  CTAs of other kernels
+    // running beside it in the forked graph retire on their own; only this kernel's own grid has to fit.
+    {
+        int perSM = 0;
+        BCS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wall_rebuild_kernel, REBUILD_THREADS, 0));
+        BCS_REQUIRE(perSM >= 1, BCS_ERR_UNSUPPORTED, "the wall-grid rebuild kernel does not fit an SM on this device");
+    }
     BCS_LAUNCH("wall_rebuild", st,
                wall_rebuild_kernel<<<numSMs, REBUILD_THREADS, 0, st>>>(a.wall, a.tgrid, V, a.T, a.vpos, a.vidx, a.triIds, a.cellStart, a.cellEnd,
                                                                         a.groupLocal, a.triCellLocal));

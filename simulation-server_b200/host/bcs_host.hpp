@@ -42,6 +42,11 @@ class UniformGrid {
     int which_;   // 0 particles, 1 triangle centres
 public:
     UniformGrid(Simulation* s, int which) : sim_(s), which_(which) {}
+    // The reference's signature (grids/uniform_grid.cuh:53: calculateGrid(const cudaVec3& positions, int objectCount)), so
+    // that main.cu:175-176 compiles unchanged.  The library owns the device arrays, so `positions` only names them (any
+    // type is accepted and ignored); objectCount must be the number of objects of the grid.
+    template <class Positions>
+    void calculateGrid(const Positions& positions, int objectCount);
     void calculateGrid();
     void download(std::vector<int32_t>& cellIds, std::vector<int32_t>& objectIds);
 };
@@ -88,6 +93,13 @@ public:
     void synchronize() { check(bcs_synchronize(h_), "bcs_synchronize"); }
 };
 
+template <class Positions>
+inline void UniformGrid::calculateGrid(const Positions&, int objectCount)
+{
+    const int n = which_ == 0 ? sim_->layout().n_particles : sim_->layout().n_triangles;
+    if (objectCount != n) throw Error(BCS_ERR_INVALID, "calculateGrid: objectCount does not match the grid's object count");
+    calculateGrid();
+}
 inline void UniformGrid::calculateGrid()
 {
     check(bcs_run_stage(sim_->handle(), which_ == 0 ? BCS_STAGE_GRID_PARTICLES : BCS_STAGE_GRID_TRIANGLES), "calculateGrid");

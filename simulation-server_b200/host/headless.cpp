@@ -103,8 +103,9 @@ int main(int argc, char** argv)
         } else {
             // MAIN LOOP - the four calls of main.cu:175-176,199,208, in that order
             while (shouldBeRunning) {
-                sim.particleGrid.calculateGrid();
-                sim.triangleCentersGrid.calculateGrid();
+                // the reference's own call sites, arguments included (the library owns the device arrays: `positions` names them)
+                sim.particleGrid.calculateGrid(bcs_host::Vec3Host{}, sim.particleCount());
+                sim.triangleCentersGrid.calculateGrid(bcs_host::Vec3Host{}, sim.layout().n_triangles);
                 sim.simulationController.calculateNextFrame();
                 sim.simulationController.propagateAll();
                 if (++frameCount >= maxFrames) shouldBeRunning = false;

@@ -266,3 +266,77 @@ def make_cylinder_vein(length: float, radius: float = 50.0, ring_step: float = 5
     end_c = np.asarray([[0.0, y_bottom, 0.0]], np.float32)
     end_r = np.asarray([radius * 0.7], np.float32)
     return pos.reshape(-1, 3), idx, end_c, end_r
+
+
+def make_bifurcated_vein(trunk_length: float = 150.0, branch_length: float = 150.0, radius: float = 50.0, branch_radius: float = 36.0,
+                         half_angle_deg: float = 25.0, ring_step: float = 5.0, ring_vertices: int = 100):
+    """A Y-shaped vein in the tessellation of :func:`make_cylinder_vein`: a trunk along -y that splits into two branches
+    leaning +-``half_angle_deg`` in x (the reference's default mesh, config/vein_definition.hpp:12, bifurcates the same way).
+    The three tubes are separate ring stacks; the branches start one ring inside the trunk's end so that the walls
+    overlap at the junction instead of being stitched.  One vein ending per branch.
+    Returns (vein_pos (V,3) f32, vein_indices (T,3) u32, ending_centers (2,3), ending_radii (2,))."""
+    n = ring_vertices
+    ang = 2.0 * np.pi * np.arange(n) / n
+
+    def tube(origin, direction, length, r):
+        d = np.asarray(direction, np.float64)
+        d /= np.linalg.norm(d)
+        # orthonormal frame: u in the x-y plane, w = z axis (branches lean in x only)
+        w = np.array([0.0, 0.0, 1.0])
+        u = np.cross(d, w)
+        u /= np.linalg.norm(u)
+        rings = int(round(length / ring_step)) + 1
+        t = (np.arange(rings) * ring_step)[:, None, None]
+        circle = (np.cos(ang)[:, None] * u[None, :] + np.sin(ang)[:, None] * w[None, :]) * r
+        return (np.asarray(origin, np.float64)[None, None, :] + t * d[None, None, :] + circle[None, :, :]).astype(np.float32)
+
+    def stitch(rings, base):
+        k = np.arange(n)
+        k1 = (k + 1) % n
+        tris = []
+        for r in range(rings - 1):
+            up, lo = base + r * n, base + (r + 1) * n
+            t = np.empty((n, 2, 3), np.uint32)
+            t[:, 0, 0] = lo + k; t[:, 0, 1] = up + k; t[:, 0, 2] = up + k1
+            t[:, 1, 0] = lo + k; t[:, 1, 1] = up + k1; t[:, 1, 2] = lo + k1
+            tris.append(t.reshape(-1, 3))
+        return np.concatenate(tris)
+
+    a = np.deg2rad(half_angle_deg)
+    split = np.array([0.0, -trunk_length + ring_step, 0.0])
+    tubes = [tube((0.0, 0.0, 0.0), (0.0, -1.0, 0.0), trunk_length, radius),
+             tube(split + np.array([-0.5 * radius, 0.0, 0.0]), (-np.sin(a), -np.cos(a), 0.0), branch_length, branch_radius),
+             tube(split + np.array([0.5 * radius, 0.0, 0.0]), (np.sin(a), -np.cos(a), 0.0), branch_length, branch_radius)]
+    pos, idx, base = [], [], 0
+    for tb in tubes:
+        pos.append(tb.reshape(-1, 3))
+        idx.append(stitch(tb.shape[0], base))
+        base += tb.shape[0] * n
+    ends = np.stack([tubes[1][-1].mean(axis=0), tubes[2][-1].mean(axis=0)]).astype(np.float32)
+    # three decimals: every coordinate survives the reference's fixed-point header format (headers.py)
+    return (np.round(np.concatenate(pos), 3).astype(np.float32), np.concatenate(idx).astype(np.uint32), np.round(ends, 3).astype(np.float32),
+            np.asarray([branch_radius * 0.7] * 2, np.float32))
+
+
+def make_rbc_celldef(count: int, radius: float = 3.9, thickness: float = 1.2) -> CellDef:
+    """A red-blood-cell preset in the reference's BloodCellDef form (blood_cells_def_type.hpp:21-31; the reference ships
+    White_blood_cell_One and Blood_dust_One only, blood_cell_presets.hpp:13,174): a biconcave disc sampled with 26
+    particles - an 8-vertex equator, an 8-vertex ring at 0.55 R on either face (thick), a centre vertex on either face
+    (thin: the dimple) - and springs along the rings, between neighbouring rings, across the disc and through it."""
+    pts = []
+    ring = lambda r, z, phase: [(r * np.cos(2 * np.pi * (k + phase) / 8), z, r * np.sin(2 * np.pi * (k + phase) / 8)) for k in range(8)]
+    pts += ring(radius, 0.0, 0.0)                                   # 0..7   equator
+    pts += ring(0.55 * radius, 0.5 * thickness, 0.5)                # 8..15  upper ring
+    pts += ring(0.55 * radius, -0.5 * thickness, 0.5)               # 16..23 lower ring
+    pts += [(0.0, 0.2 * thickness, 0.0), (0.0, -0.2 * thickness, 0.0)]   # 24, 25 dimple centres
+    v = np.round(np.asarray(pts, np.float64), 3)
+    springs = []
+    for k in range(8):
+        k1 = (k + 1) % 8
+        springs += [(k, k1), (8 + k, 8 + k1), (16 + k, 16 + k1)]                  # along the rings
+        springs += [(k, 8 + k), (k1, 8 + k), (k, 16 + k), (k1, 16 + k)]           # equator <-> rings
+        springs += [(8 + k, 16 + k), (8 + k, 24), (16 + k, 25)]                   # through the disc, to the dimple
+    springs += [(k, k + 4) for k in range(4)] + [(24, 25)]                          # across the disc
+    se = np.asarray(springs, np.int32)
+    length = np.round(np.linalg.norm(v[se[:, 0]] - v[se[:, 1]], axis=1), 4).astype(np.float32)
+    return CellDef(int(count), 26, se, length, v.astype(np.float32))

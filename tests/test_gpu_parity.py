@@ -236,6 +236,26 @@ def test_alternative_paths_equal_the_default_bitwise(bcs_lib, monkeypatch, switc
         assert np.array_equal(x, y), f"{switch}: array {w} differs from the default path"
 
 
+def test_reaction_force_disabled_vs_oracle(bcs_lib, oracle_lib):
+    """the `enableReactionForce = false` branch of the wall collision (vein_collisions.cu:248-252) - the
+    particle keeps its force and only its velocity is reflected.  libbcs vs oracle stage by stage, and the branch must
+    actually change the forces of the particles that hit the wall."""
+    sc = small_cylinder_scene()
+    sc.flags["enable_reaction_force"] = 0
+    st = pkg.make_initial_state(sc, seed=7, xz_half_width=49.0, y_range=(-25.0, -110.0))
+    with make_bcs(sc) as sim, make_oracle(oracle_lib, sc) as orc:
+        orc.upload_state(st)
+        summary = stagecheck.compare_step(sim, orc, sc, 6, "no reaction force")
+        assert summary["vein_hits"] > 20, summary
+        off = refcheck.down(sim, capi.PARTICLE_FRC)
+    sc.flags["enable_reaction_force"] = 1
+    with make_bcs(sc) as sim:
+        sim.upload_state(st)
+        sim.step(6)
+        on = refcheck.down(sim, capi.PARTICLE_FRC)
+    assert (np.abs(on - off).max(axis=1) > 1e-3).sum() > 10, "the reaction-force switch changed nothing"
+
+
 def test_fused_run_equals_single_steps(bcs_lib):
     """bcs_step(n) in row-directory mode runs the end of step k and the springs / row count of step k + 1 as one pass over
     the particle state (cellpass.cu: launch_advance); n calls of bcs_step(1) never fuse.  Same bits, teleports included."""

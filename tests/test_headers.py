@@ -24,6 +24,14 @@ def _scene():
     return pkg.Scene(user_defs=defs, vein_pos=vp, vein_indices=vi, ending_centers=ec, ending_radii=er), [n for n, _ in presets]
 
 
+def _rbc_scene():
+    """an RBC preset (26 particles, not in the reference's preset file) in a bifurcated vein"""
+    presets = workloads.reference_presets()
+    defs = [pkg.make_rbc_celldef(4), pkg.CellDef(2, presets[0][1].particles_in_cell, presets[0][1].springs, presets[0][1].spring_lengths, presets[0][1].vertices)]
+    vp, vi, ec, er = pkg.make_bifurcated_vein(trunk_length=40.0, branch_length=40.0, ring_vertices=16)
+    return pkg.Scene(user_defs=defs, vein_pos=vp, vein_indices=vi, ending_centers=ec, ending_radii=er), ["Red_blood_cell_One", presets[0][0]]
+
+
 def test_fixed_point_round_trip():
     for v in (3.849, -3.849, 7.697985, 4.757623, 50.0, -481.949, 34.946, 0.0, 1e-3):
         for p in (4, 7):
@@ -50,9 +58,24 @@ def test_headers_are_written_in_the_reference_format(tmp_path):
         assert f"using {n}_Springs = mp_list<" in presets and f"using {n}_Vertices = mp_list<" in presets
 
 
+def test_rbc_preset_and_bifurcated_vein_run_on_the_oracle(oracle_lib):
+    """an RBC preset and a Y-shaped vein as scene data - the host-core port accepts them and steps"""
+    from conftest import capi, make_oracle
+    sc, names = _rbc_scene()
+    assert sc.vein_indices.max() < len(sc.vein_pos) and len(sc.ending_radii) == 2
+    st = pkg.make_initial_state(sc, seed=3, xz_half_width=10.0, y_range=(-10.0, -25.0))
+    with make_oracle(oracle_lib, sc) as orc:
+        assert orc.n_particles == 4 * 26 + 2 * 20
+        orc.upload_state(st)
+        orc.step(5)
+        pos = np.stack(orc.download(capi.PARTICLE_POS), 1)
+        assert np.isfinite(pos).all() and np.abs(pos - np.stack([st["pos_x"], st["pos_y"], st["pos_z"]], 1)).max() > 0.5
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="reference tree not present on this machine")
-def test_written_headers_compile_in_the_reference_meta_factory(tmp_path):
-    sc, names = _scene()
+@pytest.mark.parametrize("which", ["presets", "rbc_bifurcated"])
+def test_written_headers_compile_in_the_reference_meta_factory(tmp_path, which):
+    sc, names = _scene() if which == "presets" else _rbc_scene()
     cfg = tmp_path / "cfg"
     headers.write_config(str(cfg), sc, names)
     src = tmp_path / "src"
