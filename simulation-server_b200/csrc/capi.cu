@@ -874,8 +874,9 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
                     R.enabled = 1;
                     R.nRows = (int)nRows;
                     R.rowCount = s->track(dev_alloc<unsigned>((size_t)nRows + 16));
-                    R.rowStart = s->track(dev_alloc<int>((size_t)nRows + 16));
-                    R.kp = s->track(dev_alloc<int2>(N));
+                    // + 3: the scan writes from rowStart[1] on with 16-byte vector stores
+                    R.rowStart = s->track(dev_alloc<int>((size_t)nRows + 24)) + 3;
+                    R.keyOf = s->track(dev_alloc<int>(N));
                     R.tmp = s->track(dev_alloc<int2>(N));
                     R.irregular = s->track(dev_alloc<int>(2));
                     R.error = s->track(dev_alloc<int>(1));

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
         }
 
         // ---- memory-order sweep: environment forces, F <- (F_old + F_new) / 2, near-wall probe, row count of the next grid
-        // build, coalesced write back.  The atomic of a round is issued before the stores that need its result.
+        // build (a reduction per particle), coalesced write back.
         for (int e0 = 0; e0 < nPart; e0 += 32) {
             const int e = e0 + lane;
             const bool on = e < nPart;
@@ -403,14 +403,7 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
             const int gidx = on ? particle_of(e, c, k) : 0;
             float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (on) p4 = tp[ti];
-            int key = 0, place = 0;
-            if (COUNT && on) {
-                const RowKey rk = rows_key(a.grid, a.rows, p4);
-                if (rk.oob) atomicAdd(&a.g.counters->oob, 1ull);
-                if (rk.irregular) a.rows.irregular[0] = 1;
-                key = rk.key;
-                place = (int)atomicAdd(&a.rows.rowCount[rk.row], 1u);
-            }
+            if (COUNT && on) rows_count_particle(a.grid, a.rows, p4, gidx, 1, a.g.counters);
             bool isNear = false;
             if (SPRINGS && on) {
                 const float4 v4 = tv[ti], f4 = tf[ti];
@@ -445,7 +438,6 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 }
             }
             if (INTEGRATE && on) { gpos[gidx] = p4; gvel[gidx] = tv[ti]; }
-            if (COUNT && on) a.rows.kp[gidx] = make_int2(key, place);
         }
         __syncwarp();   // the tiles are free for the next group's copies
         TICK(5);   // environment + count + write back

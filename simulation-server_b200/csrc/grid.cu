@@ -893,9 +893,11 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(const unsigned char* _
             if (i >= n) continue;
             if (pflag) { f = pflag[i]; if (!f) continue; }
         }
-        const int2 kp = R.kp[i];
-        const int row = rows_of_key(R, kp.x);
-        R.tmp[R.rowStart[row] + kp.y] = make_int2(kp.x, (f & 1) ? i : (i | (int)0x80000000));
+        const int key = R.keyOf[i];
+        const int row = rows_of_key(R, key);
+        // the row's cursor is the scan's output for it (rowStart[row + 1]); bumped once per member it ends as the row's end
+        const int slot = atomicAdd(&R.rowStart[row + 1], 1);
+        R.tmp[slot] = make_int2(key, (f & 1) ? i : (i | (int)0x80000000));
     }
 }
 
@@ -1121,10 +1123,10 @@ static void launch_grid_build_rows(const GridBuildArgs& a, cudaStream_t st)
     if (sc->twoPassScan) {
         BCS_LAUNCH("row_start_totals", st, cs_tile_totals_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals));
         BCS_LAUNCH("row_start_scan", st,
-                   cs_scan_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals, R.rowStart, nullptr, n, a.nDev));
+                   cs_scan_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals, R.rowStart + 1, nullptr, n, a.nDev));
     } else {
         BCS_LAUNCH("row_start_scan", st,
-                   cs_scan_fused_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanStatus, ctl, R.rowStart, nullptr, n, a.nDev));
+                   cs_scan_fused_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanStatus, ctl, R.rowStart + 1, nullptr, n, a.nDev));
     }
     BCS_LAUNCH("row_scatter", st, row_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, R, a.items));
     if (a.probe && a.probe->near)

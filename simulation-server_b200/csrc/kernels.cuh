@@ -26,9 +26,11 @@ struct SortScratch {
 
 // Row-directory grid build (clean semantics, sparse scenes; BCS_GRID=rows).  A "row" is the run of nx x-adjacent cells
 // of one (y, z): cell ids are x-fastest (uniform_grid.cu:33-35), so row r = id / nx and the sorted list is row-major.
-//   count    per particle: key, place = atomicAdd(rowCount[row])            (rides in the cell pass of the previous step)
-//   scan     rowStart = exclusive scan of rowCount                          (nRows entries: 0.7 M for the 1 M-particle vein)
-//   scatter  tmp[rowStart[row] + place] = (key, id)                         rows contiguous, unordered inside
+//   count    per particle: key; rowCount[row] += 1 (a reduction: nothing waits for it; rides in the cell pass of the previous step)
+//   scan     rowStart[row + 1] = exclusive scan of rowCount = first slot of the row   (0.7 M rows for the 1 M-particle vein)
+//   scatter  tmp[atomicAdd(rowStart[row + 1], 1)] = (key, id)               rows contiguous, unordered inside; the bumps turn
+//                                                                           rowStart[row + 1] into the row's END = start of row + 1,
+//                                                                           i.e. rowStart[] is now the start table itself
 //   order    per slot: rank of (key, id) inside its row (rows hold ~5 particles) -> keys / ids / sorted positions,
 //            rowCount cleared for the next build
 // The (cell id, particle id) order is unique, so keys / ids are bit-identical to the other grid builds.
@@ -36,8 +38,9 @@ struct RowsGrid {
     int enabled;
     int nRows;
     unsigned* rowCount;       // [nRows + 1] all zero between builds
-    int* rowStart;            // [nRows + 2] first sorted slot of each row; rowStart[nRows] = number of sorted slots
-    int2* kp;                 // [N] by particle id: (cell id, place inside its row)
+    int* rowStart;            // [nRows + 2] after the scatter pass: first sorted slot of each row, rowStart[nRows] = number of
+                              // sorted slots; rowStart[0] is 0 for ever (the scan writes from [1] on)
+    int* keyOf;               // [N] by particle id: cell id
     int2* tmp;                // [N] row-contiguous (cell id, id | ghost tag)
     int* irregular;           // [2] device flags: a particle sits outside the grid (its stencil is not symmetric).  [0] raised by
                               // the count pass, latched into [1] (and cleared) by the order pass; the collision stage reads [1]

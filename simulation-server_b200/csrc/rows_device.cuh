@@ -58,14 +58,15 @@ __device__ __forceinline__ RowKey rows_key(const GridDev& g, const RowsGrid& R, 
     return o;
 }
 
-// key + place of one particle.  flag bit 0: owned (only owned particles are counted as out of bounds).
+// key of one particle, its row counted (a reduction: no value comes back, nothing waits).  flag bit 0: owned (only owned
+// particles are counted as out of bounds).
 __device__ __forceinline__ void rows_count_particle(const GridDev& g, const RowsGrid& R, const float4 p, int i, int flag, Counters* __restrict__ counters)
 {
     const RowKey k = rows_key(g, R, p);
     if (k.oob && (flag & 1)) atomicAdd(&counters->oob, 1ull);
     if (k.irregular) R.irregular[0] = 1;
-    const int place = (int)atomicAdd(&R.rowCount[k.row], 1u);
-    R.kp[i] = make_int2(k.key, place);
+    atomicAdd(&R.rowCount[k.row], 1u);
+    R.keyOf[i] = k.key;
 }
 
 }  // namespace bcs
