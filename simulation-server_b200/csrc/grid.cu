@@ -908,6 +908,11 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
                                                         int* __restrict__ ids, const float4* __restrict__ pos, float4* __restrict__ spos,
                                                         const NearProbe probe)
 {
+    __shared__ int sNear, sBase;
+    if (PROBE) {
+        if (threadIdx.x == 0) sNear = 0;
+        __syncthreads();
+    }
     const int n = nDev ? *nDev : nArg;
     // latch the "irregular particle" flag of this build (the count pass of the NEXT build may already run - fused into
     // the cell pass - before this build's collision stages are through with it)
@@ -945,14 +950,21 @@ __global__ void __launch_bounds__(256) row_order_kernel(int nArg, const int* __r
             }
         }
         if (PROBE) {
+            // CTA-aggregated append: one global atomic per CTA and round (a third of the particles are near the wall, so a
+            // per-warp atomic would put ~30 000 operations per step on one address)
             const unsigned m = __ballot_sync(0xffffffffu, isNear);
-            if (m) {
-                const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-                int b = 0;
-                if (lane == leader) b = atomicAdd(probe.count, __popc(m));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (isNear) probe.list[b + __popc(m & ((1u << lane) - 1u))] = pidOut;
+            const int lane = threadIdx.x & 31;
+            int local = 0;
+            if (m && lane == 0) local = atomicAdd(&sNear, __popc(m));
+            local = __shfl_sync(0xffffffffu, local, 0);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                sBase = sNear ? atomicAdd(probe.count, sNear) : 0;
+                sNear = 0;
             }
+            __syncthreads();
+            if (isNear) probe.list[sBase + local + __popc(m & ((1u << lane) - 1u))] = pidOut;
+            __syncthreads();   // sBase is rewritten in the next round
         }
     }
 }

@@ -55,13 +55,20 @@ __global__ void __launch_bounds__(VG_THREADS) vein_gather_kernel(const VeinArgs 
     if (a.vOwned && !a.vOwned[id]) return;   // slab mode: only vertices of this rank's slab
     const float3 p = xyz(wp[threadIdx.x + VG_HALO]), v = xyz(wv[threadIdx.x + VG_HALO]);
     float3 F = f3(0.f, 0.f, 0.f);
+    // all eighteen table loads first: they are independent, and a vertex has nothing else to do while they fly
+    int nbr[BCS_VEIN_MAX_NEIGHBORS];
+    float len0[BCS_VEIN_MAX_NEIGHBORS];
+#pragma unroll
+    for (int s = 0; s < BCS_VEIN_MAX_NEIGHBORS; ++s) {
+        nbr[s] = __ldg(a.nbrIds + (size_t)s * a.V + id);
+        len0[s] = __ldg(a.nbrLen + (size_t)s * a.V + id);
+    }
 #pragma unroll
     for (int s = 0; s < BCS_VEIN_MAX_NEIGHBORS; ++s) {
         // branch-free so that the nine neighbour gathers are in flight together: an absent slot (-1) reads the
         // vertex itself, whose zero separation normalises to the zero vector and contributes exactly +0
-        const int nbRaw = __ldg(a.nbrIds + (size_t)s * a.V + id);
-        const int nb = nbRaw < 0 ? id : nbRaw;
-        const float L = __ldg(a.nbrLen + (size_t)s * a.V + id);
+        const int nb = nbr[s] < 0 ? id : nbr[s];
+        const float L = len0[s];
         const unsigned w = (unsigned)(nb - base);
         float4 q4, qv4;
         if (w < (unsigned)VG_WINDOW) { q4 = wp[w]; qv4 = wv[w]; }
