@@ -178,6 +178,7 @@ struct bcs_sim {
     PairLists pairs{};
     unsigned long long* phaseClock = nullptr;   // BCS_CP_CLOCK: per-phase cycle sums of the cell pass (developer aid)
     bool collideWalk = false;       // BCS_COLLIDE=walk: every slot scans its whole stencil (A/B partner of the pair search)
+    bool inStep = false;            // inside bcs_step: the fold of the parked pair forces rides in the wall apply / cell pass
     bool fuseSteps = false;         // bcs_step(n): end of step k + springs / row count of step k + 1 in one pass (cellpass.cu)
     bool gridBuilt = false;
     cudaGraphExec_t graphExec = nullptr;
@@ -243,6 +244,14 @@ void fill_phys(const HostScene& hs, PhysDev& p)
     p.backZ = hs.gmin[2] + s.grid_xz_margin / 2;
     p.useBloodFlow = hs.useBloodFlow; p.reactionForce = hs.reactionForce; p.bigBrake = hs.bigBrake;
     p.nEndings = (int)hs.endR.size();
+}
+
+// the parked pair forces (pairs.cu) are folded by the passes that read the forces next instead of by a pass of their own
+bool defer_fold(const bcs_sim* s)
+{
+    if (!s->rows.enabled || !s->inStep || s->collideWalk) return false;
+    const char* e = getenv("BCS_DEFER_FOLD");
+    return e ? atoi(e) != 0 : s->slab != nullptr;
 }
 
 // ---- stage launchers ------------------------------------------------------------------------------------
@@ -416,6 +425,7 @@ VeinCollideArgs vein_collide_args(bcs_sim* s)
     a.stats = s->stats; a.apply = true; a.dbgTri = nullptr; a.dbgT = nullptr;
     a.wall = s->wall;
     if (s->exhaustiveVein) a.wall.enabled = 0;
+    if (defer_fold(s)) a.pairAcc = s->pairs.acc;
     if (s->slab) {
         a.pflag = s->slab->pflag;
         a.groupLocal = s->slab->groupLocal; a.triCellLocal = s->slab->triCellLocal; a.lists = slab_lists(s->slab, s->types);
@@ -450,6 +460,9 @@ CollideArgs collide_args(bcs_sim* s)
     a.dbgCount = nullptr; a.dbgSum = nullptr; a.dbgHits = nullptr;
     a.nDev = s->slab ? s->slab->nActive : nullptr;
     a.rowsMode = s->rows.enabled != 0; a.fullWalk = s->collideWalk;
+    // deferred fold: in slab mode (the stand-alone fold sweeps all N particles of the global scene); on one GPU the fold
+    // kernel measured cheaper than the extra loads in the cell pass.  BCS_DEFER_FOLD=1 / 0 overrides.
+    a.deferFold = defer_fold(s);
     a.rowStart = s->rows.rowStart; a.rowsGrid = s->rows; a.nRows = s->rows.nRows; a.ids = s->ids[1]; a.vel = s->vel;
     a.irregular = s->rows.irregular ? s->rows.irregular + 1 : nullptr;   // latched copy (row_order_kernel)
     a.pairs = s->pairs;
@@ -464,6 +477,7 @@ IntegrateArgs integrate_args(bcs_sim* s)
     a.mx = s->mx; a.my = s->my; a.mz = s->mz; a.endC = s->endC; a.endR = s->endR;
     a.counters = s->counters; a.seed = s->seed;
     if (s->slab) { a.slab = s->slab->dev; a.lists = slab_lists(s->slab, s->types); a.moveTo = s->slab->moveTo; }
+    if (defer_fold(s)) a.pairAcc = s->pairs.acc;
     return a;
 }
 
@@ -534,9 +548,16 @@ SpringArgs spring_args(bcs_sim* s, bool withProbe)
     return a;
 }
 
+struct StepScope {   // marks "inside bcs_step" for the argument builders (deferred fold of the parked pair forces)
+    bcs_sim* s;
+    explicit StepScope(bcs_sim* sim) : s(sim) { s->inStep = true; }
+    ~StepScope() { s->inStep = false; }
+};
+
 void enqueue_step(bcs_sim* s)
 {
     if (s->slab && !s->slab->primed) slab_prime(s->slab, slab_ctx(s));
+    StepScope scope(s);
     cudaStream_t m = s->stream;
     const bool fork = s->overlap && !s->ctx.timing && s->side[0];
     if (!fork) {
@@ -630,6 +651,7 @@ void enqueue_head(bcs_sim* s)
 
 void enqueue_body(bcs_sim* s, bool last)
 {
+    StepScope scope(s);
     cudaStream_t m = s->stream;
     const bool fork = s->overlap && !s->ctx.timing && s->side[0];
     VeinCollideArgs va = vein_collide_args(s);

@@ -29,6 +29,7 @@
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
 #include "kernels.cuh"
+#include "pair_device.cuh"
 #include "rows_device.cuh"
 
 #include <algorithm>
@@ -276,10 +277,42 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 l2_prefetch(gpos + q0, b2); l2_prefetch(gvel + q0, b2); l2_prefetch(a.s.frc + q0, b2);
             }
         }
+        // deferred fold (pairs.cu): pair forces of the collision pass still parked in fixed point are added to the force
+        // before anything reads it.  Their loads are issued here, in memory order (coalesced), so that they fly together
+        // with the tile copies; the (few) non-zero sums are folded once the tiles have landed.
+        long long ax[CP_MAX_ROUNDS], ay[CP_MAX_ROUNDS], az[CP_MAX_ROUNDS];
+        if (INTEGRATE && a.g.pairAcc) {
+#pragma unroll
+            for (int r = 0; r < CP_MAX_ROUNDS; ++r) {
+                const int e = lane + 32 * r;
+                ax[r] = 0; ay[r] = 0; az[r] = 0;
+                if (e < nPart) {
+                    int c, k;
+                    split(e, c, k);
+                    const long long* acc = a.g.pairAcc + 3 * (size_t)particle_of(e, c, k);
+                    ax[r] = acc[0]; ay[r] = acc[1]; az[r] = acc[2];
+                }
+            }
+        }
         TICK(0);   // group set-up + issue
         cp_async_wait_all();
         __syncwarp();
         TICK(1);   // waiting for the tiles
+        if (INTEGRATE && a.g.pairAcc) {
+#pragma unroll
+            for (int r = 0; r < CP_MAX_ROUNDS; ++r) {
+                if ((ax[r] | ay[r] | az[r]) != 0) {
+                    const int e = lane + 32 * r;
+                    int c, k;
+                    split(e, c, k);
+                    float4& F = tf[k * stride + c];
+                    F.x += fx_value(ax[r]); F.y += fx_value(ay[r]); F.z += fx_value(az[r]);
+                    long long* acc = a.g.pairAcc + 3 * (size_t)particle_of(e, c, k);
+                    acc[0] = 0; acc[1] = 0; acc[2] = 0;
+                }
+            }
+            __syncwarp();
+        }
 
         // ---- end of the previous step: integration, vein end, respawn (blood_cells.cu:155-179, vein_end.cu:57-138)
         if (INTEGRATE) {
@@ -437,7 +470,10 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                     if (isNear) a.s.probe.list[b + __popc(m & ((1u << lane) - 1u))] = gidx;
                 }
             }
-            if (INTEGRATE && on) { gpos[gidx] = p4; gvel[gidx] = tv[ti]; }
+            if (INTEGRATE && on) {
+                gpos[gidx] = p4; gvel[gidx] = tv[ti];
+                if (!SPRINGS && a.g.pairAcc) a.s.frc[gidx] = tf[ti];   // the folded force (the spring stage writes it otherwise)
+            }
         }
         __syncwarp();   // the tiles are free for the next group's copies
         TICK(5);   // environment + count + write back

@@ -184,6 +184,7 @@ struct CollideArgs {
     // row-directory mode (pairs.cu): symmetric pair search over the sorted keys + per-slot hit lists
     bool rowsMode;
     bool fullWalk;              // BCS_COLLIDE=walk: every slot scans its whole stencil (the fallback path) instead
+    bool deferFold;             // the sums stay parked in PairLists::acc: the wall apply and the cell pass fold them (bcs_step)
     const int* rowStart;
     RowsGrid rowsGrid;          // the directory's geometry (row of a cell id: rows_of_key, rows_device.cuh)
     int nRows;
@@ -291,6 +292,7 @@ struct VeinCollideArgs {
     int liveTris;               // 1: triangles are gathered from the live vertices (tris is not refreshed per step)
     WallGridDev wall;           // wall.enabled: production path (clean semantics)
     const unsigned char* pflag; // slab mode: per-particle flags (bit 0 owned, bit 1 ghost); null otherwise
+    long long* pairAcc;         // deferred fold (pairs.cu): fixed-point pair forces still parked per particle; null = already folded
     int nCells;                 // blood cells
     int maxP;                   // largest particles-per-cell over the types
     CullEntry* cullList;        // [nCells] blood cells that may touch the wall this step
@@ -333,6 +335,7 @@ struct IntegrateArgs {
     SlabDev slab;
     OwnedLists lists;                 // owned blood cells
     signed char* moveTo;              // [B] out: rank the blood cell migrates to after this step, -1 = stays
+    long long* pairAcc;               // deferred fold (pairs.cu): parked pair forces are added to frc before it is used; null = none
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter

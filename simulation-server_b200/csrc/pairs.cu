@@ -187,60 +187,9 @@ __global__ void __launch_bounds__(PS_THREADS) pair_search_kernel(const CollideAr
     }
 }
 
-// one thread per touching pair: both contributions, added to the ends' fixed-point accumulators
-__global__ void __launch_bounds__(256) pair_force_kernel(const CollideArgs a)
+template <bool DEBUG, bool STATS>
+__device__ __forceinline__ void walk_slots(const CollideArgs& a)
 {
-    const PairLists& L = a.pairs;
-    if (L.ctl[CTL_OVERFLOW] != 0 || *a.irregular != 0) return;   // pair_walk did the stage
-    const int count = min(L.ctl[CTL_COUNT], L.cap);
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
-        const int2 pr = L.pairs[t];
-        const int ti = a.ids[pr.x], tj = a.ids[pr.y];
-        const float4 pi = a.spos[pr.x], pj = a.spos[pr.y];
-        const float3 vi = xyz(a.vel[ti & 0x7fffffff]), vj = xyz(a.vel[tj & 0x7fffffff]);
-        if (ti >= 0) {   // ghosts are partners only (forces go to owned particles, particle_collisions.cuh:36)
-            const float3 c = pair_contribution(a.phys, xyz(pi), vi, pi.w, pj, vj);
-            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)ti;
-            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
-        }
-        if (tj >= 0) {
-            const float3 c = pair_contribution(a.phys, xyz(pj), vj, pj.w, pi, vi);
-            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)tj;
-            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
-        }
-    }
-}
-
-// one thread per particle, in particle order (coalesced): non-zero sums are folded into the float force and cleared; the
-// last CTA to leave rewinds the pair list for the next search
-__global__ void __launch_bounds__(256) pair_fold_kernel(const CollideArgs a, int nParticles)
-{
-    const PairLists& L = a.pairs;
-    for (int pid = blockIdx.x * blockDim.x + threadIdx.x; pid < nParticles; pid += gridDim.x * blockDim.x) {
-        long long* acc = L.acc + 3 * (size_t)pid;
-        const long long sx = acc[0], sy = acc[1], sz = acc[2];
-        if ((sx | sy | sz) == 0) continue;   // a sum of exactly zero adds nothing
-        float4 f = a.frc[pid];
-        f.x += fx_value(sx); f.y += fx_value(sy); f.z += fx_value(sz);
-        acc[0] = 0; acc[1] = 0; acc[2] = 0;
-        a.frc[pid] = f;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(&L.ctl[CTL_DONE], 1) == (int)gridDim.x - 1) {
-            L.ctl[CTL_COUNT] = 0; L.ctl[CTL_OVERFLOW] = 0; L.ctl[CTL_DONE] = 0;
-        }
-    }
-}
-
-// Every slot scans its WHOLE stencil through the row directory (the per-slot walk of collide.cu without the compact cell
-// index): the fallback for builds with particles outside the grid or an overflowing pair list, the A/B partner of the
-// symmetric search (BCS_COLLIDE=walk), and - windows being plain linear cell ranges [c0, c0 + nb) exactly as
-// particle_collisions.cuh:53-83 forms them - correct for any key, clamped ones included.
-template <bool DEBUG, bool ALWAYS, bool STATS>
-__global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs a)
-{
-    if (!ALWAYS && !(*a.irregular != 0 || a.pairs.ctl[CTL_OVERFLOW] != 0)) return;
     const GridDev& g = a.grid;
     const int n = a.nDev ? *a.nDev : a.n;
     const int plane = g.nx * g.ny;
@@ -315,18 +264,85 @@ __global__ void __launch_bounds__(PS_THREADS) pair_walk_kernel(const CollideArgs
     }
 }
 
+
+template <bool DEBUG, bool STATS>
+__global__ void __launch_bounds__(256) pair_walk_kernel(const CollideArgs a)
+{
+    walk_slots<DEBUG, STATS>(a);
+}
+// debug view of a build the symmetric search steps aside for
+__global__ void __launch_bounds__(256) pair_walk_debug_kernel(const CollideArgs a)
+{
+    if (*a.irregular != 0) walk_slots<true, false>(a);
+}
+
+// one thread per touching pair: both contributions, added to the ends' fixed-point accumulators
+template <bool STATS>
+__global__ void __launch_bounds__(256) pair_force_kernel(const CollideArgs a)
+{
+    const PairLists& L = a.pairs;
+    const bool fallback = L.ctl[CTL_OVERFLOW] != 0 || *a.irregular != 0;
+    const int count = fallback ? 0 : min(L.ctl[CTL_COUNT], L.cap);
+    // a build with particles outside the grid, or one whose pair list overflowed: every slot walks its whole stencil
+    if (fallback) walk_slots<false, STATS>(a);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const int2 pr = L.pairs[t];
+        const int ti = a.ids[pr.x], tj = a.ids[pr.y];
+        const float4 pi = a.spos[pr.x], pj = a.spos[pr.y];
+        const float3 vi = xyz(a.vel[ti & 0x7fffffff]), vj = xyz(a.vel[tj & 0x7fffffff]);
+        if (ti >= 0) {   // ghosts are partners only (forces go to owned particles, particle_collisions.cuh:36)
+            const float3 c = pair_contribution(a.phys, xyz(pi), vi, pi.w, pj, vj);
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)ti;
+            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
+        }
+        if (tj >= 0) {
+            const float3 c = pair_contribution(a.phys, xyz(pj), vj, pj.w, pi, vi);
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(L.acc) + 3 * (size_t)tj;
+            atomicAdd(acc, (unsigned long long)fx_of(c.x)); atomicAdd(acc + 1, (unsigned long long)fx_of(c.y)); atomicAdd(acc + 2, (unsigned long long)fx_of(c.z));
+        }
+    }
+    // the last CTA to leave rewinds the pair list for the next search
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&L.ctl[CTL_DONE], 1) == (int)gridDim.x - 1) {
+            L.ctl[CTL_COUNT] = 0; L.ctl[CTL_OVERFLOW] = 0; L.ctl[CTL_DONE] = 0;
+        }
+    }
+}
+
+// one thread per particle, in particle order (coalesced): non-zero sums are folded into the float force and cleared.
+// Staged entry points only: inside bcs_step the fold rides in the passes that read the forces next (wall apply, cell pass)
+__global__ void __launch_bounds__(256) pair_fold_kernel(const CollideArgs a, int nParticles)
+{
+    const PairLists& L = a.pairs;
+    for (int pid = blockIdx.x * blockDim.x + threadIdx.x; pid < nParticles; pid += gridDim.x * blockDim.x) {
+        long long* acc = L.acc + 3 * (size_t)pid;
+        const long long sx = acc[0], sy = acc[1], sz = acc[2];
+        if ((sx | sy | sz) == 0) continue;   // a sum of exactly zero adds nothing
+        float4 f = a.frc[pid];
+        f.x += fx_value(sx); f.y += fx_value(sy); f.z += fx_value(sz);
+        acc[0] = 0; acc[1] = 0; acc[2] = 0;
+        a.frc[pid] = f;
+    }
+}
+
+// Every slot scans its WHOLE stencil through the row directory (the per-slot walk of collide.cu without the compact cell
+// index): the fallback for builds with particles outside the grid or an overflowing pair list, the A/B partner of the
+// symmetric search (BCS_COLLIDE=walk), and - windows being plain linear cell ranges [c0, c0 + nb) exactly as
+// particle_collisions.cuh:53-83 forms them - correct for any key, clamped ones included.
 }  // namespace
 
 void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st)
 {
     const int threads = PS_THREADS, allBlocks = (a.n + threads - 1) / threads;
     const int blocks = a.nDev ? std::min(allBlocks, 2 * BOUNDED_BLOCKS) : allBlocks;
-    const int walkBlocks = std::min(allBlocks, BOUNDED_BLOCKS);   // normally idle (returns at once): half a wave is enough
+    const int walkBlocks = std::max(1, std::min((a.n + 255) / 256, BOUNDED_BLOCKS));
     const bool dbg = a.dbgCount != nullptr, slab = a.nDev != nullptr;
+    const int foldBlocks = std::min((a.n + 255) / 256, 2 * BOUNDED_BLOCKS);
     if (a.fullWalk) {
-        if (dbg) BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<true, true, false><<<walkBlocks, threads, 0, st>>>(a));
-        else if (a.stats) BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<false, true, true><<<walkBlocks, threads, 0, st>>>(a));
-        else BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<false, true, false><<<walkBlocks, threads, 0, st>>>(a));
+        if (dbg) BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<true, false><<<walkBlocks, 256, 0, st>>>(a));
+        else if (a.stats) BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<false, true><<<walkBlocks, 256, 0, st>>>(a));
+        else BCS_LAUNCH("particle_collisions", st, pair_walk_kernel<false, false><<<walkBlocks, 256, 0, st>>>(a));
         BCS_CUDA(cudaGetLastError());
         return;
     }
@@ -338,13 +354,14 @@ void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st)
     using F = std::false_type;
     if (dbg) {
         // candidate counts / checksums / touching pairs per particle (test instrumentation): both ends of a pair are
-        // credited with integer atomics by the same search the production path runs
+        // credited with integer atomics by the same search the production path runs; a build with particles outside the
+        // grid takes the per-slot walk instead (the search steps aside)
         BCS_CUDA(cudaMemsetAsync(a.dbgCount, 0, (size_t)a.n * sizeof(int), st));
         BCS_CUDA(cudaMemsetAsync(a.dbgSum, 0, (size_t)a.n * sizeof(unsigned long long), st));
         BCS_CUDA(cudaMemsetAsync(a.dbgHits, 0, (size_t)a.n * sizeof(int), st));
         if (slab) search(T{}, T{}, F{});
         else search(T{}, F{}, F{});
-        BCS_LAUNCH("pair_walk", st, pair_walk_kernel<true, false, false><<<walkBlocks, threads, 0, st>>>(a));
+        BCS_LAUNCH("pair_walk", st, pair_walk_debug_kernel<<<walkBlocks, 256, 0, st>>>(a));
         BCS_CUDA(cudaGetLastError());
         return;
     }
@@ -355,12 +372,12 @@ void launch_particle_collisions_rows(const CollideArgs& a, cudaStream_t st)
         if (a.stats) search(F{}, F{}, T{});
         else search(F{}, F{}, F{});
     }
-    if (a.stats) BCS_LAUNCH("pair_walk", st, pair_walk_kernel<false, false, true><<<walkBlocks, threads, 0, st>>>(a));
-    else BCS_LAUNCH("pair_walk", st, pair_walk_kernel<false, false, false><<<walkBlocks, threads, 0, st>>>(a));
-    // sized for a few touching pairs per ten particles; both stride over the device-side pair count
+    // sized for a few touching pairs per ten particles; strides over the device-side pair count (or, in the fall-back,
+    // over the sorted slots)
     const int pairBlocks = std::max(1, std::min((a.n / 4 + 255) / 256, BOUNDED_BLOCKS));
-    BCS_LAUNCH("pair_force", st, pair_force_kernel<<<pairBlocks, 256, 0, st>>>(a));
-    BCS_LAUNCH("pair_fold", st, pair_fold_kernel<<<std::min((a.n + 255) / 256, 2 * BOUNDED_BLOCKS), 256, 0, st>>>(a, a.n));
+    if (a.stats) BCS_LAUNCH("pair_force", st, pair_force_kernel<true><<<pairBlocks, 256, 0, st>>>(a));
+    else BCS_LAUNCH("pair_force", st, pair_force_kernel<false><<<pairBlocks, 256, 0, st>>>(a));
+    if (!a.deferFold) BCS_LAUNCH("pair_fold", st, pair_fold_kernel<<<foldBlocks, 256, 0, st>>>(a, a.n));
     BCS_CUDA(cudaGetLastError());
 }
 

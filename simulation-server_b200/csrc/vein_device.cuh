@@ -3,6 +3,7 @@
 #pragma once
 #include "bcs_internal.cuh"
 #include "device_math.cuh"
+#include "pair_device.cuh"
 #include "kernels.cuh"
 
 namespace bcs {
@@ -240,7 +241,17 @@ __device__ __forceinline__ void vein_apply_hit(const VeinCollideArgs& a, int pid
     const float d2 = length_squared(rel);
     if (a.apply && hit && d2 <= ph.impact2) {
         if (!splatOnly && d2 > ph.minForce2) {
-            const float4 F4 = a.frc[pid];
+            float4 F4 = a.frc[pid];
+            if (a.pairAcc) {
+                // the collision pass parked this particle's pair forces in fixed point (pairs.cu, deferred fold): fold them
+                // before the reaction force reads the accumulated force, exactly as the stand-alone fold pass would have
+                long long* acc = a.pairAcc + 3 * (size_t)pid;
+                const long long sx = acc[0], sy = acc[1], sz = acc[2];
+                if ((sx | sy | sz) != 0) {
+                    F4.x += fx_value(sx); F4.y += fx_value(sy); F4.z += fx_value(sz);
+                    acc[0] = 0; acc[1] = 0; acc[2] = 0;
+                }
+            }
             const float3 F = xyz(F4);
             float3 add;
             if (ph.reactionForce) {

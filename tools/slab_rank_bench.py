@@ -1,0 +1,19 @@
+"""One rank of an N-rank slab decomposition alone on one GPU (BCS_SLAB_NO_COMM=1: no NCCL, no halos): graph-replayed
+ms/step of that rank's work.  usage: slab_rank_bench.py <rank> <world> [particles] [steps]"""
+import importlib, sys, os
+os.environ["BCS_SLAB_NO_COMM"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+capi = importlib.import_module("simulation-server_b200.capi"); wl = importlib.import_module("simulation-server_b200.workloads")
+dd = importlib.import_module("simulation-server_b200.distributed")
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
+steps = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+sc, st, info = wl.long_vein(n)
+planes = dd.slab_boundaries(sc, st, world)
+sim = dd.create_slab_sim(sc, st, rank, world, 0, bytes(128), planes)
+sim.step(10); sim.synchronize()
+stream = torch.cuda.ExternalStream(sim.device_view().stream, device=0)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream); sim.step(steps); e1.record(stream); sim.synchronize()
+print(f"rank {rank}/{world} of {n}: {e0.elapsed_time(e1) / steps * 1e3:.1f} us/step (no communication)  {sim.slab_counts()}")
