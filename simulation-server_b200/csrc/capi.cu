@@ -67,7 +67,13 @@ template <class T>
 static T* dev_upload(const std::vector<T>& v)
 {
     T* p = dev_alloc<T>(v.size(), false);
-    if (!v.empty()) BCS_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) {
+        // A cudaMemcpy from PAGEABLE host memory returns once the source has been staged; the DMA into device memory may
+        // still be in flight on the legacy stream, which the handle's non-blocking stream does not wait for.  Drain it:
+        // a kernel launched right after must see the whole table.
+        BCS_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     return p;
 }
 
@@ -370,6 +376,7 @@ void setup_wall(bcs_sim* s)
     w.cellBox = s->track(dev_alloc<Aabb>(s->tg.cells));
     BCS_CUDA(cudaMemcpy(w.groupBox, inv.data(), (size_t)((T + 7) / 8) * sizeof(Aabb), cudaMemcpyHostToDevice));
     BCS_CUDA(cudaMemcpy(w.cellBox, inv.data(), (size_t)s->tg.cells * sizeof(Aabb), cudaMemcpyHostToDevice));
+    BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // pageable source: see dev_upload
     w.dirty = s->track(dev_alloc<int>(1));
     w.overflow = s->track(dev_alloc<int>(1));
     w.barrier = s->track(dev_alloc<unsigned>(2));
@@ -943,6 +950,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
         s->doneBlocks = s->track(dev_alloc<unsigned>(1));
         s->typesDev = s->track(dev_alloc<TypesDev>(1));
         BCS_CUDA(cudaMemcpy(s->typesDev, &s->types, sizeof(TypesDev), cudaMemcpyHostToDevice));
+        BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
         for (const HostType& h : hs.types) s->maxP = std::max(s->maxP, h.P);
         s->vidx = s->track(dev_upload(hs.vidx));
         s->nbrIds = s->track(dev_upload(hs.nbrIds)); s->nbrLen = s->track(dev_upload(hs.nbrLen));
@@ -966,6 +974,11 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
             BCS_CUDA(cudaMemcpy(sx, hs.vx.data(), V * sizeof(float), cudaMemcpyHostToDevice));
             BCS_CUDA(cudaMemcpy(sy, hs.vy.data(), V * sizeof(float), cudaMemcpyHostToDevice));
             BCS_CUDA(cudaMemcpy(sz, hs.vz.data(), V * sizeof(float), cudaMemcpyHostToDevice));
+            // The copies come from pageable memory: cudaMemcpy returns when the source is staged, the last chunk may still be
+            // on its way (legacy stream), and pack_kernel below runs on the handle's NON-BLOCKING stream.  Without this drain
+            // the tail of the z array was occasionally packed as zeros (seen at 301 300 vertices: everything past the first
+            // 1 MiB of floats) - a vein whose end lies flat in the z = 0 plane.
+            BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
             pack_kernel<<<(V + 255) / 256, 256, 0, s->stream>>>(sx, sy, sz, s->vpos, V, s->types, s->collR, 0);
             launch_tri_centers(vein_args(s), s->tcent, s->stream);
             build_triangle_grid(s);

@@ -412,6 +412,7 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
             s->triCellLocal = salloc<unsigned char>(s, tg.cells);
             BCS_CUDA(cudaMemcpy(s->groupLocal, gl.data(), nGroups, cudaMemcpyHostToDevice));
             BCS_CUDA(cudaMemcpy(s->triCellLocal, cl.data(), tg.cells, cudaMemcpyHostToDevice));
+            BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // pageable sources: the DMA may outlive the call (capi.cu: dev_upload)
         }
 
         // message buffers

@@ -122,4 +122,9 @@ def test_bench_scene_step_is_bitwise_repeatable_1m(bcs_lib):
             out.append([refcheck.down(sim, w) for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS)])
     for name, x, y in zip(("pos", "vel", "frc", "vein pos"), *out):
         bad = np.nonzero((x != y).any(axis=1))[0]
+        if len(bad):
+            import os
+            d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+            os.makedirs(d, exist_ok=True)
+            np.savez_compressed(os.path.join(d, "repeat_fail.npz"), **{f"{n}_{k}": a for k, run in enumerate(out) for n, a in zip(("pos", "vel", "frc", "vpos"), run)})
         assert len(bad) == 0, f"{name}: {len(bad)} rows differ between two runs of the same state, first {bad[:8]}, max |d| {np.abs(x[bad] - y[bad]).max():.3e}"
