@@ -122,6 +122,7 @@ def algorithmic_bytes(kernel: str, N: int, B: int, V: int, T: int, c_occ: int, h
         "advance": 80 * N + 12 * B,
         "vein_gather": 120 * V,
         "springs": 48 * N + 12 * B,                # R pos,vel,frc 36N, W frc 12N, W centres 12B
+        "springs_count": 56 * N + 12 * B,          # head of a fused run: springs + the row count of the first grid build (W (key, place) 8N)
         "particle_collisions": 56 * N + 8 * c_occ,
         "tri_refit": 96 * T,                       # R 3 idx + 3 vertices (48), W packed triangle (48)
         "cell_box": 48 * T,                        # R packed triangles
@@ -390,6 +391,28 @@ def run_product(args):
 
     rows = int(sim.layout.grid_dims[1]) * int(sim.layout.grid_dims[2]) if "row_scatter" in prof else 0
 
+    # In a fused run the spring stage lives inside `advance`; the contract figure for the spring kernel ALONE comes from its
+    # staged entry point (bcs_run_stage), one launch per event pair, with a 256 MB fill between launches so that the 48 MB
+    # it reads are not L2 hits left by the previous launch.
+    prof_step = prof
+    if world == 1 and "springs" not in prof:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        reps, pairs = 12, []
+        with torch.cuda.stream(stream):
+            for r in range(reps):
+                flush.fill_(r)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sim.run_stage(capi.STAGE_SPRINGS)
+                e1.record(stream)
+                pairs.append((e0, e1))
+        sim.synchronize()
+        torch.cuda.synchronize()
+        t = [a.elapsed_time(b) for a, b in pairs[2:]]
+        prof = dict(prof)
+        prof["springs"] = (float(sum(t)), len(t))
+        del flush
+
     def roof(name):
         per_launch_ms = prof[name][0] / prof[name][1]
         b = algorithmic_bytes(name, N_alg, B_alg, V, T, c_occ, hits, rows)
@@ -411,7 +434,7 @@ def run_product(args):
     if "advance" in prof:
         roofline["contract_kernels"]["advance"] = roof("advance")
         roofline["contract_kernels"]["advance"]["stages_replaced_bytes"] = 140 * N_alg + 12 * B_alg
-    step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits, rows) * v[1] / prof_steps for k, v in prof.items())
+    step_bytes = sum(algorithmic_bytes(k, N_alg, B_alg, V, T, c_occ, hits, rows) * v[1] / prof_steps for k, v in prof_step.items())
     roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
@@ -467,9 +490,9 @@ def run_product(args):
         "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": reference_cuda_baseline(info["workload"]), "parity": parity,
         "kernels": kernels,
     }
-    sim.close()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)   # before the teardown: a line is never lost to a close that does not return
+    sim.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

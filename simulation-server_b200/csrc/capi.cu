@@ -531,7 +531,7 @@ SlabCtx slab_ctx(bcs_sim* s)
 {
     SlabCtx c{};
     c.types = s->types; c.N = s->hs.N; c.B = s->hs.B; c.V = s->hs.V; c.T = s->hs.T;
-    c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel;
+    c.pos = s->pos; c.vel = s->vel; c.frc = s->frc; c.vpos = s->vpos; c.vvel = s->vvel; c.centers = s->centers;
     c.plan = s->plan;
     c.maxP = s->maxP;
     c.typesDev = s->typesDev;
@@ -653,6 +653,13 @@ void enqueue_step(bcs_sim* s)
 // with the same results, bit for bit, as n unfused steps (test_fused_run_equals_single_steps).
 void enqueue_head(bcs_sim* s)
 {
+    if (s->slab) {
+        // slab mode: springs over the owned blood cells, row count over owned + ghost particles (once per run; inside the
+        // run the ghosts are counted as they are unpacked, slab.cu)
+        launch_springs(spring_args(s), s->stream);
+        launch_row_count(particle_grid_args(s), s->stream);
+        return;
+    }
     launch_springs_count(spring_args(s), s->pg, s->rows, s->counters, s->stream);
 }
 
@@ -714,10 +721,19 @@ void enqueue_body(bcs_sim* s, bool last)
         BCS_CUDA(cudaStreamWaitEvent(sVein, s->evMasked, 0));
     }
     launch_vein_integrate(vein_args(s), sVein);
+    IntegrateArgs ia = integrate_args(s);
+    if (s->slab) ia.tail = slab_tail(s->slab);   // ghost expiry + the particle part of the pack ride on the cell pass
+    if (ia.tail.ghostList) slab_pack_vertices(s->slab, slab_ctx(s), sVein);
     if (fork) BCS_CUDA(cudaEventRecord(s->evVein, sVein));
-    if (last) launch_finish_step(integrate_args(s), spring_args(s), s->doneBlocks, m);
-    else launch_advance(integrate_args(s), spring_args(s), s->pg, s->rows, s->doneBlocks, m);
+    if (last) launch_finish_step(ia, spring_args(s), s->doneBlocks, m);
+    else launch_advance(ia, spring_args(s), s->pg, s->rows, s->doneBlocks, m);
     if (fork) BCS_CUDA(cudaStreamWaitEvent(m, s->evVein, 0));
+    if (s->slab) {
+        // migration + halo exchange for the next step; inside a run the arrivals are counted into its row directory
+        SlabCount cnt{};
+        if (!last) { cnt.enabled = 1; cnt.grid = s->pg; cnt.rows = s->rows; cnt.counters = s->counters; }
+        slab_end_of_step(s->slab, slab_ctx(s), ia.tail.ghostList != nullptr, &cnt);
+    }
 }
 
 cudaGraphExec_t capture_body(bcs_sim* s, bool last, unsigned long long* kernels)
@@ -794,15 +810,16 @@ void destroy(bcs_sim* s)
         for (int k = 0; k < 7; ++k) fprintf(stderr, "  %s %.1f%%", names[k], tot ? 100.0 * (double)c[k] / (double)tot : 0.0);
         fprintf(stderr, "\n");
     }
+    // graphs first: ncclCommDestroy (slab_destroy) waits for every graph that holds captured NCCL operations to be gone
     if (s->graphExec) cudaGraphExecDestroy(s->graphExec);
+    if (s->graphMid) cudaGraphExecDestroy(s->graphMid);
+    if (s->graphLast) cudaGraphExecDestroy(s->graphLast);
     slab_destroy(s->slab);
     for (void* p : s->owned) cudaFree(p);
     s->sortP.release();
     s->sortT.release();
     for (cudaStream_t q : s->side) if (q) cudaStreamDestroy(q);
     for (cudaEvent_t e : {s->evFork, s->evSprings, s->evWall, s->evGather, s->evMasked, s->evVein, s->evRebuilt, s->evGrid}) if (e) cudaEventDestroy(e);
-    if (s->graphMid) cudaGraphExecDestroy(s->graphMid);
-    if (s->graphLast) cudaGraphExecDestroy(s->graphLast);
     if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -993,7 +1010,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
                 BCS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         }
         // fused run (bcs_step(n), n > 1): needs the row-directory grid (its count pass rides in the cell pass); single GPU
-        s->fuseSteps = s->rows.enabled && !slabOpts && !getenv("BCS_NO_FUSE");
+        s->fuseSteps = s->rows.enabled && !getenv("BCS_NO_FUSE") && !(slabOpts && getenv("BCS_SLAB_NO_FUSE"));
         if (slabOpts) {
             BCS_REQUIRE(slabOpts->struct_size == sizeof(bcs_slab_opts), BCS_ERR_INVALID, "bcs_slab_opts.struct_size mismatch");
             BCS_REQUIRE(s->semantics == BCS_SEM_CLEAN, BCS_ERR_UNSUPPORTED, "slab decomposition needs clean semantics");

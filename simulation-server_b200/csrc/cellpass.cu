@@ -31,6 +31,7 @@
 #include "kernels.cuh"
 #include "pair_device.cuh"
 #include "rows_device.cuh"
+#include "slab.cuh"
 
 #include <algorithm>
 #include <cstdint>
@@ -219,6 +220,15 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
     unsigned long long step = 0;
     if (INTEGRATE) step = *reinterpret_cast<const volatile unsigned long long*>(&a.g.counters->step);
 
+    if (INTEGRATE && LISTS && a.g.tail.ghostList) {
+        // slab mode: last step's ghosts lose their flag (the collision and wall stages of this step are through with them)
+        const int ng = *reinterpret_cast<const volatile int*>(a.g.tail.ghostCount);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ng; k += gridDim.x * blockDim.x) {
+            const int pid = a.g.tail.ghostList[k];
+            if (!(a.g.tail.pflag[pid] & 1)) a.g.tail.pflag[pid] = 0;
+        }
+    }
+
     const int nTypes = types->n;
     const int totalGroups = LISTS ? lists.blockStart[nTypes] : plan.totalBlocks;
     const int nw = gridDim.x * plan.warps;
@@ -315,6 +325,8 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
         }
 
         // ---- end of the previous step: integration, vein end, respawn (blood_cells.cu:155-179, vein_end.cu:57-138)
+        unsigned leaving = 0u;   // slab mode: blood cells of the group that change owner after this step
+        int target = -1;         // ... and where to (lanes 0 .. G-1: the group's cells)
         if (INTEGRATE) {
             const PhysDev& pg = a.g.phys;
             bool out = false;
@@ -367,17 +379,20 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 }
             }
             __syncwarp();
-            if (a.g.slab.enabled && slot0 == 0 && cell < nCells) {
+            if (a.g.slab.enabled) {
                 // ownership follows the blood cell's centre: which slab does it lie in after this step?
-                float cy = 0.f;
-                for (int k = 0; k < P; ++k) cy += tp[k * stride + cell].y;
-                cy /= (float)P;
-                int target = -1;
-                if (flag) target = a.g.slab.spawnRank;                               // respawned at the top of the vein
-                else if (cy >= a.g.slab.yHi && a.g.slab.rank > 0) target = a.g.slab.rank - 1;
-                else if (cy < a.g.slab.yLo && a.g.slab.rank < a.g.slab.world - 1) target = a.g.slab.rank + 1;
-                if (target == a.g.slab.rank) target = -1;
-                a.g.moveTo[cell_id(cell)] = (signed char)target;
+                if (slot0 == 0 && cell < nCells) {
+                    float cy = 0.f;
+                    for (int k = 0; k < P; ++k) cy += tp[k * stride + cell].y;
+                    cy /= (float)P;
+                    if (flag) target = a.g.slab.spawnRank;                               // respawned at the top of the vein
+                    else if (cy >= a.g.slab.yHi && a.g.slab.rank > 0) target = a.g.slab.rank - 1;
+                    else if (cy < a.g.slab.yLo && a.g.slab.rank < a.g.slab.world - 1) target = a.g.slab.rank + 1;
+                    if (target == a.g.slab.rank) target = -1;
+                    a.g.moveTo[cell_id(cell)] = (signed char)target;
+                }
+                // bit c: blood cell c of the group leaves this rank (slot 0's lanes are lanes 0 .. G-1 = the cells)
+                leaving = __ballot_sync(0xffffffffu, target >= 0);
             }
         }
         TICK(2);   // integration
@@ -436,8 +451,12 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
             const int gidx = on ? particle_of(e, c, k) : 0;
             float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (on) p4 = tp[ti];
-            if (COUNT && on) rows_count_particle(a.grid, a.rows, p4, gidx, 1, a.g.counters);
+            // (a blood cell that leaves the rank is counted where it arrives - and here by the pack kernel, slab.cu, if it
+            // stays around as a ghost - its springs are still this pass's job: the new owner receives the finished force)
+            if (COUNT && on && !((leaving >> c) & 1u)) rows_count_particle(a.grid, a.rows, p4, gidx, 1, a.g.counters);
             bool isNear = false;
+            float3 fOut = f3(0.f, 0.f, 0.f);   // the force the particle ends the pass with (slab mode: travels with a leaving cell)
+            if (INTEGRATE && !SPRINGS && on) fOut = xyz(tf[ti]);
             if (SPRINGS && on) {
                 const float4 v4 = tv[ti], f4 = tf[ti];
                 const float3 position = xyz(p4), velocity = xyz(v4), initialForce = xyz(f4);
@@ -451,6 +470,7 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 newForce = newForce + env;
                 const float3 out = (initialForce + newForce) / 2.0f;
                 a.s.frc[gidx] = make_float4(out.x, out.y, out.z, 0.f);
+                fOut = out;
                 if (a.s.probe.near) {
                     // near-wall probe (NearProbe, kernels.cuh): same cell arithmetic as the wall filter (wall.cu: wall_axis)
                     const NearProbe& probe = a.s.probe;
@@ -474,6 +494,61 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
                 gpos[gidx] = p4; gvel[gidx] = tv[ti];
                 if (!SPRINGS && a.g.pairAcc) a.s.frc[gidx] = tf[ti];   // the folded force (the spring stage writes it otherwise)
             }
+            if (INTEGRATE && LISTS) {
+                if (a.g.tail.ghostList) {
+                    // ---- slab mode: pack for the exchange that follows the step (SlabTail, kernels.cuh)
+                    const SlabTail& tl = a.g.tail;
+                    const SlabDev& sl = a.g.slab;
+                    const int tgt = __shfl_sync(0xffffffffu, target, c);
+                    const bool leave = on && tgt >= 0;
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on) v4 = tv[ti];
+#pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        // stays: mirrored on the neighbour whose slab it is close to (warp-aggregated append)
+                        const bool nearFace = on && !leave && (d == 0 ? (sl.rank > 0 && p4.y >= sl.yHi - sl.haloWidth)
+                                                                      : (sl.rank < sl.world - 1 && p4.y < sl.yLo + sl.haloWidth));
+                        const unsigned m = __ballot_sync(0xffffffffu, nearFace);
+                        if (m) {
+                            const int leader = __ffs(m) - 1;
+                            int b = 0;
+                            if (lane == leader) b = atomicAdd(&tl.sendHdr[d][1], __popc(m));
+                            b = __shfl_sync(0xffffffffu, b, leader);
+                            if (nearFace) {
+                                const int kq = b + __popc(m & ((1u << lane) - 1u));
+                                if (kq < tl.capHalo) {
+                                    HaloRecord r;
+                                    r.id = gidx; r.px = p4.x; r.py = p4.y; r.pz = p4.z; r.vx = v4.x; r.vy = v4.y; r.vz = v4.z; r.pad = 0.f;
+                                    reinterpret_cast<HaloRecord*>(tl.halo[d])[kq] = r;
+                                } else {
+                                    atomicExch(tl.errorFlag, 1);
+                                }
+                            }
+                        }
+                    }
+                    if (leave) {
+                        // the blood cell leaves: full state (finished force, centre) goes to its new owner
+                        const int d = tgt == sl.rank - 1 ? 0 : tgt == sl.rank + 1 ? 1 : 2;
+                        const int kq = atomicAdd(&tl.sendHdr[d][0], 1);
+                        if (kq < tl.capMig) {
+                            const float4 ctr = SPRINGS ? sc[c] : a.s.centers[cell_id(c)];
+                            MigRecord r;
+                            r.id = gidx; r.px = p4.x; r.py = p4.y; r.pz = p4.z; r.vx = v4.x; r.vy = v4.y; r.vz = v4.z;
+                            r.fx = fOut.x; r.fy = fOut.y; r.fz = fOut.z; r.cx = ctr.x; r.cy = ctr.y; r.cz = ctr.z;
+                            reinterpret_cast<MigRecord*>(tl.mig[d])[kq] = r;
+                        } else {
+                            atomicExch(tl.errorFlag, 1);
+                        }
+                        // on this side its particles stay around as ghosts for the next step if they are near the face they
+                        // crossed (a respawned cell goes to the top of the vein, far from any face of this slab)
+                        const bool keep = (d == 0 && p4.y >= sl.yHi - sl.haloWidth && p4.y < sl.yHi + sl.haloWidth) ||
+                                          (d == 1 && p4.y < sl.yLo + sl.haloWidth && p4.y >= sl.yLo - sl.haloWidth);
+                        if (keep) tl.keepList[atomicAdd(tl.keepCount, 1)] = gidx;   // flagged + counted by the unpack kernel
+                        else tl.pflag[gidx] = 0;
+                        if (k == 0) tl.ownedCell[cell_id(c)] = 0;
+                    }
+                }
+            }
         }
         __syncwarp();   // the tiles are free for the next group's copies
         TICK(5);   // environment + count + write back
@@ -488,6 +563,8 @@ __global__ void __launch_bounds__(128, MB) cell_pass_kernel(const CellPassArgs a
             if (atomicAdd(a.doneBlocks, 1u + (unsigned)(step >> 63)) == gridDim.x - 1) {
                 *a.doneBlocks = 0;
                 a.g.counters->step = step + 1;
+                // slab mode: every CTA has walked its share of the old ghost list - rewind it for the unpack kernel
+                if (LISTS && a.g.tail.ghostList) *a.g.tail.ghostCount = 0;
             }
         }
     }
@@ -541,7 +618,7 @@ void launch_springs_count(const SpringArgs& s, const GridDev& grid, const RowsGr
     CellPassArgs a{};
     a.s = s; a.grid = grid; a.rows = rows;
     a.g.counters = counters;
-    launch_variant<false, true, true>(a, "springs", st);
+    launch_variant<false, true, true>(a, "springs_count", st);
 }
 
 void launch_finish_step(const IntegrateArgs& g, const SpringArgs& s, unsigned* doneBlocks, cudaStream_t st)

@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_kernel(const unsigned* _
     const bool last = (n > 0) ? (base <= n - 1 && n - 1 < base + SCAN_ITEMS) : (blockIdx.x == 0 && tid == 0);
     if (last) {
         if (total) *total = run;
-        if (MODE == 1) out[n] = finalValueDev ? *finalValueDev : finalValue;   // occStart[numOcc] = number of sorted slots
+        if (MODE == 1) out[n] = total ? run : (finalValueDev ? *finalValueDev : finalValue);   // occStart[numOcc] = number of sorted slots (= the grand total when that is asked for)
     }
     (void)sBase;
 }
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) cs_scan_fused_kernel(const unsig
         const bool last = (n > 0) ? (base <= n - 1 && n - 1 < base + SCAN_ITEMS) : (tile == 0 && tid == 0);
         if (last) {
             if (total) *total = run;
-            if (MODE == 1) out[n] = finalValueDev ? *finalValueDev : finalValue;   // occStart[numOcc] = number of sorted slots
+            if (MODE == 1) out[n] = total ? run : (finalValueDev ? *finalValueDev : finalValue);   // occStart[numOcc] = number of sorted slots (= the grand total when that is asked for)
         }
     }
     // the last block to leave prepares the next launch
@@ -1130,15 +1130,17 @@ static void launch_grid_build_rows(const GridBuildArgs& a, cudaStream_t st)
     SortScratch* sc = a.scratch;
     if (!R.countDone) launch_row_count(a, st);
     // rowStart = exclusive scan of the per-row counts; rowStart[nRows] = number of sorted slots
+    // (slab mode, count fused into the previous step: nobody has counted the active particles - the scan's total is it)
+    int* const total = (R.countDone && a.nDevOut) ? a.nDevOut : nullptr;
     const int tiles = (R.nRows + SCAN_TILE - 1) / SCAN_TILE;
     ScanCtl* ctl = reinterpret_cast<ScanCtl*>(sc->scanCtl);
     if (sc->twoPassScan) {
         BCS_LAUNCH("row_start_totals", st, cs_tile_totals_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals));
         BCS_LAUNCH("row_start_scan", st,
-                   cs_scan_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals, R.rowStart + 1, nullptr, n, a.nDev));
+                   cs_scan_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanTotals, R.rowStart + 1, total, n, a.nDev));
     } else {
         BCS_LAUNCH("row_start_scan", st,
-                   cs_scan_fused_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanStatus, ctl, R.rowStart + 1, nullptr, n, a.nDev));
+                   cs_scan_fused_kernel<1><<<tiles, SCAN_THREADS, 0, st>>>(R.rowCount, R.nRows, nullptr, sc->scanStatus, ctl, R.rowStart + 1, total, n, a.nDev));
     }
     BCS_LAUNCH("row_scatter", st, row_scatter_kernel<<<itemBlocks, 256, 0, st>>>(a.pflag, n, R, a.items));
     if (a.probe && a.probe->near)

@@ -316,6 +316,28 @@ void launch_wall_slot_info(const int* sortedTriKeys, const int* triIds, const un
                            cudaStream_t st);
 
 // ---- integrate.cu --------------------------------------------------------------------------------------
+// Slab mode, fused run: the end-of-step chores of the halo exchange ride on the cell pass that ends the step (cellpass.cu)
+// instead of launches of their own:
+//   * on its way in, every CTA walks a share of last step's ghost list and clears the flags (the collision and wall stages
+//     are through with them); the last CTA to leave rewinds the ghost count;
+//   * the write-back sweep appends a halo record for every particle near a slab face and, for a blood cell that changes
+//     owner, its migration records (finished force, centre) to the send buffers (formats: slab.cuh) - the state is in
+//     registers there anyway, the stand-alone pack kernel re-read 32 B per owned particle.
+// Particles of a leaving cell that stay around as ghosts go to keepList; the unpack kernel flags and counts them.
+struct SlabTail {
+    const int* ghostList;   // null = not used
+    int* ghostCount;
+    unsigned char* pflag;
+    unsigned char* ownedCell;
+    int* sendHdr[3];        // SlabHeader of the up / down / spawn-rank message: {nMig, nHalo, nVerts, ...}
+    char* mig[3];           // MigRecord regions of the three messages
+    char* halo[2];          // HaloRecord regions of the two neighbour messages
+    int capMig, capHalo;
+    int* keepList;
+    int* keepCount;
+    int* errorFlag;         // sticky: a message overflowed
+};
+
 struct IntegrateArgs {
     TypesDev types;
     PhysDev phys;
@@ -336,6 +358,7 @@ struct IntegrateArgs {
     OwnedLists lists;                 // owned blood cells
     signed char* moveTo;              // [B] out: rank the blood cell migrates to after this step, -1 = stays
     long long* pairAcc;               // deferred fold (pairs.cu): parked pair forces are added to frc before it is used; null = none
+    SlabTail tail;                    // slab mode, fused run
 };
 void launch_integrate_particles(const IntegrateArgs& a, cudaStream_t st);
 void launch_vein_end(const IntegrateArgs& a, cudaStream_t st);   // also advances the device step counter

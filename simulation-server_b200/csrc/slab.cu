@@ -20,6 +20,8 @@
 // single-GPU run restricted to the rank's active particles.
 #include <nccl.h>
 
+#include "rows_device.cuh"
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -78,35 +80,53 @@ __global__ void __launch_bounds__(256) slab_init_vertices_kernel(int V, SlabDev 
 }
 
 // ---- owned-cell lists (rebuilt every step after the exchange) ---------------------------------------------------
-__global__ void __launch_bounds__(256) slab_list_cells_kernel(const TypesDev* __restrict__ types, int nCells, const unsigned char* __restrict__ ownedCell,
-                                                             int* __restrict__ cells, int* __restrict__ count)
+constexpr int LIST_THREADS = 512;
+__global__ void __launch_bounds__(LIST_THREADS) slab_list_cells_kernel(const TypesDev* __restrict__ types, int nCells, const unsigned char* __restrict__ ownedCell,
+                                                                      int* __restrict__ cells, int* __restrict__ count, SpringPlan plan,
+                                                                      int* __restrict__ blockStart, int* __restrict__ cellPrefix, unsigned* __restrict__ done,
+                                                                      SlabBuffers buf, int* __restrict__ keepCount, int nv0, int nv1)
 {
+    __shared__ int sCount[BCS_MAX_TYPES], sBase[BCS_MAX_TYPES];
+    if (threadIdx.x < BCS_MAX_TYPES) sCount[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // this step's messages have been sent and unpacked: rewind the send headers and the keep list for the next pack
+        for (int d = 0; d < 3; ++d) { buf.send[d]->nMig = 0; buf.send[d]->nHalo = 0; buf.send[d]->nVerts = d == 0 ? nv0 : d == 1 ? nv1 : 0; }
+        *keepCount = 0;
+    }
+    __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool own = c < nCells && ownedCell[c];
     int t = 0;
     while (own && t + 1 < types->n && c >= types->t[t + 1].cStart) ++t;
-    // warp-aggregated append: one atomic per (warp, type) instead of one per blood cell
+    // append, aggregated twice: one shared-memory atomic per (warp, type), one global atomic per (CTA, type)
     const unsigned active = __ballot_sync(0xffffffffu, own);
+    int local = 0;
     if (own) {
         const unsigned peers = __match_any_sync(active, t);
         const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
         int base = 0;
-        if (lane == leader) base = atomicAdd(&count[t], __popc(peers));
+        if (lane == leader) base = atomicAdd(&sCount[t], __popc(peers));
         base = __shfl_sync(peers, base, leader);
-        cells[types->t[t].cStart + base + __popc(peers & ((1u << lane) - 1u))] = c;   // type t's segment starts at cStart_t
+        local = base + __popc(peers & ((1u << lane) - 1u));
     }
-}
-
-__global__ void slab_list_prefix_kernel(int nTypes, SpringPlan plan, const int* __restrict__ count, int* __restrict__ blockStart,
-                                        int* __restrict__ cellPrefix)
-{
-    int b = 0, c = 0;
-    for (int t = 0; t < nTypes; ++t) {
-        blockStart[t] = b; cellPrefix[t] = c;
-        b += (count[t] + plan.cellsPerBlock[t] - 1) / plan.cellsPerBlock[t];
-        c += count[t];
+    __syncthreads();
+    if (threadIdx.x < BCS_MAX_TYPES && sCount[threadIdx.x]) sBase[threadIdx.x] = atomicAdd(&count[threadIdx.x], sCount[threadIdx.x]);
+    __syncthreads();
+    if (own) cells[types->t[t].cStart + sBase[t] + local] = c;   // type t's segment starts at cStart_t
+    // the last CTA to arrive turns the per-type counts into the prefixes the cell-group kernels index by
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        const int nTypes = types->n;
+        int bsum = 0, k = 0;
+        for (int ty = 0; ty < nTypes; ++ty) {
+            const int cnt = atomicAdd(&count[ty], 0);   // the other CTAs' atomics, read where they were performed
+            blockStart[ty] = bsum; cellPrefix[ty] = k;
+            bsum += (cnt + plan.cellsPerBlock[ty] - 1) / plan.cellsPerBlock[ty];
+            k += cnt;
+        }
+        blockStart[nTypes] = bsum; cellPrefix[nTypes] = k;
     }
-    blockStart[nTypes] = b; cellPrefix[nTypes] = c;
 }
 
 // ---- pack ---------------------------------------------------------------------------------------------------
@@ -118,11 +138,37 @@ __device__ __forceinline__ int dest_of(const SlabDev& s, int target)
     return 2;
 }
 
+struct VertexPack {          // the vertex part of the pack: static lists -> the vertex regions of the two neighbour messages
+    const int* list[2];
+    int count[2];
+    VertexRecord* out[2];
+    const float4 *vpos, *vvel;
+};
+
+__device__ __forceinline__ void pack_vertices(const VertexPack& vp, int first, int stride)
+{
+    // vein vertices of the static halo lists (owned vertices near a face), both directions
+    for (int k = first; k < vp.count[0] + vp.count[1]; k += stride) {
+        const int d = k >= vp.count[0] ? 1 : 0, kk = d ? k - vp.count[0] : k;
+        const int v = vp.list[d][kk];
+        const float4 p = vp.vpos[v], w = vp.vvel[v];
+        VertexRecord r;
+        r.id = v; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = w.x; r.vy = w.y; r.vz = w.z; r.pad = 0.f;
+        vp.out[d][kk] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) slab_pack_vertices_kernel(const VertexPack vp)
+{
+    pack_vertices(vp, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
 __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restrict__ types, int n, SlabDev slab, const float4* __restrict__ pos,
                                                        const float4* __restrict__ vel, const float4* __restrict__ frc,
                                                        unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                        const signed char* __restrict__ moveTo, SlabBuffers buf, int* __restrict__ ghostList,
-                                                       int* __restrict__ ghostCount, int* __restrict__ errorFlag, const ActiveItems items)
+                                                       int* __restrict__ ghostCount, int* __restrict__ errorFlag, const ActiveItems items,
+                                                       const float4* __restrict__ centers, const SlabCount cnt, const VertexPack vp)
 {
     // bounded grid striding over the rank's owned items (or, before the lists exist, over all particles)
     const int total = items.cells ? items.cellPrefix[types->n] * items.maxP : n;
@@ -153,6 +199,8 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
                 r.id = i; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = v.x; r.vy = v.y; r.vz = v.z;
                 const float4 F = frc[i];
                 r.fx = F.x; r.fy = F.y; r.fz = F.z;
+                const float4 ctr = centers[c];
+                r.cx = ctr.x; r.cy = ctr.y; r.cz = ctr.z;
                 buf.mig[d][k] = r;
             } else {
                 atomicExch(errorFlag, 1);
@@ -162,7 +210,10 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
             const bool keep = (d == 0 && p.y >= slab.yHi - slab.haloWidth && p.y < slab.yHi + slab.haloWidth) ||
                               (d == 1 && p.y < slab.yLo + slab.haloWidth && p.y >= slab.yLo - slab.haloWidth);
             pflag[i] = keep ? 2 : 0;
-            if (keep) ghostList[atomicAdd(ghostCount, 1)] = i;
+            if (keep) {
+                ghostList[atomicAdd(ghostCount, 1)] = i;
+                if (cnt.enabled) rows_count_particle(cnt.grid, cnt.rows, p, i, 2, cnt.counters);
+            }
             if (i == types->t[t].pStart + (c - types->t[t].cStart) * types->t[t].P) ownedCell[c] = 0;
             continue;
         }
@@ -181,6 +232,7 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const TypesDev* __restri
             }
         }
     }
+    pack_vertices(vp, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // last step's ghosts lose their flag, then (same single CTA, after a barrier) the send headers and the ghost count are
@@ -197,24 +249,6 @@ __global__ void __launch_bounds__(1024) slab_expire_reset_kernel(const int* __re
     if (threadIdx.x < 3) { buf.send[threadIdx.x]->nMig = 0; buf.send[threadIdx.x]->nHalo = 0; buf.send[threadIdx.x]->nVerts = 0; }
     __syncthreads();
     if (threadIdx.x == 0) { *ghostCount = 0; buf.send[0]->nVerts = nv0; buf.send[1]->nVerts = nv1; }
-}
-
-// vein vertices of the static halo lists (owned vertices near a face)
-__global__ void __launch_bounds__(256) slab_pack_vertices_kernel(const int* __restrict__ list0, int count0, VertexRecord* __restrict__ out0,
-                                                                const int* __restrict__ list1, int count1, VertexRecord* __restrict__ out1,
-                                                                const float4* __restrict__ vpos, const float4* __restrict__ vvel)
-{
-    // blockIdx.y = direction (up / down neighbour)
-    const int* list = blockIdx.y ? list1 : list0;
-    const int count = blockIdx.y ? count1 : count0;
-    VertexRecord* out = blockIdx.y ? out1 : out0;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    const int v = list[k];
-    const float4 p = vpos[v], w = vvel[v];
-    VertexRecord r;
-    r.id = v; r.px = p.x; r.py = p.y; r.pz = p.z; r.vx = w.x; r.vy = w.y; r.vz = w.z; r.pad = 0.f;
-    out[k] = r;
 }
 
 __global__ void slab_reset_headers_kernel(SlabBuffers buf, int* ghostCount, int nv0, int nv1)
@@ -237,8 +271,22 @@ __global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __rest
                                                          float4* __restrict__ frc, float4* __restrict__ vpos, float4* __restrict__ vvel,
                                                          unsigned char* __restrict__ ownedCell, unsigned char* __restrict__ pflag,
                                                          int* __restrict__ ghostList, int* __restrict__ ghostCount,
-                                                         const float4* __restrict__ wallBuilt, float wallMargin, int* __restrict__ wallDirty)
+                                                         const float4* __restrict__ wallBuilt, float wallMargin, int* __restrict__ wallDirty,
+                                                         float4* __restrict__ centers, const SlabCount cnt, int* __restrict__ listCount,
+                                                         const int* __restrict__ keepList, const int* __restrict__ keepCount)
 {
+    // the owned-cell lists are rebuilt by the next kernel: its per-type counters start from zero
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < BCS_MAX_TYPES) listCount[threadIdx.x] = 0;
+    if (blockIdx.y == 0) {
+        // particles of the blood cells that just left and stay around as ghosts (packed by the cell pass, SlabTail)
+        const int nk = *keepCount;
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
+            const int pid = keepList[k];
+            pflag[pid] = 2;
+            ghostList[atomicAdd(ghostCount, 1)] = pid;
+            if (cnt.enabled) rows_count_particle(cnt.grid, cnt.rows, pos[pid], pid, 2, cnt.counters);
+        }
+    }
     const char* raw = src.raw[blockIdx.y];
     const bool full = src.full[blockIdx.y] != 0;
     const SlabHeader* hdr = (const SlabHeader*)raw;
@@ -252,17 +300,23 @@ __global__ void __launch_bounds__(256) slab_unpack_kernel(const TypesDev* __rest
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         if (k < nMig) {
             const MigRecord r = mig[k];
-            pos[r.id] = make_float4(r.px, r.py, r.pz, pos[r.id].w);   // .w = collision radius, static per particle
+            const float4 p = make_float4(r.px, r.py, r.pz, pos[r.id].w);   // .w = collision radius, static per particle
+            pos[r.id] = p;
             vel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
             frc[r.id] = make_float4(r.fx, r.fy, r.fz, 0.f);
             pflag[r.id] = 1;
-            ownedCell[cell_of_particle(types, r.id)] = 1;
+            const int c = cell_of_particle(types, r.id);
+            ownedCell[c] = 1;
+            centers[c] = make_float4(r.cx, r.cy, r.cz, 0.f);   // every particle of the cell carries the same value
+            if (cnt.enabled) rows_count_particle(cnt.grid, cnt.rows, p, r.id, 1, cnt.counters);
         } else if (k < nMig + nHalo) {
             const HaloRecord r = halo[k - nMig];
-            pos[r.id] = make_float4(r.px, r.py, r.pz, pos[r.id].w);
+            const float4 p = make_float4(r.px, r.py, r.pz, pos[r.id].w);
+            pos[r.id] = p;
             vel[r.id] = make_float4(r.vx, r.vy, r.vz, 0.f);
             pflag[r.id] = 2;
             ghostList[atomicAdd(ghostCount, 1)] = r.id;
+            if (cnt.enabled) rows_count_particle(cnt.grid, cnt.rows, p, r.id, 2, cnt.counters);
         } else {
             const VertexRecord r = verts[k - nMig - nHalo];
             vpos[r.id] = make_float4(r.px, r.py, r.pz, 0.f);
@@ -344,6 +398,9 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
         s->listCount = salloc<int>(s, BCS_MAX_TYPES);
         s->listBlockStart = salloc<int>(s, BCS_MAX_TYPES + 1);
         s->listCellPrefix = salloc<int>(s, BCS_MAX_TYPES + 1);
+        s->listDone = salloc<unsigned>(s, 1);
+        s->keepList = salloc<int>(s, ctx.N);
+        s->keepCount = salloc<int>(s, 1);
 
         // static vein decomposition from the rest positions: owned vertices, halo lists, triangles to refit
         std::vector<unsigned char> vOwned(ctx.V);
@@ -460,40 +517,69 @@ static VertexRecord* vertex_region(const SlabState* s, char* raw)
     return (VertexRecord*)(raw + sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord) + (size_t)s->capHalo * sizeof(HaloRecord));
 }
 
-static void unpack_all(SlabState* s, const SlabCtx& ctx, const UnpackSources& src)
+static void unpack_all(SlabState* s, const SlabCtx& ctx, const UnpackSources& src, const SlabCount& cnt)
 {
-    if (!src.n) return;
     BCS_LAUNCH("slab_unpack", ctx.stream,
                slab_unpack_kernel<<<dim3(32, src.n), 256, 0, ctx.stream>>>(ctx.typesDev, src, s->capVert, s->capMig, s->capHalo, ctx.pos, ctx.vel,
                                                                           ctx.frc, ctx.vpos, ctx.vvel, s->ownedCell, s->pflag, s->ghostList, s->ghostCount,
-                                                                          ctx.wallBuilt, ctx.wallMargin, ctx.wallDirty));
+                                                                          ctx.wallBuilt, ctx.wallMargin, ctx.wallDirty, ctx.centers, cnt, s->listCount,
+                                                                          s->keepList, s->keepCount));
 }
 
-void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
+SlabTail slab_tail(const SlabState* s)
+{
+    SlabTail t{};
+    if (!s->listsValid) return t;   // before the first exchange the pack kernel sweeps the flags itself
+    t.ghostList = s->ghostList; t.ghostCount = s->ghostCount; t.pflag = s->pflag; t.ownedCell = s->ownedCell;
+    for (int d = 0; d < 3; ++d) { t.sendHdr[d] = reinterpret_cast<int*>(s->buf.send[d]); t.mig[d] = reinterpret_cast<char*>(s->buf.mig[d]); }
+    for (int d = 0; d < 2; ++d) t.halo[d] = reinterpret_cast<char*>(s->buf.halo[d]);
+    t.capMig = s->capMig; t.capHalo = s->capHalo;
+    t.keepList = s->keepList; t.keepCount = s->keepCount; t.errorFlag = s->errorFlag;
+    return t;
+}
+
+static VertexPack vertex_pack(SlabState* s, const SlabCtx& ctx)
+{
+    VertexPack vp{};
+    for (int d = 0; d < 2; ++d) { vp.list[d] = s->vertList[d]; vp.count[d] = s->vertCount[d]; vp.out[d] = vertex_region(s, s->sendRaw[d]); }
+    vp.vpos = ctx.vpos; vp.vvel = ctx.vvel;
+    return vp;
+}
+
+// fused run: the particle part of the pack rides on the cell pass (SlabTail); the vertex part runs behind the vein integrator
+void slab_pack_vertices(SlabState* s, const SlabCtx& ctx, cudaStream_t st)
+{
+    const int nv = s->vertCount[0] + s->vertCount[1];
+    if (!nv) return;
+    BCS_LAUNCH("slab_pack_vertices", st, slab_pack_vertices_kernel<<<(nv + 255) / 256, 256, 0, st>>>(vertex_pack(s, ctx)));
+    BCS_CUDA(cudaGetLastError());
+}
+
+void slab_end_of_step(SlabState* s, const SlabCtx& ctx, bool packed, const SlabCount* count)
 {
     cudaStream_t st = ctx.stream;
-    ActiveItems items{};
-    if (s->listsValid) {
-        items.cells = s->listCells; items.cellPrefix = s->listCellPrefix; items.ghostList = s->ghostList; items.ghostCount = s->ghostCount;
-        items.types = ctx.typesDev; items.maxP = ctx.maxP;
-        BCS_LAUNCH("slab_expire_reset", st,
-                   slab_expire_reset_kernel<<<1, 1024, 0, st>>>(s->ghostList, s->ghostCount, s->pflag, s->buf, s->vertCount[0], s->vertCount[1]));
+    SlabCount cnt{};
+    if (count) cnt = *count;
+    if (!packed) {
+        ActiveItems items{};
+        if (s->listsValid) {
+            items.cells = s->listCells; items.cellPrefix = s->listCellPrefix; items.ghostList = s->ghostList; items.ghostCount = s->ghostCount;
+            items.types = ctx.typesDev; items.maxP = ctx.maxP;
+            BCS_LAUNCH("slab_expire_reset", st,
+                       slab_expire_reset_kernel<<<1, 1024, 0, st>>>(s->ghostList, s->ghostCount, s->pflag, s->buf, s->vertCount[0], s->vertCount[1]));
+        } else {
+            BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
+        }
+        const long long packItems = std::max<long long>(s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N, s->vertCount[0] + s->vertCount[1]);
+        BCS_LAUNCH("slab_pack", st,
+                   slab_pack_kernel<<<(int)std::max<long long>(1, std::min<long long>((packItems + 255) / 256, BOUNDED_BLOCKS)), 256, 0, st>>>(
+                       ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell, s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
+                       s->errorFlag, items, ctx.centers, cnt, vertex_pack(s, ctx)));
+        BCS_CUDA(cudaGetLastError());
     } else {
-        BCS_LAUNCH("slab_reset", st, slab_reset_headers_kernel<<<1, 32, 0, st>>>(s->buf, s->ghostCount, s->vertCount[0], s->vertCount[1]));
+        BCS_REQUIRE(s->listsValid, BCS_ERR_STATE, "internal: the cell pass cannot have packed before the first exchange");
     }
-    const long long packItems = s->listsValid ? (long long)ctx.B * ctx.maxP : ctx.N;
-    BCS_LAUNCH("slab_pack", st,
-               slab_pack_kernel<<<(int)std::min<long long>((packItems + 255) / 256, BOUNDED_BLOCKS), 256, 0, st>>>(ctx.typesDev, ctx.N, s->dev, ctx.pos, ctx.vel, ctx.frc, s->ownedCell,
-                                                                                 s->pflag, s->moveTo, s->buf, s->ghostList, s->ghostCount,
-                                                                                 s->errorFlag, items));
-    if (s->vertCount[0] || s->vertCount[1]) {
-        const int most = max(s->vertCount[0], s->vertCount[1]);
-        BCS_LAUNCH("slab_pack_vertices", st,
-                   slab_pack_vertices_kernel<<<dim3((most + 255) / 256, 2), 256, 0, st>>>(s->vertList[0], s->vertCount[0], vertex_region(s, s->sendRaw[0]),
-                                                                                        s->vertList[1], s->vertCount[1], vertex_region(s, s->sendRaw[1]),
-                                                                                        ctx.vpos, ctx.vvel));
-    }
-    BCS_CUDA(cudaGetLastError());
+    bool unpacked = false;
     if (s->dev.world > 1 && s->comm) {
         s->exchange(st);
         UnpackSources src{};
@@ -507,21 +593,25 @@ void slab_end_of_step(SlabState* s, const SlabCtx& ctx)
         if (s->dev.rank < s->dev.world - 1) add(s->recvRaw[1], true);
         for (char* raw : s->spawnRecvRaw)
             if (raw) add(raw, false);
-        unpack_all(s, ctx, src);
+        if (src.n) {
+            unpack_all(s, ctx, src, cnt);
+            unpacked = true;
+        }
     }
+    if (!unpacked) BCS_CUDA(cudaMemsetAsync(s->listCount, 0, BCS_MAX_TYPES * sizeof(int), st));   // (the unpack kernel clears them otherwise)
     slab_build_lists(s, ctx);
     s->listsValid = true;
     BCS_CUDA(cudaGetLastError());
 }
 
+// expects the per-type counters (listCount) zeroed; also rewinds the send headers for the next pack
 void slab_build_lists(SlabState* s, const SlabCtx& ctx)
 {
     cudaStream_t st = ctx.stream;
-    BCS_CUDA(cudaMemsetAsync(s->listCount, 0, BCS_MAX_TYPES * sizeof(int), st));
     BCS_LAUNCH("slab_list_cells", st,
-               slab_list_cells_kernel<<<(ctx.B + 255) / 256, 256, 0, st>>>(ctx.typesDev, ctx.B, s->ownedCell, s->listCells, s->listCount));
-    BCS_LAUNCH("slab_list_prefix", st,
-               slab_list_prefix_kernel<<<1, 1, 0, st>>>(ctx.types.n, ctx.plan, s->listCount, s->listBlockStart, s->listCellPrefix));
+               slab_list_cells_kernel<<<(ctx.B + LIST_THREADS - 1) / LIST_THREADS, LIST_THREADS, 0, st>>>(
+                   ctx.typesDev, ctx.B, s->ownedCell, s->listCells, s->listCount, ctx.plan, s->listBlockStart, s->listCellPrefix, s->listDone, s->buf,
+                   s->keepCount, s->vertCount[0], s->vertCount[1]));
     BCS_CUDA(cudaGetLastError());
 }
 

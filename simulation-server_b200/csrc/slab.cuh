@@ -11,9 +11,10 @@ struct SlabHeader {          // first 32 bytes of every message
     int nVerts;              // vein vertex records
     int pad[5];
 };
-struct MigRecord {           // 40 B: full state of one particle of a migrating blood cell
+struct MigRecord {           // 52 B: full state of one particle of a migrating blood cell (+ the cell's centre, an output array)
     int id;
     float px, py, pz, vx, vy, vz, fx, fy, fz;
+    float cx, cy, cz;
 };
 struct HaloRecord {          // 32 B
     int id;
@@ -28,10 +29,17 @@ struct SlabBuffers {         // device view of the three send buffers (up, down,
     int capMig, capHalo;
 };
 
+struct SlabCount {           // fused run (capi.cu: run_fused): particles that arrive or stay around as ghosts are counted into
+    int enabled;             // the row directory of the NEXT grid build as they are packed / unpacked (the cell pass that
+    GridDev grid;            // ended the step has counted the particles that stay owned)
+    RowsGrid rows;
+    Counters* counters;
+};
+
 struct SlabCtx {             // what the slab code needs from the simulation handle
     TypesDev types;
     int N, B, V, T;
-    float4 *pos, *vel, *frc, *vpos, *vvel;
+    float4 *pos, *vel, *frc, *vpos, *vvel, *centers;
     SpringPlan plan;         // cells per CTA of the cell-group kernels
     int maxP;                // largest particles-per-cell
     const TypesDev* typesDev;   // device copy of the type table
@@ -57,6 +65,8 @@ struct SlabState {
     signed char* moveTo = nullptr;
     int *ghostList = nullptr, *ghostCount = nullptr, *nActive = nullptr, *errorFlag = nullptr;
     int *listCells = nullptr, *listCount = nullptr, *listBlockStart = nullptr, *listCellPrefix = nullptr;   // owned-cell lists
+    unsigned* listDone = nullptr;   // CTA arrival counter of the list kernel (the last one writes the prefixes)
+    int *keepList = nullptr, *keepCount = nullptr;   // fused run: particles of cells that just left and stay around as ghosts
     char* sendRaw[3] = {nullptr, nullptr, nullptr};
     char* recvRaw[2] = {nullptr, nullptr};
     std::vector<char*> spawnRecvRaw;
@@ -78,7 +88,11 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
                        const int* dTriCellEnd, const SlabCtx& ctx);
 void slab_destroy(SlabState* s);
 void slab_prime(SlabState* s, const SlabCtx& ctx);          // ownership from the uploaded state + first halo exchange
-void slab_end_of_step(SlabState* s, const SlabCtx& ctx);    // pack -> exchange -> unpack
+// pack -> exchange -> unpack -> owned-cell lists.  packed: the cell pass that ended the step has expired the old ghosts and
+// packed the particle records (SlabTail, kernels.cuh) and slab_pack_vertices has run; count: see SlabCount
+void slab_end_of_step(SlabState* s, const SlabCtx& ctx, bool packed = false, const SlabCount* count = nullptr);
+SlabTail slab_tail(const SlabState* s);
+void slab_pack_vertices(SlabState* s, const SlabCtx& ctx, cudaStream_t st);
 OwnedLists slab_lists(const SlabState* s, const TypesDev& types);
 void slab_build_lists(SlabState* s, const SlabCtx& ctx);       // compacted owned blood cells for the cell-group kernels
 void slab_unique_id(char out[128]);

@@ -78,6 +78,8 @@ def main():
             print(msg, flush=True)
     if rank == 0:
         print("MGPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+        ref.close()
+    sim.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

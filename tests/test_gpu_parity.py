@@ -1,5 +1,7 @@
 """GPU (B200): parity of libbcs.so - called through its C ABI - with (a) dumps of the reference CUDA build
 (reference-compatible semantics) and (b) the CPU oracle (clean and reference-compatible semantics)."""
+import importlib
+
 import numpy as np
 import pytest
 
@@ -273,6 +275,32 @@ def test_fused_run_equals_single_steps(bcs_lib):
                 assert np.array_equal(refcheck.down(a, w), refcheck.down(b, w)), f"after a fused run of {block}: array {w} differs"
         assert a.step_count() == b.step_count() == 60
         assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_single_rank_slab_handle_equals_plain_handle(bcs_lib, monkeypatch, fuse):
+    """A slab-decomposition handle with world size 1 owns every blood cell: it runs the slab code paths (owned-cell lists,
+    row directory over a window of cell rows, deferred fold, the fused run with the end-of-step chores riding on the cell
+    pass) without a neighbour, and must reproduce the plain handle bit for bit - respawns at the vein end included."""
+    if not fuse:
+        monkeypatch.setenv("BCS_SLAB_NO_FUSE", "1")
+    dd = importlib.import_module("simulation-server_b200.distributed")
+    sc = small_cylinder_scene(120, 100, 120.0)
+    st = pkg.make_initial_state(sc, seed=5, xz_half_width=40.0, y_range=(-25.0, -95.0))
+    arrays = (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC, capi.VEIN_POS, capi.VEIN_VEL, capi.CELL_CENTERS)
+    with make_bcs(sc) as a:
+        b = dd.create_slab_sim(sc, st, 0, 1, 0, bytes(128), seed=1234)
+        try:
+            a.upload_state(st)
+            for block in (1, 2, 7, 30, 20):
+                a.step(block)
+                b.step(block)
+                for w in arrays:
+                    assert np.array_equal(refcheck.down(a, w), refcheck.down(b, w)), f"after a run of {block}: array {w} differs"
+            assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
+            assert b.slab_counts()["owned_cells"] == a.n_cells
+        finally:
+            b.close()
 
 
 def test_particles_outside_the_grid_take_the_full_walk(bcs_lib, oracle_lib, monkeypatch):

@@ -1,0 +1,21 @@
+#!/bin/bash
+# usage: gpu_r2_e.sh <ranks>   multi-GPU parity (bitwise vs one GPU) + strong / weak bench lines
+N=${1:-2}
+O=gpurun_out/r02e_$N; mkdir -p $O
+timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "single_rank_slab" > $O/test.log 2>&1; echo "slab test exit $?"; tail -3 $O/test.log
+run() { timeout $1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
+run 240 29511 tests/mgpu_check.py 40000 60 > $O/mgpu_40k.log 2>&1; echo "mgpu 40k exit $?"; grep -E "MGPU_CHECK|step 60" $O/mgpu_40k.log | cut -c1-400
+run 300 29512 tests/mgpu_check.py 1000000 40 > $O/mgpu_1m.log 2>&1; echo "mgpu 1M exit $?"; grep -E "MGPU_CHECK|step 40" $O/mgpu_1m.log | cut -c1-400
+run 400 29513 bench.py --gpus $N --steps 100 --warmup 10 > $O/bench_strong.json 2> $O/bench_strong.err; echo "bench strong exit $?"
+run 500 29514 bench.py --gpus $N --steps 100 --warmup 10 --scaling weak --no-parity > $O/bench_weak.json 2> $O/bench_weak.err; echo "bench weak exit $?"
+python - <<PY
+import json
+for f in ("bench_strong","bench_weak"):
+    try:
+        d=json.loads(open("$O/"+f+".json").read().strip().splitlines()[-1])
+        print(f, d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"], d.get("parity"))
+        print("   ", {k: round(v["ms_per_step"]*1e3,1) for k,v in d["kernels"].items()})
+    except Exception as e:
+        print(f, "failed", e)
+PY
+tail -5 $O/bench_strong.err $O/bench_weak.err

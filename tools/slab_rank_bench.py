@@ -17,3 +17,9 @@ stream = torch.cuda.ExternalStream(sim.device_view().stream, device=0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); sim.step(steps); e1.record(stream); sim.synchronize()
 print(f"rank {rank}/{world} of {n}: {e0.elapsed_time(e1) / steps * 1e3:.1f} us/step (no communication)  {sim.slab_counts()}")
+if os.environ.get("SLAB_PROFILE", "1") != "0":
+    prof = sim.profile_steps(5)
+    tot = sum(v[0] for v in prof.values())
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        print(f"   {k:24s} {v[0] / 5 * 1e3:8.1f} us/step  {v[1] / 5:4.1f} launches/step  {v[0] / tot * 100:5.1f}%")
+    print(f"   serialised sum {tot / 5 * 1e3:.1f} us/step, {sum(v[1] for v in prof.values()) / 5:.0f} launches/step")
