@@ -357,6 +357,16 @@ int bcs_create_slab(const bcs_scene* scene, const bcs_opts* opts, const bcs_slab
 /* owned[c] = 1 if this rank currently owns blood cell c (n_cells entries); state arrays downloaded from a rank are
  * only meaningful for the blood cells it owns. */
 int bcs_download_ownership(bcs_sim* sim, uint8_t* owned, int32_t n_cells);
+/* Owned-only transfers: bcs_upload / bcs_download for the particle arrays (positions, velocities, forces) that move only
+ * the particles of the blood cells this rank currently OWNS across the bus.  x, y, z are full-length arrays
+ * (n = n_particles) in the reference's layout (cudaVec3, utilities/cuda_vec3.cuh); entries of other ranks' blood cells
+ * are not read (upload) / not written (download), so N ranks working on the same host arrays fill them completely.
+ * Ownership does not change in an upload (the next step decides about migration from the new positions); after an
+ * upload of positions or velocities the next bcs_step first refreshes the neighbours' ghosts with one halo exchange -
+ * every rank of the decomposition must therefore make the same sequence of calls.  Synchronous (a pinned staging buffer
+ * inside the handle is reused).  On a handle without slab decomposition these are bcs_upload / bcs_download. */
+int bcs_upload_owned(bcs_sim* sim, int array, const float* x, const float* y, const float* z, int32_t n);
+int bcs_download_owned(bcs_sim* sim, int array, float* x, float* y, float* z, int32_t n);
 /* Number of active (owned + ghost) particles of the last grid build and of ghosts in the last exchange. */
 int bcs_slab_counts(bcs_sim* sim, int32_t* active_particles, int32_t* ghost_particles, int32_t* owned_cells);
 

@@ -258,6 +258,19 @@ class Sim:
         self._call("download", self._h, which, _fp(x), _fp(y), _fp(z), C.c_int32(n))
         return x, y, z
 
+    def upload_owned(self, which: int, x, y, z):
+        """Slab mode: only the particles of the blood cells this rank owns cross the bus (bcs_upload_owned)."""
+        x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
+        self._call("upload_owned", self._h, which, _fp(x), _fp(y), _fp(z), C.c_int32(x.size))
+
+    def download_owned(self, which: int, out=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Slab mode: fills only the entries of the blood cells this rank owns (bcs_download_owned); `out` = three
+        full-length float32 arrays to fill in place (other entries are left alone)."""
+        n = self._len(which)
+        x, y, z = out if out is not None else tuple(np.zeros(n, np.float32) for _ in range(3))
+        self._call("download_owned", self._h, which, _fp(x), _fp(y), _fp(z), C.c_int32(n))
+        return x, y, z
+
     def upload_state(self, st: Dict[str, np.ndarray]):
         self.upload(PARTICLE_POS, st["pos_x"], st["pos_y"], st["pos_z"])
         self.upload(PARTICLE_VEL, st["vel_x"], st["vel_y"], st["vel_z"])

@@ -1,4 +1,6 @@
-// Particle-particle collision / repulsion pass over the 27-cell neighbourhood.
+// Particle-particle collision / repulsion pass over the 27-cell neighbourhood - the paths that walk the per-cell index
+// (reference semantics; clean semantics on dense scenes).  Sparse scenes (the 1 M-particle bench workload) build the
+// row-directory grid instead and collide through the symmetric pair search of pairs.cu.
 //
 // Stands in for sim::calculateParticleCollisions<UniformGrid> (simulation/particle_collisions.cuh:104-269)
 // -> detectCollisionsInNeighborCells (:53-83) -> detectCollision (:26-38)
@@ -65,8 +67,8 @@ __device__ __forceinline__ void evaluate_deferred(const PhysDev& ph, const float
         if (k < df.n) pair_force(ph, p1, v1, r1, spos[df.j[k]], svel, df.j[k], acc);
 }
 
-// clean-semantics walk of one sorted slot through the compact cell index (global memory); see the tiled kernel below
-// for the production path
+// clean-semantics walk of one sorted slot through the compact cell index (global memory): the default of this file
+// (dense scenes, where the grid build is the compact cell index; sparse scenes take the row directory + pairs.cu)
 constexpr int WALK_THREADS = 128;
 template <bool DEBUG, bool STATS, bool FLAT>
 __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, const float3 p1, const float3 v1, const float r1, int cell, int x0,
@@ -173,7 +175,8 @@ __device__ __forceinline__ void clean_slot_walk(const CollideArgs& a, int slot, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Clean semantics, production path: the neighbour runs are STAGED IN SHARED MEMORY per tile of sorted slots.
+// Clean semantics, A/B alternative (BCS_COLLIDE=tiled; measured slower than the walk above on the bench scenes, kept
+// for comparison): the neighbour runs are STAGED IN SHARED MEMORY per tile of sorted slots.
 //
 // Cell ids are z-major (uniform_grid.cu:33-35), so a tile of 256 consecutive sorted slots covers a run of x-rows
 // (y,z) of one z-layer, and everything its particles can collide with lies in THREE contiguous slot windows - the

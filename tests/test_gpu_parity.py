@@ -299,6 +299,17 @@ def test_single_rank_slab_handle_equals_plain_handle(bcs_lib, monkeypatch, fuse)
                     assert np.array_equal(refcheck.down(a, w), refcheck.down(b, w)), f"after a run of {block}: array {w} differs"
             assert a.stats()["teleported_cells"] == b.stats()["teleported_cells"] > 0
             assert b.slab_counts()["owned_cells"] == a.n_cells
+            # owned-only transfers (bcs_upload_owned / bcs_download_owned): this rank owns everything, so they move everything;
+            # an upload of positions makes the next step refresh the halo first - with the same state the run must not change
+            for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC):
+                got = b.download_owned(w)
+                assert all(np.array_equal(g, f) for g, f in zip(got, b.download(w)))
+                b.upload_owned(w, *got)
+                a.upload(w, *got)
+            a.step(12)
+            b.step(12)
+            for w in arrays:
+                assert np.array_equal(refcheck.down(a, w), refcheck.down(b, w)), f"after owned-only transfers: array {w} differs"
         finally:
             b.close()
 
