@@ -444,16 +444,31 @@ def run_product(args):
     op = [ctypes.cast(v.data_ptr(), ctypes.POINTER(ctypes.c_float)) for v in out]
     n32 = ctypes.c_int32(N)
 
-    # N > 1: every rank moves only the particles of the blood cells it owns (bcs_upload_owned / bcs_download_owned); the
-    # host arrays are the full-length ones of the reference's layout on every rank
-    up, down = ("upload_owned", "download_owned") if world > 1 else ("upload", "download")
+    # N > 1: every rank moves only the particles of the blood cells it owns (bcs_upload_owned / bcs_download_owned) between
+    # the device and full-length host arrays in the reference's layout.  A blood cell that changes owner during the step
+    # reaches its new owner's host arrays through that rank's download, so the loop carries the whole particle state
+    # (positions, velocities, forces) both ways; at N = 1 the step's result read back is the positions.
+    arrays = {capi.PARTICLE_POS: (hp["pos_x"], hp["pos_y"], hp["pos_z"]), capi.PARTICLE_VEL: (hp["vel_x"], hp["vel_y"], hp["vel_z"]),
+              capi.PARTICLE_FRC: (hp["frc_x"], hp["frc_y"], hp["frc_z"])}
 
     def e2e_step():
-        sim._call(up, sim._h, capi.PARTICLE_POS, hp["pos_x"], hp["pos_y"], hp["pos_z"], n32)
-        sim._call(up, sim._h, capi.PARTICLE_VEL, hp["vel_x"], hp["vel_y"], hp["vel_z"], n32)
-        sim._call(up, sim._h, capi.PARTICLE_FRC, hp["frc_x"], hp["frc_y"], hp["frc_z"], n32)
+        if world > 1:
+            for w, (ax, ay, az) in arrays.items():
+                sim._call("upload_owned", sim._h, w, ax, ay, az, n32)
+            sim._call("step", sim._h, ctypes.c_int32(1))
+            for w, (ax, ay, az) in arrays.items():
+                sim._call("download_owned", sim._h, w, ax, ay, az, n32)
+            return
+        for w, (ax, ay, az) in arrays.items():
+            sim._call("upload", sim._h, w, ax, ay, az, n32)
         sim._call("step", sim._h, ctypes.c_int32(1))
-        sim._call(down, sim._h, capi.PARTICLE_POS, op[0], op[1], op[2], n32)
+        sim._call("download", sim._h, capi.PARTICLE_POS, op[0], op[1], op[2], n32)
+
+    if world > 1:
+        # the host arrays start as the CURRENT state of the blood cells this rank owns (an owned-only upload does not move
+        # ownership: what is uploaded has to be the state of the cells the rank holds)
+        for w, (ax, ay, az) in arrays.items():
+            sim._call("download_owned", sim._h, w, ax, ay, az, n32)
 
     e2e_steps = max(3, min(args.steps, 30))
     for _ in range(3):
@@ -467,13 +482,13 @@ def run_product(args):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     barrier()
     if world > 1:
-        # bytes over all ranks: 3 arrays x 12 B + the 4 B slot index per owned particle up; 12 B per owned particle + the
-        # ownership flags (1 B per blood cell) down
+        # bytes over all ranks: 3 arrays x 12 B + the 4 B slot index per owned particle up; 3 arrays x 12 B per owned particle +
+        # the ownership flags (1 B per blood cell and rank) down
         cnts = sim.slab_counts()
         own = torch.tensor([float(cnts["active_particles"] - cnts["ghost_particles"])], dtype=torch.float64, device="cuda")
         dist.all_reduce(own)
         owned_particles = int(own.item())
-        h2d, d2h = 40 * owned_particles, 12 * owned_particles + B * world
+        h2d, d2h = 40 * owned_particles, 36 * owned_particles + B * world
     else:
         h2d, d2h = 36 * N, 12 * N
     e2e = {"value": N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

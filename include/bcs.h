@@ -363,8 +363,10 @@ int bcs_download_ownership(bcs_sim* sim, uint8_t* owned, int32_t n_cells);
  * are not read (upload) / not written (download), so N ranks working on the same host arrays fill them completely.
  * Ownership does not change in an upload (the next step decides about migration from the new positions); after an
  * upload of positions or velocities the next bcs_step first refreshes the neighbours' ghosts with one halo exchange -
- * every rank of the decomposition must therefore make the same sequence of calls.  Synchronous (a pinned staging buffer
- * inside the handle is reused).  On a handle without slab decomposition these are bcs_upload / bcs_download. */
+ * every rank of the decomposition must therefore make the same sequence of calls.  With PINNED arrays (cudaHostAlloc /
+ * cudaHostRegister) the kernels read and write the host arrays in place over the bus, walking the rank's owned-cell
+ * lists, and the upload is asynchronous like bcs_upload; pageable arrays go through a host-side gather and a staging
+ * buffer (correct, several times slower).  On a handle without slab decomposition these are bcs_upload / bcs_download. */
 int bcs_upload_owned(bcs_sim* sim, int array, const float* x, const float* y, const float* z, int32_t n);
 int bcs_download_owned(bcs_sim* sim, int array, float* x, float* y, float* z, int32_t n);
 /* Number of active (owned + ghost) particles of the last grid build and of ghosts in the last exchange. */

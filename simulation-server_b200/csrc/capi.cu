@@ -125,6 +125,40 @@ __global__ void __launch_bounds__(256) unpack_owned_kernel(const float4* __restr
     const float4 v = in[idx[k]];
     x[k] = v.x; y[k] = v.y; z[k] = v.z;
 }
+// ... and, when the caller's arrays are pinned host memory, straight between them and the device arrays (zero copy over the
+// bus: the kernel walks the rank's owned-cell lists - the 20-odd particles of a blood cell are one contiguous 80-byte run
+// per component - so nothing is gathered on the host and no ownership table has to be read back first)
+__global__ void __launch_bounds__(256) upload_owned_direct_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                                                  const ActiveItems items, float4* __restrict__ out, const float* __restrict__ collR,
+                                                                  int setRadius)
+{
+    const TypesDev* types = items.types;
+    const int total = items.cellPrefix[types->n] * items.maxP;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        int fl = 0;
+        const int i = active_item(items, item, fl);
+        if (i < 0) continue;
+        float w = 0.f;
+        if (setRadius) {
+            int t = 0;
+            while (t + 1 < types->n && i >= types->t[t + 1].pStart) ++t;
+            w = collR[types->t[t].mStart + (i - types->t[t].pStart) % types->t[t].P];
+        }
+        out[i] = make_float4(x[i], y[i], z[i], w);
+    }
+}
+__global__ void __launch_bounds__(256) download_owned_direct_kernel(const float4* __restrict__ in, const ActiveItems items, float* __restrict__ x,
+                                                                    float* __restrict__ y, float* __restrict__ z)
+{
+    const int total = items.cellPrefix[items.types->n] * items.maxP;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+        int fl = 0;
+        const int i = active_item(items, item, fl);
+        if (i < 0) continue;
+        const float4 v = in[i];
+        x[i] = v.x; y[i] = v.y; z[i] = v.z;
+    }
+}
 // graphics/glcontroller.cu:23-50 equivalents: xyz into a strided float buffer (stride 6: interleaved with normals; 3: offsets)
 __global__ void __launch_bounds__(256) export_xyz_kernel(const float4* __restrict__ in, int n, float* __restrict__ out6, float* __restrict__ out3)
 {
@@ -1144,6 +1178,30 @@ static void refresh_halo_if_stale(bcs_sim* s)
     slab_end_of_step(s->slab, slab_ctx(s));
 }
 
+// device-visible aliases of three host arrays if all of them are pinned (cudaHostAlloc / cudaHostRegister) memory
+static bool pinned_aliases(const float* x, const float* y, const float* z, const float* out[3])
+{
+    const float* in[3] = {x, y, z};
+    for (int k = 0; k < 3; ++k) {
+        cudaPointerAttributes at{};
+        const bool ok = cudaPointerGetAttributes(&at, in[k]) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer;
+        cudaGetLastError();
+        if (!ok) return false;
+        out[k] = static_cast<const float*>(at.devicePointer);
+    }
+    return true;
+}
+
+static ActiveItems owned_items(bcs_sim* s)
+{
+    if (!s->slab->primed) slab_prime(s->slab, slab_ctx(s));
+    ActiveItems it{};
+    it.cells = s->slab->listCells; it.cellPrefix = s->slab->listCellPrefix;
+    it.ghostList = s->slab->ghostList; it.ghostCount = s->slab->ghostCount;
+    it.types = s->typesDev; it.maxP = s->maxP;
+    return it;
+}
+
 int bcs_upload_owned(bcs_sim* s, int which, const float* x, const float* y, const float* z, int32_t n)
 {
     if (s && !s->slab) return bcs_upload(s, which, x, y, z, n);
@@ -1154,6 +1212,17 @@ int bcs_upload_owned(bcs_sim* s, int which, const float* x, const float* y, cons
     BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
     CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
+    const float* dp[3];
+    if (pinned_aliases(x, y, z, dp)) {
+        // pinned arrays: as with bcs_upload the call is asynchronous - the arrays are read when the stream gets there
+        Array a = array_of(s, which);
+        const long long items = (long long)s->hs.B * s->maxP;
+        upload_owned_direct_kernel<<<(int)std::max<long long>(1, std::min<long long>((items + 255) / 256, BOUNDED_BLOCKS)), 256, 0, s->stream>>>(
+            dp[0], dp[1], dp[2], owned_items(s), a.ptr, s->collR, a.isParticlePos ? 1 : 0);
+        BCS_CUDA(cudaGetLastError());
+        if (which != BCS_PARTICLE_FRC) s->haloStale = true;
+        return BCS_OK;
+    }
     refresh_owned(s);
     const int m = s->nOwnedParticles;
     float* hx = s->hostStage; float* hy = hx + m; float* hz = hy + m;
@@ -1187,6 +1256,17 @@ int bcs_download_owned(bcs_sim* s, int which, float* x, float* y, float* z, int3
     BCS_REQUIRE(n == s->hs.N, BCS_ERR_INVALID, "array length mismatch");
     CtxScope scope(&s->ctx);
     BCS_CUDA(cudaSetDevice(s->device));
+    const float* dp[3];
+    if (pinned_aliases(x, y, z, dp)) {
+        Array a = array_of(s, which);
+        const long long items = (long long)s->hs.B * s->maxP;
+        download_owned_direct_kernel<<<(int)std::max<long long>(1, std::min<long long>((items + 255) / 256, BOUNDED_BLOCKS)), 256, 0, s->stream>>>(
+            a.ptr, owned_items(s), const_cast<float*>(dp[0]), const_cast<float*>(dp[1]), const_cast<float*>(dp[2]));
+        BCS_CUDA(cudaGetLastError());
+        BCS_CUDA(cudaStreamSynchronize(s->stream));
+        check_device_flags(s);
+        return BCS_OK;
+    }
     refresh_owned(s);
     const int m = s->nOwnedParticles;
     if (m) {

@@ -80,10 +80,16 @@ def main():
     # uploading it back (no change) makes the next step refresh the halos first, and the run must go on bit for bit
     parts = {w: np.stack(sim.download_owned(w), 1) for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC)}
     for w, arr in parts.items():
-        sim.upload_owned(w, arr[:, 0], arr[:, 1], arr[:, 2])
+        cols = [np.ascontiguousarray(arr[:, k]) for k in range(3)]
+        if w == capi.PARTICLE_VEL:   # one array through the pinned (zero-copy) path
+            cols = [torch.from_numpy(c).pin_memory().numpy() for c in cols]
+        sim.upload_owned(w, *cols)
+        sim.synchronize()   # a pinned upload is asynchronous: the arrays must outlive it
     sim.step(block)
     sim.synchronize()
-    after = np.stack(sim.download_owned(capi.PARTICLE_POS), 1)
+    # (this download through pinned arrays: the kernel writes the host memory in place, walking the owned-cell lists)
+    pinned = tuple(torch.zeros(sim.n_particles, dtype=torch.float32).pin_memory().numpy() for _ in range(3))
+    after = np.stack(sim.download_owned(capi.PARTICLE_POS, out=pinned), 1)
     gathered = [None] * world
     dist.all_gather_object(gathered, (parts, after))
     if rank == 0:

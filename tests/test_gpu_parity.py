@@ -301,10 +301,16 @@ def test_single_rank_slab_handle_equals_plain_handle(bcs_lib, monkeypatch, fuse)
             assert b.slab_counts()["owned_cells"] == a.n_cells
             # owned-only transfers (bcs_upload_owned / bcs_download_owned): this rank owns everything, so they move everything;
             # an upload of positions makes the next step refresh the halo first - with the same state the run must not change
+            import torch
             for w in (capi.PARTICLE_POS, capi.PARTICLE_VEL, capi.PARTICLE_FRC):
-                got = b.download_owned(w)
+                got = b.download_owned(w)   # pageable arrays: host-side gather + staging buffer
                 assert all(np.array_equal(g, f) for g, f in zip(got, b.download(w)))
-                b.upload_owned(w, *got)
+                # pinned arrays: the kernels read / write the host arrays in place
+                pinned = tuple(torch.zeros(b.n_particles, dtype=torch.float32).pin_memory().numpy() for _ in range(3))
+                b.download_owned(w, out=pinned)
+                assert all(np.array_equal(g, f) for g, f in zip(got, pinned))
+                b.upload_owned(w, *(pinned if w != capi.PARTICLE_VEL else got))
+                b.synchronize()   # a pinned upload is asynchronous: the arrays must stay untouched until the stream has read them
                 a.upload(w, *got)
             a.step(12)
             b.step(12)
