@@ -994,7 +994,7 @@ static int create_impl(const bcs_scene* scene, const bcs_opts* opts, const bcs_s
                     R.keyOf = s->track(dev_alloc<int>(N));
                     R.tmp = s->track(dev_alloc<int2>(N));
                     R.irregular = s->track(dev_alloc<int>(2));
-                    R.error = s->track(dev_alloc<int>(1));
+                    R.error = s->track(dev_alloc<int>(4));
                     R.nx = s->pg.nx; R.ny = s->pg.ny; R.nyL = rowNyL; R.y0 = rowY0;
                     R.local = (rowNyL != s->pg.ny) ? 1 : 0;
                     {
@@ -1639,10 +1639,15 @@ static void check_device_flags(bcs_sim* s)
 {
     if (s->slab) BCS_REQUIRE(!slab_check_error(s->slab, s->stream), BCS_ERR_STATE, "a halo / migration message overflowed its capacity (raise bcs_slab_opts capacities)");
     if (s->rows.enabled && s->rows.local) {
-        int flag = 0;
-        BCS_CUDA(cudaMemcpyAsync(&flag, s->rows.error, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        int flag[4] = {0, 0, 0, 0};
+        BCS_CUDA(cudaMemcpyAsync(flag, s->rows.error, sizeof flag, cudaMemcpyDeviceToHost, s->stream));
         BCS_CUDA(cudaStreamSynchronize(s->stream));
-        BCS_REQUIRE(!flag, BCS_ERR_STATE, "an active particle left the rank's window of grid rows (raise bcs_slab_opts.halo_width)");
+        if (flag[0]) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "an active particle left the rank's window of grid rows (cell row %d of layer %d; the window is rows %d..%d): "
+                     "raise bcs_slab_opts.halo_width", flag[1], flag[2], s->rows.y0, s->rows.y0 + s->rows.nyL - 1);
+            throw Error{BCS_ERR_STATE, msg};
+        }
     }
     if (s->wall.enabled) {
         int overflow = 0;

@@ -17,7 +17,8 @@ __device__ __forceinline__ int rows_local(const RowsGrid& R, int cy, int cz)
 {
     int y = cy - R.y0;
     if ((unsigned)y >= (unsigned)R.nyL) {
-        *R.error = 1;   // an active particle outside slab + halo: the message capacities / halo width no longer fit the run
+        // an active particle outside slab + halo: the halo width no longer fits the run.  [1], [2]: its cell row / layer
+        if (atomicCAS(R.error, 0, 1) == 0) { R.error[1] = cy; R.error[2] = cz; }
         y = max(0, min(y, R.nyL - 1));
     }
     return cz * R.nyL + y;

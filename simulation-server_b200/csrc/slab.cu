@@ -472,6 +472,29 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
             BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));   // pageable sources: the DMA may outlive the call (capi.cu: dev_upload)
         }
 
+        // BCS_SLAB_NO_COMM=1: profiling aid - one rank of an N-rank decomposition runs alone (no NCCL, no halos)
+        if (init.world > 1 && !getenv("BCS_SLAB_NO_COMM")) {
+            ncclUniqueId id;
+            std::memcpy(&id, init.ncclId, 128);
+            ncclComm_t comm;
+            BCS_NCCL(ncclCommInitRank(&comm, init.world, id, init.rank));
+            s->comm = (void*)comm;
+            // Every message of the exchange has the SAME size on every rank (a send and the receive it pairs with must agree,
+            // and the vertex halo of a face holds a ring of vertices more or less depending on where the plane falls between
+            // two rings): the vertex capacity is the largest any rank needs.
+            int* d = salloc<int>(s, 1);
+            BCS_CUDA(cudaMemcpy(d, &s->capVert, sizeof(int), cudaMemcpyHostToDevice));
+            cudaStream_t q = nullptr;
+            BCS_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            BCS_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+            ncclResult_t r = ncclAllReduce(d, d, 1, ncclInt, ncclMax, comm, q);
+            cudaError_t e = cudaStreamSynchronize(q);
+            cudaStreamDestroy(q);
+            BCS_NCCL(r);
+            BCS_CUDA(e);
+            BCS_CUDA(cudaMemcpy(&s->capVert, d, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+
         // message buffers
         s->msgBytes = sizeof(SlabHeader) + (size_t)s->capMig * sizeof(MigRecord) + (size_t)s->capHalo * sizeof(HaloRecord) +
                       (size_t)s->capVert * sizeof(VertexRecord);
@@ -489,14 +512,6 @@ SlabState* slab_create(const SlabInit& init, const HostScene& hs, const GridDev&
         }
         s->buf.capMig = s->capMig; s->buf.capHalo = s->capHalo;
 
-        // BCS_SLAB_NO_COMM=1: profiling aid - one rank of an N-rank decomposition runs alone (no NCCL, no halos)
-        if (init.world > 1 && !getenv("BCS_SLAB_NO_COMM")) {
-            ncclUniqueId id;
-            std::memcpy(&id, init.ncclId, 128);
-            ncclComm_t comm;
-            BCS_NCCL(ncclCommInitRank(&comm, init.world, id, init.rank));
-            s->comm = (void*)comm;
-        }
         return s;
     } catch (...) {
         slab_destroy(s);
