@@ -187,13 +187,27 @@ def time_oracle(args, steps: int, warmup: int):
     sc, st, info = workloads.by_name(args.workload, args.particles)
     sim = capi.Sim(sc, semantics=semantics_of(args, capi), lib=lib, prefix="orc_")
     sim.upload_state(st)
-    sim.step(warmup)
+    # bounded: the CPU step costs ~0.27 s per million particles, so a long `--steps K` is cut after `budget_s` of timed work
+    # (the per-step cost does not drift over a few hundred steps; the line reports how many steps were timed)
+    budget_s = float(os.environ.get("BCS_REF_BUDGET_S", "150"))
     t0 = time.perf_counter()
-    sim.step(steps)
+    for w in range(warmup):
+        sim.step(1)
+        if w >= 2 and time.perf_counter() - t0 > 0.2 * budget_s:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps:
+        sim.step(1)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
     n = sim.n_particles
     sim.close()
-    return n * steps / dt, dt / steps * 1e3, cores, n, info
+    info = dict(info)
+    info["steps_timed"] = done
+    return n * done / dt, dt / done * 1e3, cores, n, info
 
 
 def run_reference_arm(args):
@@ -210,7 +224,7 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"the whole {info['workload']} workload ({n} particles), {args.steps} steps after {args.warmup} warm-up; "
+                         "sample": f"the whole {info['workload']} workload ({n} particles), {info['steps_timed']} steps after warm-up; "
                                    f"upstream has no CPU path, this is the host-core port under oracle/ (OpenMP, {cores} threads)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
